@@ -1,0 +1,99 @@
+"""ctypes binding of ``include/clipdb.h`` (the C-ABI shared library).
+
+There is no fallback: if ``libclipdb_b200.so`` is missing, or a call returns a
+non-zero code, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import (POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint32,
+                    c_void_p)
+
+from . import build as _build
+
+OK = 0
+ERR_NAMES = {1: "INVALID", 2: "CUDA", 3: "NOMEM", 4: "STATE", 5: "UNSUPPORTED"}
+METRIC_COSINE = 0
+METRIC_L2 = 1
+BLEND_POSITIVE_ZERO_NORM = 1
+BLEND_NEGATIVE_ZERO_NORM = 2
+ABI_VERSION = 1
+
+# every symbol include/clipdb.h declares: (name, restype, argtypes)
+_F = POINTER(c_float)
+_I64 = POINTER(c_int64)
+_I32 = POINTER(c_int32)
+_U32 = POINTER(c_uint32)
+_D = POINTER(c_double)
+_CTX = c_void_p
+
+SIGNATURES = [
+    ("clipdb_abi_version", c_int, []),
+    ("clipdb_create", c_int, [c_int, POINTER(_CTX)]),
+    ("clipdb_destroy", None, [_CTX]),
+    ("clipdb_last_error", c_char_p, [_CTX]),
+    ("clipdb_set_stream", c_int, [_CTX, c_void_p]),
+    ("clipdb_synchronize", c_int, [_CTX]),
+    ("clipdb_set_option", c_int, [_CTX, c_char_p, c_int64]),
+    ("clipdb_get_option", c_int, [_CTX, c_char_p, _I64]),
+    ("clipdb_launch_count", c_int64, [_CTX]),
+    ("clipdb_load_rows", c_int, [_CTX, c_void_p, c_void_p, c_int64, c_int32]),
+    ("clipdb_append_rows", c_int, [_CTX, c_void_p, c_void_p, c_int64]),
+    ("clipdb_update_row", c_int, [_CTX, c_int64, c_void_p]),
+    ("clipdb_attach_rows", c_int, [_CTX, c_void_p, c_void_p, c_int64, c_int32, c_int64]),
+    ("clipdb_num_rows", c_int64, [_CTX]),
+    ("clipdb_dim", c_int32, [_CTX]),
+    ("clipdb_set_mask", c_int, [_CTX, c_void_p, c_int64]),
+    ("clipdb_clear_mask", c_int, [_CTX]),
+    ("clipdb_blend", c_int, [_CTX, _F, _F, c_double, c_double, _F, _D, c_int32, c_int32, _F, _I32]),
+    ("clipdb_blend_device", c_int, [_CTX, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    ("clipdb_search", c_int, [_CTX, _F, c_int32, c_int32, c_int32, c_int32, _I64, _F, _I32, _I64]),
+    ("clipdb_search_device", c_int, [_CTX, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                     c_void_p, c_void_p, c_void_p, c_void_p]),
+    ("clipdb_blend_search", c_int, [_CTX, _F, _F, c_double, c_double, _F, _D, c_int32, c_int32,
+                                    c_int32, c_int32, _I64, _F, _I32, _I64, _F, _I32]),
+    ("clipdb_merge_device", c_int, [_CTX, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                                    c_void_p, c_void_p, c_void_p]),
+]
+
+_lib = None
+
+
+class ClipdbError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"clipdb error {code} ({ERR_NAMES.get(code, '?')}): {message}")
+        self.code = code
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    """dlopen the in-tree CUDA library and type every entry point."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} is missing: the CUDA extension is not built and there is no CPU fallback. "
+            "Run `python -m clip_database_b200.build` (or __graft_entry__.build()).")
+    L = ctypes.CDLL(path)
+    for name, restype, argtypes in SIGNATURES:
+        fn = getattr(L, name)  # AttributeError = symbol not exported
+        fn.restype = restype
+        fn.argtypes = argtypes
+    got = L.clipdb_abi_version()
+    if got != ABI_VERSION:
+        raise RuntimeError(f"{path}: ABI version {got}, binding expects {ABI_VERSION}; rebuild")
+    _lib = L
+    return L
+
+
+def check(ctx, rc: int) -> None:
+    if rc != OK:
+        msg = load().clipdb_last_error(ctx)
+        raise ClipdbError(rc, msg.decode("utf-8", "replace") if msg else "")

@@ -1,0 +1,878 @@
+// clipdb.cu — the C ABI declared in include/clipdb.h (host orchestration).
+//
+// One context = one GPU's resident float32 row store + workspaces + a stream.
+// The search entry points replace the statement the reference executes at
+// image_database.py:1564-1583; clipdb_blend replaces the numpy arithmetic at
+// image_database.py:1378-1398 / 545-604.  No CPU fallback anywhere: a missing
+// device or a failed launch is an error code.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "../../include/clipdb.h"
+#include "blend.cuh"
+#include "merge.cuh"
+#include "scan_topk.cuh"
+
+using namespace clipdb;
+
+namespace {
+
+constexpr int ABI_VERSION = 1;
+constexpr int FUSED_K_MAX = 128;        // largest k served by the register-resident lists
+constexpr int MERGE_SHARD_MAX_KEYS = 16384;
+
+struct Buffer {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace
+
+struct clipdb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::string err;
+    int64_t launches = 0;
+
+    // resident store
+    float *rows = nullptr;
+    int64_t *rowids = nullptr;
+    bool owns_rows = false;
+    int64_t n = 0, cap = 0;
+    int32_t dim = 0, ld = 0;
+    int64_t rowid_base = 0;
+    uint32_t *mask = nullptr;
+    int64_t mask_words = 0;
+
+    // workspaces (grown on demand)
+    Buffer cand_a, cand_b, nan_ctr, all_keys_a, all_keys_b, cub_tmp;
+    Buffer d_query, d_out_rowids, d_out_dist, d_out_n, d_out_nan;
+    Buffer d_blend_in, d_blend_flags;
+    Buffer pinned;      // host staging (inputs, then results)
+    Buffer pinned_aux;  // host staging for the blended query read-back
+
+    // options
+    int64_t scan_variant = 0;  // 0 auto (TMA ring when dim == 1152), 1 TMA ring, 2 direct loads
+    int64_t scan_ctas = 0;     // 0 = one per SM (TMA) / ldg_ctas_per_sm per SM (direct)
+    int64_t ldg_ctas_per_sm = 4;
+    int64_t evict_first = 1;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int fail(clipdb_ctx *c, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define CU_TRY(c, expr)                                                                     \
+    do {                                                                                    \
+        cudaError_t e__ = (expr);                                                           \
+        if (e__ != cudaSuccess)                                                             \
+            return fail((c), e__ == cudaErrorMemoryAllocation ? CLIPDB_ERR_NOMEM            \
+                                                              : CLIPDB_ERR_CUDA,            \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__,  \
+                        __LINE__);                                                          \
+    } while (0)
+
+#define RC_TRY(expr)                   \
+    do {                               \
+        int rc__ = (expr);             \
+        if (rc__ != CLIPDB_OK) return rc__; \
+    } while (0)
+
+int ensure_device(clipdb_ctx *c, Buffer &b, size_t bytes) {
+    if (b.bytes >= bytes && b.p) return CLIPDB_OK;
+    if (b.p) {
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        CU_TRY(c, cudaFree(b.p));
+        b.p = nullptr;
+        b.bytes = 0;
+    }
+    size_t want = bytes < 256 ? 256 : bytes;
+    CU_TRY(c, cudaMalloc(&b.p, want));
+    b.bytes = want;
+    return CLIPDB_OK;
+}
+
+int ensure_pinned(clipdb_ctx *c, size_t bytes) {
+    Buffer &b = c->pinned;
+    if (b.bytes >= bytes && b.p) return CLIPDB_OK;
+    if (b.p) {
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        CU_TRY(c, cudaFreeHost(b.p));
+        b.p = nullptr;
+        b.bytes = 0;
+    }
+    size_t want = bytes < 65536 ? 65536 : bytes;
+    CU_TRY(c, cudaMallocHost(&b.p, want));
+    b.bytes = want;
+    return CLIPDB_OK;
+}
+
+void free_buffer(Buffer &b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+}
+
+bool is_device_pointer(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+void release_store(clipdb_ctx *c) {
+    if (c->owns_rows) {
+        if (c->rows) cudaFree(c->rows);
+        if (c->rowids) cudaFree(c->rowids);
+    }
+    c->rows = nullptr;
+    c->rowids = nullptr;
+    c->owns_rows = false;
+    c->n = c->cap = 0;
+    c->dim = c->ld = 0;
+    c->rowid_base = 0;
+    if (c->mask) cudaFree(c->mask);
+    c->mask = nullptr;
+    c->mask_words = 0;
+}
+
+// copy `m` rows of `dim` floats (host or device) into the store at row `at`
+int copy_rows_in(clipdb_ctx *c, const float *src, const int64_t *src_ids, int64_t at, int64_t m) {
+    if (m == 0) return CLIPDB_OK;
+    float *dst = c->rows + at * c->ld;
+    if (c->ld == c->dim) {
+        CU_TRY(c, cudaMemcpyAsync(dst, src, static_cast<size_t>(m) * c->dim * sizeof(float),
+                                  cudaMemcpyDefault, c->stream));
+    } else {
+        CU_TRY(c, cudaMemsetAsync(dst, 0, static_cast<size_t>(m) * c->ld * sizeof(float), c->stream));
+        CU_TRY(c, cudaMemcpy2DAsync(dst, c->ld * sizeof(float), src, c->dim * sizeof(float),
+                                    c->dim * sizeof(float), static_cast<size_t>(m),
+                                    cudaMemcpyDefault, c->stream));
+    }
+    if (c->rowids) {
+        if (!src_ids) return fail(c, CLIPDB_ERR_INVALID, "store has explicit rowids; rowids required");
+        CU_TRY(c, cudaMemcpyAsync(c->rowids + at, src_ids, static_cast<size_t>(m) * sizeof(int64_t),
+                                  cudaMemcpyDefault, c->stream));
+    }
+    CU_TRY(c, cudaStreamSynchronize(c->stream));  // caller's buffer may be freed on return
+    return CLIPDB_OK;
+}
+
+int alloc_store(clipdb_ctx *c, int64_t cap, int32_t dim, bool with_ids) {
+    release_store(c);
+    c->dim = dim;
+    c->ld = (dim + 3) & ~3;
+    c->cap = cap > 0 ? cap : 1;
+    c->owns_rows = true;
+    CU_TRY(c, cudaMalloc(reinterpret_cast<void **>(&c->rows),
+                         static_cast<size_t>(c->cap) * c->ld * sizeof(float)));
+    if (with_ids)
+        CU_TRY(c, cudaMalloc(reinterpret_cast<void **>(&c->rowids),
+                             static_cast<size_t>(c->cap) * sizeof(int64_t)));
+    return CLIPDB_OK;
+}
+
+// ---- kernel dispatch ------------------------------------------------------------
+
+template <int KPL, int METRIC, bool ALL>
+int launch_scan_tma(clipdb_ctx *c, const ScanArgs &a, int grid) {
+    auto kern = scan_tma_kernel<KPL, METRIC, ALL>;
+    static thread_local int configured_device = -1;  // attribute is per device & per instantiation
+    if (configured_device != c->device) {
+        CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       SCAN_SMEM_BYTES));
+        configured_device = c->device;
+    }
+    kern<<<grid, SCAN_THREADS, SCAN_SMEM_BYTES, c->stream>>>(a);
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    return CLIPDB_OK;
+}
+
+template <int DIM_T, int KPL, int METRIC, bool ALL>
+int launch_scan_ldg(clipdb_ctx *c, const ScanArgs &a, int grid) {
+    auto kern = scan_ldg_kernel<DIM_T, KPL, METRIC, ALL>;
+    const size_t smem = static_cast<size_t>(next_pow2(LDG_WARPS * 32 * KPL)) * sizeof(uint64_t) +
+                        static_cast<size_t>(a.ld) * sizeof(float);
+    if (smem > 48 * 1024) {
+        static thread_local int configured_device = -1;
+        static thread_local size_t configured_bytes = 0;
+        if (configured_device != c->device || configured_bytes < smem) {
+            CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem)));
+            configured_device = c->device;
+            configured_bytes = smem;
+        }
+    }
+    kern<<<grid, LDG_THREADS, smem, c->stream>>>(a);
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    return CLIPDB_OK;
+}
+
+template <int KPL, bool ALL>
+int launch_scan_metric(clipdb_ctx *c, const ScanArgs &a, int metric, bool tma, int grid) {
+    if (tma) {
+        return metric == CLIPDB_METRIC_COSINE ? launch_scan_tma<KPL, METRIC_COSINE, ALL>(c, a, grid)
+                                              : launch_scan_tma<KPL, METRIC_L2, ALL>(c, a, grid);
+    }
+    if (a.dim == SCAN_DIM) {
+        return metric == CLIPDB_METRIC_COSINE
+                   ? launch_scan_ldg<SCAN_DIM, KPL, METRIC_COSINE, ALL>(c, a, grid)
+                   : launch_scan_ldg<SCAN_DIM, KPL, METRIC_L2, ALL>(c, a, grid);
+    }
+    return metric == CLIPDB_METRIC_COSINE ? launch_scan_ldg<0, KPL, METRIC_COSINE, ALL>(c, a, grid)
+                                          : launch_scan_ldg<0, KPL, METRIC_L2, ALL>(c, a, grid);
+}
+
+bool use_tma_variant(const clipdb_ctx *c) {
+    if (c->scan_variant == 2) return false;
+    return c->dim == SCAN_DIM && c->ld == SCAN_DIM;
+}
+
+int scan_grid(const clipdb_ctx *c, bool tma) {
+    if (c->scan_ctas > 0) return static_cast<int>(c->scan_ctas);
+    return tma ? c->sm_count : c->sm_count * static_cast<int>(c->ldg_ctas_per_sm);
+}
+
+// one query: scan + merge tree (k <= FUSED_K_MAX) or scan + radix sort (any k)
+int search_one(clipdb_ctx *c, const float *d_query, int k, int metric, bool use_mask,
+               int64_t *d_out_rowids, float *d_out_dist, int32_t *d_out_n, int64_t *d_out_nan,
+               unsigned long long *d_nan_ctr) {
+    CU_TRY(c, cudaMemsetAsync(d_nan_ctr, 0, sizeof(unsigned long long), c->stream));
+    const int64_t kk = k < c->n ? k : c->n;
+    if (kk <= 0) {
+        CU_TRY(c, cudaMemsetAsync(d_out_n, 0, sizeof(int32_t), c->stream));
+        if (d_out_nan) CU_TRY(c, cudaMemsetAsync(d_out_nan, 0, sizeof(int64_t), c->stream));
+        return CLIPDB_OK;
+    }
+    const bool tma = use_tma_variant(c);
+    const int grid = scan_grid(c, tma);
+
+    ScanArgs a{};
+    a.rows = c->rows;
+    a.query = d_query;
+    a.mask = use_mask ? c->mask : nullptr;
+    a.nan_rows = d_nan_ctr;
+    a.n = c->n;
+    a.dim = c->dim;
+    a.ld = c->ld;
+    a.k = static_cast<int>(kk);
+    a.evict_first = static_cast<int>(c->evict_first);
+
+    DecodeArgs dec{};
+    dec.rowids = c->rowids;
+    dec.rowid_base = c->rowid_base;
+    dec.out_rowids = d_out_rowids;
+    dec.out_dist = d_out_dist;
+    dec.out_n = d_out_n;
+    dec.out_nan = d_out_nan;
+    dec.nan_rows = d_nan_ctr;
+    dec.k = static_cast<int>(kk);
+
+    if (kk <= FUSED_K_MAX) {
+        const int kpl = kk <= 32 ? 1 : (kk <= 64 ? 2 : 4);
+        const int stride = 32 * kpl;
+        a.cand_stride = stride;
+        RC_TRY(ensure_device(c, c->cand_a, static_cast<size_t>(grid) * stride * sizeof(uint64_t)));
+        a.cand = static_cast<uint64_t *>(c->cand_a.p);
+        switch (kpl) {
+            case 1: RC_TRY((launch_scan_metric<1, false>(c, a, metric, tma, grid))); break;
+            case 2: RC_TRY((launch_scan_metric<2, false>(c, a, metric, tma, grid))); break;
+            default: RC_TRY((launch_scan_metric<4, false>(c, a, metric, tma, grid))); break;
+        }
+        // merge tree: lists -> ceil(lists / per_cta) -> ... -> 1 (decoded)
+        const int per_cta = MERGE_KEYS / stride;
+        int lists = grid;
+        const uint64_t *in = static_cast<const uint64_t *>(c->cand_a.p);
+        RC_TRY(ensure_device(c, c->cand_b,
+                             static_cast<size_t>((grid + per_cta - 1) / per_cta) * stride *
+                                 sizeof(uint64_t) * 2));
+        uint64_t *ping = static_cast<uint64_t *>(c->cand_b.p);
+        uint64_t *pong = ping + static_cast<size_t>((grid + per_cta - 1) / per_cta) * stride;
+        for (;;) {
+            const int ctas = (lists + per_cta - 1) / per_cta;
+            const int last = ctas == 1;
+            reduce_lists_kernel<<<ctas, MERGE_THREADS, 0, c->stream>>>(in, lists, stride, per_cta,
+                                                                       ping, dec, last);
+            CU_TRY(c, cudaGetLastError());
+            c->launches++;
+            if (last) break;
+            in = ping;
+            lists = ctas;
+            uint64_t *t = ping;
+            ping = pong;
+            pong = t;
+        }
+        return CLIPDB_OK;
+    }
+
+    // general k: every key to HBM (8 B/row next to the 4*dim B/row just read), radix sort, decode
+    const size_t key_bytes = static_cast<size_t>(c->n) * sizeof(uint64_t);
+    RC_TRY(ensure_device(c, c->all_keys_a, key_bytes));
+    RC_TRY(ensure_device(c, c->all_keys_b, key_bytes));
+    a.all_keys = static_cast<uint64_t *>(c->all_keys_a.p);
+    a.cand_stride = 32;
+    a.k = 0;
+    RC_TRY((launch_scan_metric<1, true>(c, a, metric, tma, grid)));
+    size_t tmp_bytes = 0;
+    CU_TRY(c, cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, a.all_keys,
+                                             static_cast<uint64_t *>(c->all_keys_b.p), c->n, 0, 64,
+                                             c->stream));
+    RC_TRY(ensure_device(c, c->cub_tmp, tmp_bytes));
+    CU_TRY(c, cub::DeviceRadixSort::SortKeys(c->cub_tmp.p, tmp_bytes, a.all_keys,
+                                             static_cast<uint64_t *>(c->all_keys_b.p), c->n, 0, 64,
+                                             c->stream));
+    c->launches++;  // counted once; CUB's passes are library kernels, not ours
+    CU_TRY(c, cudaMemsetAsync(d_out_n, 0, sizeof(int32_t), c->stream));
+    const int threads = 256;
+    const int blocks = static_cast<int>((kk + threads - 1) / threads);
+    decode_sorted_kernel<<<blocks, threads, 0, c->stream>>>(
+        static_cast<const uint64_t *>(c->all_keys_b.p), c->n, dec);
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    return CLIPDB_OK;
+}
+
+int search_device_locked(clipdb_ctx *c, const float *d_queries, int32_t nq, int32_t k,
+                         int32_t metric, int32_t use_mask, int64_t *d_out_rowids,
+                         float *d_out_dist, int32_t *d_out_n, int64_t *d_out_nan) {
+    if (!c->rows || c->dim == 0) return fail(c, CLIPDB_ERR_STATE, "no rows loaded");
+    if (nq < 0 || !d_queries || !d_out_n || (k > 0 && (!d_out_rowids || !d_out_dist)))
+        return fail(c, CLIPDB_ERR_INVALID, "search: null pointer or negative nq");
+    if (metric != CLIPDB_METRIC_COSINE && metric != CLIPDB_METRIC_L2)
+        return fail(c, CLIPDB_ERR_INVALID, "search: unknown metric %d", metric);
+    if (use_mask && !c->mask) return fail(c, CLIPDB_ERR_STATE, "search: use_mask set but no mask installed");
+    if (c->n >= (1ll << 32)) return fail(c, CLIPDB_ERR_UNSUPPORTED, "more than 2^32-1 rows per context");
+    RC_TRY(ensure_device(c, c->nan_ctr, static_cast<size_t>(nq > 0 ? nq : 1) * sizeof(unsigned long long)));
+    const int64_t kcols = k > 0 ? k : 0;
+    for (int32_t q = 0; q < nq; q++) {
+        RC_TRY(search_one(c, d_queries + static_cast<size_t>(q) * c->dim, k, metric, use_mask != 0,
+                          d_out_rowids + q * kcols, d_out_dist + q * kcols, d_out_n + q,
+                          d_out_nan ? d_out_nan + q : nullptr,
+                          static_cast<unsigned long long *>(c->nan_ctr.p) + q));
+    }
+    return CLIPDB_OK;
+}
+
+int blend_device_locked(clipdb_ctx *c, const float *d_e1, const float *d_e2, const float *d_w,
+                        const float *d_negs, const float *d_neg_w, int32_t n_neg, int32_t dim,
+                        int32_t batch, float *d_out, int32_t *d_flags) {
+    if (!d_e1 || !d_out || dim <= 0 || batch < 0 || n_neg < 0)
+        return fail(c, CLIPDB_ERR_INVALID, "blend: bad argument");
+    if (d_e2 && !d_w) return fail(c, CLIPDB_ERR_INVALID, "blend: weights required with a second query");
+    if (n_neg > 0 && (!d_negs || !d_neg_w))
+        return fail(c, CLIPDB_ERR_INVALID, "blend: negatives given without data or weights");
+    if (batch == 0) return CLIPDB_OK;
+    const size_t smem = static_cast<size_t>(dim) * sizeof(float);
+    if (smem > 48 * 1024) return fail(c, CLIPDB_ERR_UNSUPPORTED, "blend: dim %d too large", dim);
+    BlendArgs a{};
+    a.e1 = d_e1;
+    a.e2 = d_e2;
+    a.w = d_w;
+    a.negs = n_neg > 0 ? d_negs : nullptr;
+    a.neg_w = d_neg_w;
+    a.out = d_out;
+    a.flags = d_flags;
+    a.n_neg = n_neg;
+    a.dim = dim;
+    blend_kernel<<<batch, BLEND_THREADS, smem, c->stream>>>(a);
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    return CLIPDB_OK;
+}
+
+// stage the host inputs of one blend into device memory; returns device pointers
+struct BlendStaged {
+    float *e1, *e2, *w, *negs, *neg_w, *out;
+    int32_t *flags;
+};
+
+int stage_blend(clipdb_ctx *c, const float *e1, const float *e2, double w0, double w1,
+                const float *negs, const double *neg_w, int32_t n_neg, int32_t dim,
+                BlendStaged *st) {
+    if (!e1 || dim <= 0 || n_neg < 0 || (n_neg > 0 && (!negs || !neg_w)))
+        return fail(c, CLIPDB_ERR_INVALID, "blend: bad argument");
+    // float layout: e1[dim] e2[dim] w[2] neg_w[n_neg] negs[n_neg*dim] | out[dim]
+    const size_t n_in = static_cast<size_t>(dim) * 2 + 2 + n_neg + static_cast<size_t>(n_neg) * dim;
+    const size_t n_in_pad = (n_in + 3) & ~static_cast<size_t>(3);
+    RC_TRY(ensure_pinned(c, (n_in_pad + dim) * sizeof(float) + 64));
+    RC_TRY(ensure_device(c, c->d_blend_in, (n_in_pad + dim) * sizeof(float)));
+    RC_TRY(ensure_device(c, c->d_blend_flags, sizeof(int32_t)));
+    float *h = static_cast<float *>(c->pinned.p);
+    memcpy(h, e1, dim * sizeof(float));
+    if (e2) memcpy(h + dim, e2, dim * sizeof(float));
+    else memset(h + dim, 0, dim * sizeof(float));
+    // weight normalisation exactly as image_database.py:1379-1383 (Python floats = doubles),
+    // then the weak-scalar cast to float32 numpy applies when multiplying a float32 array
+    double total = w0 + w1;
+    if (total == 0.0) {
+        w0 = 0.5;
+        w1 = 0.5;
+        total = 1.0;
+    }
+    h[2 * dim + 0] = static_cast<float>(w0 / total);
+    h[2 * dim + 1] = static_cast<float>(w1 / total);
+    for (int j = 0; j < n_neg; j++) h[2 * dim + 2 + j] = static_cast<float>(neg_w[j]);
+    if (n_neg > 0) memcpy(h + 2 * dim + 2 + n_neg, negs, static_cast<size_t>(n_neg) * dim * sizeof(float));
+    float *d = static_cast<float *>(c->d_blend_in.p);
+    CU_TRY(c, cudaMemcpyAsync(d, h, n_in * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    st->e1 = d;
+    st->e2 = e2 ? d + dim : nullptr;
+    st->w = d + 2 * dim;
+    st->neg_w = d + 2 * dim + 2;
+    st->negs = d + 2 * dim + 2 + n_neg;
+    st->out = d + n_in_pad;
+    st->flags = static_cast<int32_t *>(c->d_blend_flags.p);
+    return CLIPDB_OK;
+}
+
+}  // namespace
+
+// ================================ C ABI ==========================================
+
+extern "C" {
+
+int clipdb_abi_version(void) { return ABI_VERSION; }
+
+int clipdb_create(int device, clipdb_ctx **out) {
+    if (!out) return CLIPDB_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return CLIPDB_ERR_CUDA;  // no CPU fallback
+    }
+    if (device < 0 || device >= count) return CLIPDB_ERR_INVALID;
+    clipdb_ctx *c = new (std::nothrow) clipdb_ctx();
+    if (!c) return CLIPDB_ERR_NOMEM;
+    c->device = device;
+    DeviceGuard g(device);
+    cudaDeviceProp prop;
+    if (!g.ok || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        delete c;
+        return CLIPDB_ERR_CUDA;
+    }
+    if (prop.major < 10) {
+        cudaStreamDestroy(c->own_stream);
+        delete c;
+        return CLIPDB_ERR_UNSUPPORTED;  // sm_100a code only
+    }
+    c->sm_count = prop.multiProcessorCount;
+    c->stream = c->own_stream;
+    *out = c;
+    return CLIPDB_OK;
+}
+
+void clipdb_destroy(clipdb_ctx *c) {
+    if (!c) return;
+    {
+        DeviceGuard g(c->device);
+        cudaStreamSynchronize(c->stream);
+        release_store(c);
+        Buffer *bufs[] = {&c->cand_a, &c->cand_b, &c->nan_ctr, &c->all_keys_a, &c->all_keys_b,
+                          &c->cub_tmp, &c->d_query, &c->d_out_rowids, &c->d_out_dist, &c->d_out_n,
+                          &c->d_out_nan, &c->d_blend_in, &c->d_blend_flags};
+        for (Buffer *b : bufs) free_buffer(*b);
+        if (c->pinned.p) cudaFreeHost(c->pinned.p);
+        if (c->pinned_aux.p) cudaFreeHost(c->pinned_aux.p);
+        if (c->own_stream) cudaStreamDestroy(c->own_stream);
+        cudaGetLastError();
+    }
+    delete c;
+}
+
+const char *clipdb_last_error(const clipdb_ctx *c) { return c ? c->err.c_str() : "null context"; }
+
+int clipdb_set_stream(clipdb_ctx *c, void *cuda_stream) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+    return CLIPDB_OK;
+}
+
+int clipdb_synchronize(clipdb_ctx *c) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return CLIPDB_OK;
+}
+
+static int64_t *option_slot(clipdb_ctx *c, const char *name) {
+    if (!name) return nullptr;
+    if (!strcmp(name, "scan_variant")) return &c->scan_variant;
+    if (!strcmp(name, "scan_ctas")) return &c->scan_ctas;
+    if (!strcmp(name, "ldg_ctas_per_sm")) return &c->ldg_ctas_per_sm;
+    if (!strcmp(name, "evict_first")) return &c->evict_first;
+    return nullptr;
+}
+
+int clipdb_set_option(clipdb_ctx *c, const char *name, int64_t value) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    int64_t *slot = option_slot(c, name);
+    if (!slot) return fail(c, CLIPDB_ERR_INVALID, "unknown option '%s'", name ? name : "(null)");
+    if (value < 0 || value > (1 << 20)) return fail(c, CLIPDB_ERR_INVALID, "option '%s' out of range", name);
+    if (slot == &c->ldg_ctas_per_sm && value == 0) value = 1;
+    *slot = value;
+    return CLIPDB_OK;
+}
+
+int clipdb_get_option(clipdb_ctx *c, const char *name, int64_t *value) {
+    if (!c || !value) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (name && !strcmp(name, "sm_count")) {
+        *value = c->sm_count;
+        return CLIPDB_OK;
+    }
+    int64_t *slot = option_slot(c, name);
+    if (!slot) return fail(c, CLIPDB_ERR_INVALID, "unknown option '%s'", name ? name : "(null)");
+    *value = *slot;
+    return CLIPDB_OK;
+}
+
+int64_t clipdb_launch_count(const clipdb_ctx *c) { return c ? c->launches : 0; }
+
+int clipdb_load_rows(clipdb_ctx *c, const float *rows, const int64_t *rowids, int64_t n, int32_t dim) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (n < 0 || dim <= 0 || (n > 0 && !rows)) return fail(c, CLIPDB_ERR_INVALID, "load_rows: bad argument");
+    DeviceGuard g(c->device);
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    RC_TRY(alloc_store(c, n, dim, rowids != nullptr));
+    RC_TRY(copy_rows_in(c, rows, rowids, 0, n));
+    c->n = n;
+    return CLIPDB_OK;
+}
+
+int clipdb_append_rows(clipdb_ctx *c, const float *rows, const int64_t *rowids, int64_t m) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->rows || !c->owns_rows) return fail(c, CLIPDB_ERR_STATE, "append_rows: no owned store (load first)");
+    if (m < 0 || (m > 0 && !rows)) return fail(c, CLIPDB_ERR_INVALID, "append_rows: bad argument");
+    if ((c->rowids != nullptr) != (rowids != nullptr) && m > 0)
+        return fail(c, CLIPDB_ERR_INVALID, "append_rows: rowids must match the store (explicit vs implicit)");
+    DeviceGuard g(c->device);
+    if (c->n + m > c->cap) {
+        int64_t cap = c->cap + c->cap / 2;
+        if (cap < c->n + m) cap = c->n + m;
+        float *nr = nullptr;
+        int64_t *ni = nullptr;
+        CU_TRY(c, cudaMalloc(reinterpret_cast<void **>(&nr), static_cast<size_t>(cap) * c->ld * sizeof(float)));
+        CU_TRY(c, cudaMemcpyAsync(nr, c->rows, static_cast<size_t>(c->n) * c->ld * sizeof(float),
+                                  cudaMemcpyDeviceToDevice, c->stream));
+        if (c->rowids) {
+            CU_TRY(c, cudaMalloc(reinterpret_cast<void **>(&ni), static_cast<size_t>(cap) * sizeof(int64_t)));
+            CU_TRY(c, cudaMemcpyAsync(ni, c->rowids, static_cast<size_t>(c->n) * sizeof(int64_t),
+                                      cudaMemcpyDeviceToDevice, c->stream));
+        }
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->rows);
+        if (c->rowids) cudaFree(c->rowids);
+        c->rows = nr;
+        c->rowids = ni;
+        c->cap = cap;
+    }
+    RC_TRY(copy_rows_in(c, rows, rowids, c->n, m));
+    c->n += m;
+    if (c->mask) {  // a mask sized for the old row count no longer applies
+        cudaFree(c->mask);
+        c->mask = nullptr;
+        c->mask_words = 0;
+    }
+    return CLIPDB_OK;
+}
+
+int clipdb_update_row(clipdb_ctx *c, int64_t position, const float *row) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->rows || !c->owns_rows) return fail(c, CLIPDB_ERR_STATE, "update_row: no owned store");
+    if (position < 0 || position >= c->n || !row) return fail(c, CLIPDB_ERR_INVALID, "update_row: bad argument");
+    DeviceGuard g(c->device);
+    CU_TRY(c, cudaMemcpyAsync(c->rows + position * c->ld, row, c->dim * sizeof(float), cudaMemcpyDefault,
+                              c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return CLIPDB_OK;
+}
+
+int clipdb_attach_rows(clipdb_ctx *c, const float *d_rows, const int64_t *d_rowids, int64_t n,
+                       int32_t dim, int64_t rowid_base) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (n < 0 || dim <= 0 || !d_rows) return fail(c, CLIPDB_ERR_INVALID, "attach_rows: bad argument");
+    if (dim % 4 != 0 || (reinterpret_cast<uintptr_t>(d_rows) & 15))
+        return fail(c, CLIPDB_ERR_INVALID, "attach_rows: dim must be a multiple of 4 and rows 16-byte aligned");
+    DeviceGuard g(c->device);
+    if (!is_device_pointer(d_rows) || (d_rowids && !is_device_pointer(d_rowids)))
+        return fail(c, CLIPDB_ERR_INVALID, "attach_rows: device pointers required");
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    release_store(c);
+    c->rows = const_cast<float *>(d_rows);
+    c->rowids = const_cast<int64_t *>(d_rowids);
+    c->owns_rows = false;
+    c->n = c->cap = n;
+    c->dim = c->ld = dim;
+    c->rowid_base = rowid_base;
+    return CLIPDB_OK;
+}
+
+int64_t clipdb_num_rows(const clipdb_ctx *c) { return c ? c->n : 0; }
+int32_t clipdb_dim(const clipdb_ctx *c) { return c ? c->dim : 0; }
+
+int clipdb_set_mask(clipdb_ctx *c, const uint32_t *words, int64_t n_words) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->rows) return fail(c, CLIPDB_ERR_STATE, "set_mask: no rows loaded");
+    const int64_t need = (c->n + 31) / 32;
+    if (!words || n_words < need) return fail(c, CLIPDB_ERR_INVALID, "set_mask: need %lld words", (long long)need);
+    DeviceGuard g(c->device);
+    if (c->mask_words < need) {
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        if (c->mask) cudaFree(c->mask);
+        c->mask = nullptr;
+        c->mask_words = 0;
+        CU_TRY(c, cudaMalloc(reinterpret_cast<void **>(&c->mask), static_cast<size_t>(need > 0 ? need : 1) * 4));
+        c->mask_words = need;
+    }
+    CU_TRY(c, cudaMemcpyAsync(c->mask, words, static_cast<size_t>(need) * 4, cudaMemcpyDefault, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return CLIPDB_OK;
+}
+
+int clipdb_clear_mask(clipdb_ctx *c) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->mask) cudaFree(c->mask);
+    c->mask = nullptr;
+    c->mask_words = 0;
+    return CLIPDB_OK;
+}
+
+int clipdb_blend_device(clipdb_ctx *c, const float *d_e1, const float *d_e2, const float *d_w,
+                        const float *d_negs, const float *d_neg_w, int32_t n_neg, int32_t dim,
+                        int32_t batch, float *d_out, int32_t *d_out_flags) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    return blend_device_locked(c, d_e1, d_e2, d_w, d_negs, d_neg_w, n_neg, dim, batch, d_out, d_out_flags);
+}
+
+int clipdb_blend(clipdb_ctx *c, const float *e1, const float *e2, double w0, double w1,
+                 const float *negs, const double *neg_w, int32_t n_neg, int32_t dim, float *out,
+                 int32_t *out_flags) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!out) return fail(c, CLIPDB_ERR_INVALID, "blend: out is null");
+    DeviceGuard g(c->device);
+    BlendStaged st;
+    RC_TRY(stage_blend(c, e1, e2, w0, w1, negs, neg_w, n_neg, dim, &st));
+    RC_TRY(blend_device_locked(c, st.e1, st.e2, st.w, st.negs, st.neg_w, n_neg, dim, 1, st.out, st.flags));
+    float *h = static_cast<float *>(c->pinned.p);
+    // results land behind the staged inputs in the pinned buffer
+    const size_t off = static_cast<size_t>(st.out - static_cast<float *>(c->d_blend_in.p));
+    CU_TRY(c, cudaMemcpyAsync(h + off, st.out, dim * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    int32_t *hflags = reinterpret_cast<int32_t *>(h + off + dim);
+    CU_TRY(c, cudaMemcpyAsync(hflags, st.flags, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    memcpy(out, h + off, dim * sizeof(float));
+    if (out_flags) *out_flags = *hflags;
+    return CLIPDB_OK;
+}
+
+int clipdb_search_device(clipdb_ctx *c, const float *d_queries, int32_t nq, int32_t k, int32_t metric,
+                         int32_t use_mask, int64_t *d_out_rowids, float *d_out_dist,
+                         int32_t *d_out_n, int64_t *d_out_nan) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    return search_device_locked(c, d_queries, nq, k, metric, use_mask, d_out_rowids, d_out_dist,
+                                d_out_n, d_out_nan);
+}
+
+// shared tail of the host search entry points: results D2H + unpack
+static int fetch_results(clipdb_ctx *c, int32_t nq, int64_t kcols, int64_t *out_rowids,
+                         float *out_dist, int32_t *out_n, int64_t *out_nan) {
+    const size_t b_ids = static_cast<size_t>(nq) * kcols * sizeof(int64_t);
+    const size_t b_dist = static_cast<size_t>(nq) * kcols * sizeof(float);
+    const size_t b_n = static_cast<size_t>(nq) * sizeof(int32_t);
+    const size_t b_nan = static_cast<size_t>(nq) * sizeof(int64_t);
+    // pinned layout (8-byte aligned pieces first): nan | ids | dist | n
+    RC_TRY(ensure_pinned(c, b_nan + b_ids + b_dist + b_n + 64));
+    uint8_t *h = static_cast<uint8_t *>(c->pinned.p);
+    uint8_t *h_nan = h, *h_ids = h_nan + b_nan, *h_dist = h_ids + b_ids, *h_n = h_dist + b_dist;
+    CU_TRY(c, cudaMemcpyAsync(h_nan, c->d_out_nan.p, b_nan, cudaMemcpyDeviceToHost, c->stream));
+    if (kcols > 0) {
+        CU_TRY(c, cudaMemcpyAsync(h_ids, c->d_out_rowids.p, b_ids, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(c, cudaMemcpyAsync(h_dist, c->d_out_dist.p, b_dist, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU_TRY(c, cudaMemcpyAsync(h_n, c->d_out_n.p, b_n, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    memcpy(out_n, h_n, b_n);
+    if (out_nan) memcpy(out_nan, h_nan, b_nan);
+    for (int32_t q = 0; q < nq; q++) {
+        const int32_t m = reinterpret_cast<int32_t *>(h_n)[q];
+        if (m > 0) {
+            memcpy(out_rowids + q * kcols, h_ids + static_cast<size_t>(q) * kcols * sizeof(int64_t),
+                   static_cast<size_t>(m) * sizeof(int64_t));
+            memcpy(out_dist + q * kcols, h_dist + static_cast<size_t>(q) * kcols * sizeof(float),
+                   static_cast<size_t>(m) * sizeof(float));
+        }
+    }
+    return CLIPDB_OK;
+}
+
+static int ensure_result_buffers(clipdb_ctx *c, int32_t nq, int64_t kcols) {
+    const size_t cells = static_cast<size_t>(nq > 0 ? nq : 1) * (kcols > 0 ? kcols : 1);
+    RC_TRY(ensure_device(c, c->d_out_rowids, cells * sizeof(int64_t)));
+    RC_TRY(ensure_device(c, c->d_out_dist, cells * sizeof(float)));
+    RC_TRY(ensure_device(c, c->d_out_n, static_cast<size_t>(nq > 0 ? nq : 1) * sizeof(int32_t)));
+    RC_TRY(ensure_device(c, c->d_out_nan, static_cast<size_t>(nq > 0 ? nq : 1) * sizeof(int64_t)));
+    return CLIPDB_OK;
+}
+
+int clipdb_search(clipdb_ctx *c, const float *queries, int32_t nq, int32_t k, int32_t metric,
+                  int32_t use_mask, int64_t *out_rowids, float *out_dist, int32_t *out_n,
+                  int64_t *out_nan) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->rows || c->dim == 0) return fail(c, CLIPDB_ERR_STATE, "no rows loaded");
+    if (nq < 0 || !queries || !out_n || (k > 0 && (!out_rowids || !out_dist)))
+        return fail(c, CLIPDB_ERR_INVALID, "search: null pointer or negative nq");
+    if (nq == 0) return CLIPDB_OK;
+    DeviceGuard g(c->device);
+    // effective columns: the caller's arrays are nq x k, ours too
+    const int64_t kcols = k > 0 ? k : 0;
+    const size_t qbytes = static_cast<size_t>(nq) * c->dim * sizeof(float);
+    RC_TRY(ensure_pinned(c, qbytes));
+    RC_TRY(ensure_device(c, c->d_query, qbytes));
+    RC_TRY(ensure_result_buffers(c, nq, kcols));
+    memcpy(c->pinned.p, queries, qbytes);
+    CU_TRY(c, cudaMemcpyAsync(c->d_query.p, c->pinned.p, qbytes, cudaMemcpyHostToDevice, c->stream));
+    // the pinned buffer is reused for results: the H2D above is ordered before them on the stream
+    RC_TRY(search_device_locked(c, static_cast<const float *>(c->d_query.p), nq, k, metric, use_mask,
+                                static_cast<int64_t *>(c->d_out_rowids.p),
+                                static_cast<float *>(c->d_out_dist.p),
+                                static_cast<int32_t *>(c->d_out_n.p),
+                                static_cast<int64_t *>(c->d_out_nan.p)));
+    return fetch_results(c, nq, kcols, out_rowids, out_dist, out_n, out_nan);
+}
+
+int clipdb_blend_search(clipdb_ctx *c, const float *e1, const float *e2, double w0, double w1,
+                        const float *negs, const double *neg_w, int32_t n_neg, int32_t k,
+                        int32_t metric, int32_t use_mask, int64_t *out_rowids, float *out_dist,
+                        int32_t *out_n, int64_t *out_nan, float *out_query, int32_t *out_flags) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->rows || c->dim == 0) return fail(c, CLIPDB_ERR_STATE, "no rows loaded");
+    if (!out_n || (k > 0 && (!out_rowids || !out_dist)))
+        return fail(c, CLIPDB_ERR_INVALID, "blend_search: null output pointer");
+    DeviceGuard g(c->device);
+    const int32_t dim = c->dim;
+    const int64_t kcols = k > 0 ? k : 0;
+    BlendStaged st;
+    RC_TRY(stage_blend(c, e1, e2, w0, w1, negs, neg_w, n_neg, dim, &st));
+    RC_TRY(ensure_result_buffers(c, 1, kcols));
+    RC_TRY(ensure_device(c, c->d_query, static_cast<size_t>(dim) * sizeof(float) + sizeof(int32_t)));
+    float *d_q = static_cast<float *>(c->d_query.p);
+    RC_TRY(blend_device_locked(c, st.e1, st.e2, st.w, st.negs, st.neg_w, n_neg, dim, 1, d_q, st.flags));
+    RC_TRY(search_device_locked(c, d_q, 1, k, metric, use_mask, static_cast<int64_t *>(c->d_out_rowids.p),
+                                static_cast<float *>(c->d_out_dist.p), static_cast<int32_t *>(c->d_out_n.p),
+                                static_cast<int64_t *>(c->d_out_nan.p)));
+    // optional read-back of the blended query and the fallback flags, through their own
+    // pinned area so the result staging below can reuse the main one
+    float *h_aux = nullptr;
+    if (out_query || out_flags) {
+        const size_t aux_bytes = static_cast<size_t>(dim) * sizeof(float) + sizeof(int32_t);
+        if (c->pinned_aux.bytes < aux_bytes) {
+            if (c->pinned_aux.p) {
+                CU_TRY(c, cudaStreamSynchronize(c->stream));
+                CU_TRY(c, cudaFreeHost(c->pinned_aux.p));
+                c->pinned_aux.p = nullptr;
+                c->pinned_aux.bytes = 0;
+            }
+            CU_TRY(c, cudaMallocHost(&c->pinned_aux.p, aux_bytes));
+            c->pinned_aux.bytes = aux_bytes;
+        }
+        h_aux = static_cast<float *>(c->pinned_aux.p);
+        CU_TRY(c, cudaMemcpyAsync(h_aux, d_q, dim * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(c, cudaMemcpyAsync(h_aux + dim, st.flags, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    }
+    RC_TRY(fetch_results(c, 1, kcols, out_rowids, out_dist, out_n, out_nan));  // syncs the stream
+    if (out_query) memcpy(out_query, h_aux, dim * sizeof(float));
+    if (out_flags) memcpy(out_flags, h_aux + dim, sizeof(int32_t));
+    return CLIPDB_OK;
+}
+
+int clipdb_merge_device(clipdb_ctx *c, const float *d_dist, const int64_t *d_rowids,
+                        const int32_t *d_counts, int32_t lists, int32_t k, float *d_out_dist,
+                        int64_t *d_out_rowids, int32_t *d_out_n) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!d_dist || !d_rowids || !d_counts || !d_out_dist || !d_out_rowids || !d_out_n || lists <= 0 || k < 0)
+        return fail(c, CLIPDB_ERR_INVALID, "merge: bad argument");
+    DeviceGuard g(c->device);
+    if (k == 0) {
+        CU_TRY(c, cudaMemsetAsync(d_out_n, 0, sizeof(int32_t), c->stream));
+        return CLIPDB_OK;
+    }
+    const int64_t total = static_cast<int64_t>(lists) * k;
+    if (total > MERGE_SHARD_MAX_KEYS)
+        return fail(c, CLIPDB_ERR_UNSUPPORTED, "merge: lists*k = %lld exceeds %d", (long long)total,
+                    MERGE_SHARD_MAX_KEYS);
+    const size_t smem = static_cast<size_t>(next_pow2(static_cast<int>(total))) * sizeof(uint64_t);
+    if (smem > 48 * 1024) {
+        static thread_local int configured_device = -1;
+        if (configured_device != c->device) {
+            CU_TRY(c, cudaFuncSetAttribute(merge_shards_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           MERGE_SHARD_MAX_KEYS * static_cast<int>(sizeof(uint64_t))));
+            configured_device = c->device;
+        }
+    }
+    merge_shards_kernel<<<1, MERGE_THREADS, smem, c->stream>>>(d_dist, d_rowids, d_counts, lists, k,
+                                                               d_out_dist, d_out_rowids, d_out_n);
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    return CLIPDB_OK;
+}
+
+}  // extern "C"

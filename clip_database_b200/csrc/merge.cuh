@@ -1,0 +1,114 @@
+// merge.cuh — reduce per-CTA candidate lists to the final top-k and decode it.
+//
+// Integer work only: the keys (common.cuh) already encode SQLite's
+// (distance, scan sequence) order (image_database.py:1572-1573), so merging is
+// a sort of 64-bit keys and the result is bit-exact whatever the list layout.
+#pragma once
+
+#include "common.cuh"
+
+namespace clipdb {
+
+constexpr int MERGE_KEYS = 2048;   // keys one CTA sorts in shared memory (16 KB)
+constexpr int MERGE_THREADS = 1024;
+
+struct DecodeArgs {
+    const int64_t *rowids;               // nullable: rowid = rowid_base + position
+    int64_t rowid_base;
+    int64_t *out_rowids;                 // [k]
+    float *out_dist;                     // [k]
+    int32_t *out_n;                      // [1]
+    int64_t *out_nan;                    // nullable [1]
+    const unsigned long long *nan_rows;  // counter the scan accumulated
+    int k;
+};
+
+__device__ __forceinline__ void decode_one(const DecodeArgs &d, int i, uint64_t key) {
+    const uint32_t pos = static_cast<uint32_t>(key & 0xFFFFFFFFull);
+    d.out_dist[i] = orderable_f32(static_cast<uint32_t>(key >> 32));
+    d.out_rowids[i] = d.rowids ? d.rowids[pos] : d.rowid_base + static_cast<int64_t>(pos);
+}
+
+// One level of the reduction tree: CTA b merges lists [b*lists_per_cta, ...) of
+// `stride` ascending keys each into one ascending list of `stride` keys.  When
+// do_decode != 0 (single CTA, last level) the first k keys are decoded into the
+// caller's result arrays instead.
+__global__ void __launch_bounds__(MERGE_THREADS) reduce_lists_kernel(
+    const uint64_t *__restrict__ in, int n_lists, int stride, int lists_per_cta,
+    uint64_t *__restrict__ out, DecodeArgs dec, int do_decode) {
+    __shared__ uint64_t s[MERGE_KEYS];
+    const int tid = threadIdx.x;
+    const int l0 = blockIdx.x * lists_per_cta;
+    int nl = n_lists - l0;
+    if (nl > lists_per_cta) nl = lists_per_cta;
+    const int total = nl * stride;
+    const int padded = next_pow2(total);
+    const uint64_t *src = in + static_cast<size_t>(l0) * stride;
+    for (int i = tid; i < padded; i += MERGE_THREADS) s[i] = i < total ? src[i] : KEY_EMPTY;
+    block_bitonic_sort(s, padded, tid, MERGE_THREADS);
+    if (!do_decode) {
+        uint64_t *dst = out + static_cast<size_t>(blockIdx.x) * stride;
+        for (int i = tid; i < stride; i += MERGE_THREADS) dst[i] = i < padded ? s[i] : KEY_EMPTY;
+        return;
+    }
+    int found = 0;
+    for (int base = 0; base < dec.k; base += MERGE_THREADS) {
+        const int i = base + tid;
+        const bool valid = i < dec.k && i < padded && s[i] != KEY_EMPTY;
+        if (valid) decode_one(dec, i, s[i]);
+        found += __syncthreads_count(valid);
+    }
+    if (tid == 0) {
+        *dec.out_n = found;
+        if (dec.out_nan) *dec.out_nan = static_cast<int64_t>(*dec.nan_rows);
+    }
+}
+
+// General-k path: `keys` is the fully sorted key vector (n entries); decode the
+// first k.  out_n must be zeroed beforehand.
+__global__ void decode_sorted_kernel(const uint64_t *__restrict__ keys, long long n, DecodeArgs dec) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const bool valid = i < dec.k && i < n && keys[i] != KEY_EMPTY;
+    if (valid) decode_one(dec, static_cast<int>(i), keys[i]);
+    const unsigned votes = __ballot_sync(FULL_MASK, valid);
+    if ((threadIdx.x & 31) == 0 && votes) atomicAdd(dec.out_n, __popc(votes));
+    if (i == 0 && dec.out_nan) *dec.out_nan = static_cast<int64_t>(*dec.nan_rows);
+}
+
+// Shard merge (multi-GPU): `lists` sorted result lists of k (distance, rowid)
+// pairs, shard order = rowid order.  Key = (distance, list, position), which is
+// (distance, rowid) because shards are contiguous rowid ranges.
+__global__ void __launch_bounds__(MERGE_THREADS) merge_shards_kernel(
+    const float *__restrict__ dist, const int64_t *__restrict__ rowids,
+    const int32_t *__restrict__ counts, int lists, int k, float *__restrict__ out_dist,
+    int64_t *__restrict__ out_rowids, int32_t *__restrict__ out_n) {
+    extern __shared__ __align__(16) uint8_t merge_smem[];
+    uint64_t *s = reinterpret_cast<uint64_t *>(merge_smem);
+    const int tid = threadIdx.x;
+    const int total = lists * k;
+    const int padded = next_pow2(total);
+    for (int i = tid; i < padded; i += MERGE_THREADS) {
+        uint64_t key = KEY_EMPTY;
+        if (i < total) {
+            const int l = i / k, p = i - l * k;
+            const float d = dist[i];
+            if (p < counts[l] && d == d) key = make_key(d, static_cast<uint32_t>(i));
+        }
+        s[i] = key;
+    }
+    block_bitonic_sort(s, padded, tid, MERGE_THREADS);
+    int found = 0;
+    for (int base = 0; base < k; base += MERGE_THREADS) {
+        const int i = base + tid;
+        const bool valid = i < k && i < padded && s[i] != KEY_EMPTY;
+        if (valid) {
+            const uint32_t src = static_cast<uint32_t>(s[i] & 0xFFFFFFFFull);
+            out_dist[i] = dist[src];
+            out_rowids[i] = rowids[src];
+        }
+        found += __syncthreads_count(valid);
+    }
+    if (tid == 0) *out_n = found;
+}
+
+}  // namespace clipdb

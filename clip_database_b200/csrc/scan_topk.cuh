@@ -1,0 +1,363 @@
+// scan_topk.cuh — K1 + K2: the distance scan fused with top-k selection.
+//
+// Replaces, for one query, what SQLite + sqlite-vec do per search
+// (image_database.py:1564-1574, executed at :1582): score EVERY stored
+// float32 row against the query with vec_distance_cosine and keep the k
+// smallest (distance, scan sequence) pairs.  The distance vector is never
+// written to HBM: each warp keeps a k-entry candidate list in registers, each
+// CTA emits one sorted list, and merge.cuh reduces the lists to the answer.
+//
+// Roofline: HBM.  Algorithmic bytes per query = n * dim * 4 (the row store is
+// read exactly once); ~1 flop per byte.  Two variants of the same arithmetic:
+//   scan_tma_kernel  dim == 1152 (the reference's only width).  Persistent,
+//                    one CTA per SM.  One producer thread streams 8-row tiles
+//                    (36,864 B, one contiguous span) global->shared with
+//                    cp.async.bulk (TMA engine, SASS UBLKCP) into a 6-stage
+//                    mbarrier ring; 16 consumer warps (two groups of 8 that
+//                    alternate tiles) read conflict-free LDS.128, reduce with
+//                    warp shuffles and maintain the candidate lists.
+//   scan_ldg_kernel  any dim (multiple of 4, padded by the loader).  Each warp
+//                    grid-strides over rows with 128-bit streaming loads
+//                    (ld.global.nc.L1::no_allocate), query staged in shared.
+#pragma once
+
+#include "common.cuh"
+
+namespace clipdb {
+
+constexpr int METRIC_COSINE = 0;
+constexpr int METRIC_L2 = 1;
+
+constexpr int SCAN_DIM = 1152;  // SigLIP 2 SO400M width, `embedding float[1152]` (idb:290-294)
+constexpr int SCAN_CHUNKS = SCAN_DIM / 128;  // float4 chunks per lane per row = 9
+constexpr int SCAN_ROW_BYTES = SCAN_DIM * 4;  // 4608 = 36 x 128 B
+constexpr int SCAN_GROUP_WARPS = 8;           // consumer warps per tile (= rows per tile)
+constexpr int SCAN_GROUPS = 2;                // consumer groups alternating tiles
+constexpr int SCAN_CONSUMER_WARPS = SCAN_GROUP_WARPS * SCAN_GROUPS;
+constexpr int SCAN_TILE_ROWS = SCAN_GROUP_WARPS;
+constexpr int SCAN_STAGES = 6;
+constexpr int SCAN_STAGE_BYTES = SCAN_TILE_ROWS * SCAN_ROW_BYTES;  // 36,864
+constexpr int SCAN_THREADS = (SCAN_CONSUMER_WARPS + 1) * 32;       // + producer warp
+constexpr int SCAN_SMEM_HEADER = 128;                              // barriers
+constexpr int SCAN_SMEM_BYTES = SCAN_SMEM_HEADER + SCAN_STAGES * SCAN_STAGE_BYTES;
+
+constexpr int LDG_WARPS = 8;
+constexpr int LDG_THREADS = LDG_WARPS * 32;
+
+struct ScanArgs {
+    const float *rows;             // [n][ld] float32, scan order
+    const float *query;            // [dim]
+    const uint32_t *mask;          // nullable admission bitset
+    uint64_t *cand;                // [gridDim.x][cand_stride], each ascending
+    unsigned long long *nan_rows;  // += admitted rows whose distance is NaN
+    uint64_t *all_keys;            // WRITE_ALL: [n] keys (KEY_EMPTY = not admitted / NaN)
+    long long n;
+    int dim;
+    int ld;           // row stride in floats (multiple of 4)
+    int k;            // requested k, <= cand_stride
+    int cand_stride;  // 32 * KPL
+    int evict_first;  // stream rows with an L2 evict-first policy
+};
+
+// ---- per-warp candidate list ---------------------------------------------------
+// 32*KPL slots spread over the lanes' registers, unsorted; `thr` is the largest
+// key held (warp-uniform).  Slots >= k are disabled so the list holds exactly
+// the k best keys seen so far; a new key enters iff key < thr and replaces the
+// current maximum.  Admission is rare (~k/rows-seen), so the common path is one
+// compare.
+template <int KPL>
+struct WarpTopK {
+    uint64_t keys[KPL];
+    uint64_t thr;
+
+    __device__ __forceinline__ void init(int k, int lane) {
+#pragma unroll
+        for (int j = 0; j < KPL; j++) keys[j] = (j * 32 + lane < k) ? KEY_EMPTY : KEY_DISABLED;
+        thr = (k > 0) ? KEY_EMPTY : KEY_DISABLED;
+    }
+
+    // key < thr on entry; key is warp-uniform
+    __device__ __forceinline__ void insert(uint64_t key, int lane) {
+        int slot = -1;
+#pragma unroll
+        for (int j = KPL - 1; j >= 0; j--)
+            if (keys[j] == thr) slot = j;
+        unsigned holders = __ballot_sync(FULL_MASK, slot >= 0);
+        int owner = __ffs(holders) - 1;
+        if (lane == owner) {
+#pragma unroll
+            for (int j = 0; j < KPL; j++)
+                if (j == slot) keys[j] = key;
+        }
+        uint64_t m = keys[0];
+#pragma unroll
+        for (int j = 1; j < KPL; j++) m = umax64(m, keys[j]);
+        thr = warp_max_u64(m);
+    }
+
+    __device__ __forceinline__ void dump(uint64_t *dst, int lane) const {
+#pragma unroll
+        for (int j = 0; j < KPL; j++)
+            dst[j * 32 + lane] = (keys[j] == KEY_DISABLED) ? KEY_EMPTY : keys[j];
+    }
+};
+
+// The reference arithmetic once the three float32 sums exist (oracle_ref.c):
+// roots, product, divide and subtract in double, narrowed to float32.
+template <int METRIC>
+__device__ __forceinline__ float finish_distance(float s0, float s1, double sqrt_b) {
+    if (METRIC == METRIC_COSINE)
+        return static_cast<float>(1.0 - static_cast<double>(s0) /
+                                            (sqrt(static_cast<double>(s1)) * sqrt_b));
+    return static_cast<float>(sqrt(static_cast<double>(s0)));
+}
+
+template <int METRIC>
+__device__ __forceinline__ void accumulate(const float4 v, const float4 q, float (&s0)[4],
+                                           float (&s1)[4]) {
+    if (METRIC == METRIC_COSINE) {
+        s0[0] = fmaf(v.x, q.x, s0[0]);
+        s0[1] = fmaf(v.y, q.y, s0[1]);
+        s0[2] = fmaf(v.z, q.z, s0[2]);
+        s0[3] = fmaf(v.w, q.w, s0[3]);
+        s1[0] = fmaf(v.x, v.x, s1[0]);
+        s1[1] = fmaf(v.y, v.y, s1[1]);
+        s1[2] = fmaf(v.z, v.z, s1[2]);
+        s1[3] = fmaf(v.w, v.w, s1[3]);
+    } else {
+        float dx = v.x - q.x, dy = v.y - q.y, dz = v.z - q.z, dw = v.w - q.w;
+        s0[0] = fmaf(dx, dx, s0[0]);
+        s0[1] = fmaf(dy, dy, s0[1]);
+        s0[2] = fmaf(dz, dz, s0[2]);
+        s0[3] = fmaf(dw, dw, s0[3]);
+    }
+}
+
+// Row sums are complete in every lane: turn them into a key and offer it.
+template <int KPL, int METRIC, bool WRITE_ALL>
+__device__ __forceinline__ void offer_row(float s0, float s1, double sqrt_b, long long pos,
+                                          WarpTopK<KPL> &top, unsigned &nan_rows,
+                                          uint64_t *all_keys, int lane) {
+    float d = finish_distance<METRIC>(s0, s1, sqrt_b);
+    if (d != d) {
+        nan_rows++;
+        if (WRITE_ALL && lane == 0) all_keys[pos] = KEY_EMPTY;
+        return;
+    }
+    uint64_t key = make_key(d, static_cast<uint32_t>(pos));
+    if (WRITE_ALL) {
+        if (lane == 0) all_keys[pos] = key;
+    } else if (key < top.thr) {
+        top.insert(key, lane);
+    }
+}
+
+__device__ __forceinline__ bool row_admitted(const uint32_t *mask, long long pos) {
+    return mask == nullptr || ((__ldg(mask + (pos >> 5)) >> (pos & 31)) & 1u);
+}
+
+// All warps' lists -> one ascending list of cand_stride keys for this CTA.
+// `scratch` holds next_pow2(warps * 32 * KPL) keys.
+template <int KPL>
+__device__ __forceinline__ void emit_cta_list(uint64_t *scratch, int n_lists,
+                                              uint64_t *cand_out, int tid, int nthreads) {
+    const int total = n_lists * 32 * KPL;
+    const int padded = next_pow2(total);
+    for (int i = total + tid; i < padded; i += nthreads) scratch[i] = KEY_EMPTY;
+    block_bitonic_sort(scratch, padded, tid, nthreads);
+    for (int i = tid; i < 32 * KPL; i += nthreads) cand_out[i] = scratch[i];
+}
+
+// ---- TMA-ring variant, dim == 1152 ------------------------------------------------
+template <int KPL, int METRIC, bool WRITE_ALL>
+__global__ void __launch_bounds__(SCAN_THREADS, 1) scan_tma_kernel(const ScanArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem);
+    uint64_t *empty_bar = full_bar + SCAN_STAGES;
+    uint8_t *ring = smem + SCAN_SMEM_HEADER;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+
+    const long long total_tiles = (a.n + SCAN_TILE_ROWS - 1) / SCAN_TILE_ROWS;
+    const long long first = blockIdx.x;
+    const long long step = gridDim.x;
+    const long long my_tiles = first < total_tiles ? (total_tiles - first + step - 1) / step : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < SCAN_STAGES; s++) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], SCAN_GROUP_WARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    WarpTopK<KPL> top;
+    top.init(a.k, lane);
+    unsigned nan_rows = 0;
+
+    if (warp == SCAN_CONSUMER_WARPS) {
+        // ===== producer: one thread feeds the ring =====
+        if (lane == 0) {
+            const uint64_t policy = l2_policy_evict_first();
+            for (long long it = 0; it < my_tiles; it++) {
+                const int s = static_cast<int>(it % SCAN_STAGES);
+                const uint32_t phase = static_cast<uint32_t>((it / SCAN_STAGES) & 1);
+                mbar_wait(&empty_bar[s], phase ^ 1u);
+                const long long row0 = (first + it * step) * SCAN_TILE_ROWS;
+                const long long left = a.n - row0;
+                const uint32_t bytes =
+                    static_cast<uint32_t>((left < SCAN_TILE_ROWS ? left : SCAN_TILE_ROWS) *
+                                          SCAN_ROW_BYTES);
+                mbar_arrive_expect_tx(&full_bar[s], bytes);
+                const float *src = a.rows + row0 * SCAN_DIM;
+                if (a.evict_first)
+                    bulk_copy_g2s_hint(ring + s * SCAN_STAGE_BYTES, src, bytes, &full_bar[s], policy);
+                else
+                    bulk_copy_g2s(ring + s * SCAN_STAGE_BYTES, src, bytes, &full_bar[s]);
+            }
+        }
+    } else {
+        // ===== consumers: group g takes tiles it == g (mod SCAN_GROUPS), warp wi row wi =====
+        const int group = warp / SCAN_GROUP_WARPS;
+        const int wi = warp % SCAN_GROUP_WARPS;
+
+        float4 q[SCAN_CHUNKS];
+        const float4 *q4 = reinterpret_cast<const float4 *>(a.query);
+        float bsum = 0.f;
+#pragma unroll
+        for (int j = 0; j < SCAN_CHUNKS; j++) {
+            q[j] = __ldg(q4 + lane + 32 * j);
+            bsum = fmaf(q[j].x, q[j].x, bsum);
+            bsum = fmaf(q[j].y, q[j].y, bsum);
+            bsum = fmaf(q[j].z, q[j].z, bsum);
+            bsum = fmaf(q[j].w, q[j].w, bsum);
+        }
+        const double sqrt_b = sqrt(static_cast<double>(warp_sum(bsum)));
+
+        for (long long it = group; it < my_tiles; it += SCAN_GROUPS) {
+            const int s = static_cast<int>(it % SCAN_STAGES);
+            const uint32_t phase = static_cast<uint32_t>((it / SCAN_STAGES) & 1);
+            const long long pos = (first + it * step) * SCAN_TILE_ROWS + wi;
+            mbar_wait(&full_bar[s], phase);
+            if (pos < a.n && row_admitted(a.mask, pos)) {
+                const float4 *src =
+                    reinterpret_cast<const float4 *>(ring + s * SCAN_STAGE_BYTES + wi * SCAN_ROW_BYTES);
+                float4 v[SCAN_CHUNKS];
+#pragma unroll
+                for (int j = 0; j < SCAN_CHUNKS; j++) v[j] = src[lane + 32 * j];
+                float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int j = 0; j < SCAN_CHUNKS; j++) accumulate<METRIC>(v[j], q[j], s0, s1);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[s]);  // row is in registers: free the slot
+                float t0 = warp_sum((s0[0] + s0[1]) + (s0[2] + s0[3]));
+                float t1 = (METRIC == METRIC_COSINE) ? warp_sum((s1[0] + s1[1]) + (s1[2] + s1[3])) : 0.f;
+                offer_row<KPL, METRIC, WRITE_ALL>(t0, t1, sqrt_b, pos, top, nan_rows, a.all_keys, lane);
+            } else {
+                if (WRITE_ALL && pos < a.n && lane == 0) a.all_keys[pos] = KEY_EMPTY;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[s]);
+            }
+        }
+    }
+
+    if (nan_rows && lane == 0) atomicAdd(a.nan_rows, static_cast<unsigned long long>(nan_rows));
+    if (WRITE_ALL) return;
+
+    // every issued copy has been consumed (each full barrier was waited on), so
+    // the ring can be reused as sort scratch
+    __syncthreads();
+    uint64_t *scratch = reinterpret_cast<uint64_t *>(ring);
+    if (warp < SCAN_CONSUMER_WARPS) top.dump(scratch + warp * 32 * KPL, lane);
+    __syncthreads();
+    emit_cta_list<KPL>(scratch, SCAN_CONSUMER_WARPS,
+                       a.cand + static_cast<size_t>(blockIdx.x) * a.cand_stride, tid, SCAN_THREADS);
+}
+
+// ---- direct-load variant, any dim -----------------------------------------------
+// DIM_T > 0: compile-time dim (query chunks in registers); DIM_T == 0: runtime dim.
+template <int DIM_T, int KPL, int METRIC, bool WRITE_ALL>
+__global__ void __launch_bounds__(LDG_THREADS) scan_ldg_kernel(const ScanArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const int dim = DIM_T > 0 ? DIM_T : a.dim;
+    const int ld = DIM_T > 0 ? DIM_T : a.ld;
+    const int chunks = ld >> 2;  // float4 per row (padding floats are zero)
+
+    // sort scratch and the query share the dynamic shared memory
+    uint64_t *scratch = reinterpret_cast<uint64_t *>(smem);
+    float4 *qs = reinterpret_cast<float4 *>(smem + next_pow2(LDG_WARPS * 32 * KPL) * sizeof(uint64_t));
+    for (int c = tid; c < chunks; c += LDG_THREADS) {
+        float4 v;
+        const int base = c * 4;
+        v.x = base + 0 < dim ? __ldg(a.query + base + 0) : 0.f;
+        v.y = base + 1 < dim ? __ldg(a.query + base + 1) : 0.f;
+        v.z = base + 2 < dim ? __ldg(a.query + base + 2) : 0.f;
+        v.w = base + 3 < dim ? __ldg(a.query + base + 3) : 0.f;
+        qs[c] = v;
+    }
+    __syncthreads();
+
+    float bsum = 0.f;
+    for (int c = lane; c < chunks; c += 32) {
+        float4 v = qs[c];
+        bsum = fmaf(v.x, v.x, bsum);
+        bsum = fmaf(v.y, v.y, bsum);
+        bsum = fmaf(v.z, v.z, bsum);
+        bsum = fmaf(v.w, v.w, bsum);
+    }
+    const double sqrt_b = sqrt(static_cast<double>(warp_sum(bsum)));
+
+    WarpTopK<KPL> top;
+    top.init(a.k, lane);
+    unsigned nan_rows = 0;
+
+    const long long warp_global = static_cast<long long>(blockIdx.x) * LDG_WARPS + warp;
+    const long long warp_count = static_cast<long long>(gridDim.x) * LDG_WARPS;
+
+    for (long long pos = warp_global; pos < a.n; pos += warp_count) {
+        if (!row_admitted(a.mask, pos)) {
+            if (WRITE_ALL && lane == 0) a.all_keys[pos] = KEY_EMPTY;
+            continue;
+        }
+        const float4 *src = reinterpret_cast<const float4 *>(a.rows + pos * ld);
+        float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+        if (DIM_T > 0) {
+            constexpr int CH = DIM_T > 0 ? DIM_T / 128 : 1;
+            float4 v[CH];
+#pragma unroll
+            for (int j = 0; j < CH; j++) v[j] = ldg_stream(src + lane + 32 * j);
+#pragma unroll
+            for (int j = 0; j < CH; j++) accumulate<METRIC>(v[j], qs[lane + 32 * j], s0, s1);
+        } else {
+            int c = lane;
+            for (; c + 96 < chunks; c += 128) {
+                float4 v0 = ldg_stream(src + c), v1 = ldg_stream(src + c + 32);
+                float4 v2 = ldg_stream(src + c + 64), v3 = ldg_stream(src + c + 96);
+                accumulate<METRIC>(v0, qs[c], s0, s1);
+                accumulate<METRIC>(v1, qs[c + 32], s0, s1);
+                accumulate<METRIC>(v2, qs[c + 64], s0, s1);
+                accumulate<METRIC>(v3, qs[c + 96], s0, s1);
+            }
+            for (; c < chunks; c += 32) accumulate<METRIC>(ldg_stream(src + c), qs[c], s0, s1);
+        }
+        float t0 = warp_sum((s0[0] + s0[1]) + (s0[2] + s0[3]));
+        float t1 = (METRIC == METRIC_COSINE) ? warp_sum((s1[0] + s1[1]) + (s1[2] + s1[3])) : 0.f;
+        offer_row<KPL, METRIC, WRITE_ALL>(t0, t1, sqrt_b, pos, top, nan_rows, a.all_keys, lane);
+    }
+
+    if (nan_rows && lane == 0) atomicAdd(a.nan_rows, static_cast<unsigned long long>(nan_rows));
+    if (WRITE_ALL) return;
+
+    top.dump(scratch + warp * 32 * KPL, lane);
+    __syncthreads();
+    emit_cta_list<KPL>(scratch, LDG_WARPS, a.cand + static_cast<size_t>(blockIdx.x) * a.cand_stride,
+                       tid, LDG_THREADS);
+}
+
+}  // namespace clipdb

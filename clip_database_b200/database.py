@@ -1,0 +1,321 @@
+"""``ImageDatabase`` — the reference's search surface on top of the GPU index.
+
+Mirrors ``ImageDatabase.search`` (image_database.py:1308-1658): same signature,
+same result type (``List[Tuple[file_path, similarity]]`` sorted by similarity
+descending), same guards and fallbacks — with the body replaced: the store is
+loaded once from the SQLite database into resident HBM and every search is one
+blend + scan + top-k on the GPU instead of a per-row SQL function call.
+
+The SigLIP model is out of scope (no weights offline): ``search()`` takes text /
+image-path queries only when an ``embedder`` is supplied; ``search_embedding()``
+takes the float32[1152] vectors directly and is what ``search()`` calls after
+embedding.  There is no CPU search path.
+"""
+from __future__ import annotations
+
+import os
+import sqlite3
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import loader, schema
+from .index import GpuIndex
+
+Result = List[Tuple[str, float]]
+
+
+class Embedder:
+    """Interface for the out-of-scope model: text / image path -> float32[dim] (or None)."""
+
+    def text(self, query: str) -> Optional[np.ndarray]:       # image_database.py:509-543
+        raise NotImplementedError
+
+    def image(self, path: str) -> Optional[np.ndarray]:       # image_database.py:443-463
+        raise NotImplementedError
+
+
+def like_prefix_mask(file_paths: Sequence[str], folders: Sequence[str],
+                     lowered: Optional[List[bytes]] = None) -> np.ndarray:
+    """Rows the reference's folder WHERE clause admits (image_database.py:1513-1529, 1576-1579).
+
+    The reference normalises each folder with ``os.path.abspath`` + a trailing
+    separator, escapes ``\\ % _`` and matches ``file_path LIKE <folder>% ESCAPE '\\'``:
+    a prefix match in which SQLite's LIKE folds ASCII letters only.
+    """
+    prefixes = []
+    for folder in folders:
+        f = os.path.abspath(folder)
+        if not f.endswith(os.sep):
+            f += os.sep
+        prefixes.append(f.encode("utf-8").lower())       # bytes.lower() folds ASCII only, as LIKE does
+    if lowered is None:
+        lowered = [p.encode("utf-8").lower() for p in file_paths]
+    pref = tuple(prefixes)
+    return np.fromiter((p.startswith(pref) for p in lowered), dtype=bool, count=len(lowered))
+
+
+def filter_duplicates(results: Result, codes: Dict[str, np.ndarray], tolerance_bits: int = 2) -> Result:
+    """Post-filter of image_database.py:1207-1306 given each result's stored sign code.
+
+    ``codes`` maps file_path -> uint8[1152] (absent = no binary embedding: kept).
+    Walks results in order; a result within ``tolerance_bits`` differing positions
+    of an earlier group's first code is a duplicate: it replaces the group's kept
+    entry only if strictly more similar.  The survivors are re-sorted by
+    similarity descending (stable).
+    """
+    group_code: List[np.ndarray] = []     # code that founded each group (never replaced, :1278-1287)
+    group_best: List[Tuple[str, float]] = []
+    kept: Result = []
+    for path, sim in results:
+        code = codes.get(path)
+        if code is None:
+            kept.append((path, sim))
+            continue
+        hit = -1
+        if group_code:
+            diff = (np.stack(group_code) != code[None, :]).sum(axis=1)
+            near = np.nonzero(diff <= tolerance_bits)[0]
+            if near.size:
+                hit = int(near[0])
+        if hit < 0:
+            group_code.append(code)
+            group_best.append((path, sim))
+            kept.append((path, sim))
+        elif sim > group_best[hit][1]:
+            old = group_best[hit][0]
+            group_best[hit] = (path, sim)
+            kept = [(p, s) for p, s in kept if p != old]
+            kept.append((path, sim))
+    kept.sort(key=lambda r: r[1], reverse=True)
+    return kept
+
+
+class ImageDatabase:
+    """Drop-in for the search half of the reference class of the same name."""
+
+    embedding_dim = schema.EMBEDDING_DIM
+
+    def __init__(self, db_path: str, device: int = 0, embedder: Optional[Embedder] = None,
+                 nan_policy: str = "reference", verbose: bool = False):
+        if nan_policy not in ("reference", "exclude"):
+            raise ValueError("nan_policy must be 'reference' or 'exclude'")
+        self.db_path = db_path
+        self.embedder = embedder
+        self.nan_policy = nan_policy
+        self.verbose = verbose
+        self.index = GpuIndex(device)
+        self._paths: List[str] = []
+        self._lowered: Optional[List[bytes]] = None
+        self._image_ids = np.zeros(0, dtype=np.int64)
+        self._rowid_to_pos: Dict[int, int] = {}
+        self._binary_count = 0
+        self._vec0_count = 0
+        self._mask_key: Optional[Tuple[str, ...]] = None
+        self.reload()
+
+    # ---- store ----------------------------------------------------------------------
+    def _log(self, *a) -> None:
+        if self.verbose:
+            print(*a, flush=True)
+
+    def reload(self) -> None:
+        """(Re)read the whole database into HBM."""
+        host = loader.read_store(self.db_path)
+        self._binary_count = host.binary_count
+        self._vec0_count = host.vec0_count
+        self._paths = list(host.file_paths)
+        self._lowered = None
+        self._image_ids = host.image_ids
+        self._rowids = host.rowids
+        self._rowid_to_pos = {int(r): i for i, r in enumerate(host.rowids)}
+        self._mask_key = None
+        if host.rows.shape[0]:
+            self.index.load(host.rows, host.rowids)
+        self._log(f"loaded {host.rows.shape[0]} rows ({host.source}); {host.dropped} vec0 rows without "
+                  f"a mapping were skipped")
+
+    def refresh(self) -> int:
+        """Append rows the scanner added since the last load (new vec0 rowids are always
+        larger: INSERT INTO vec0 auto-assigns, image_database.py:1171-1175).  Returns
+        the number of rows appended.  In-place UPDATEs of old rows need ``reload()``."""
+        last = int(self._rowids[-1]) if len(self._paths) else None
+        host = loader.read_store(self.db_path, expect_dim=self.index.dim or None, min_rowid=last)
+        self._binary_count = host.binary_count
+        self._vec0_count = self._vec0_count + host.vec0_count if last is not None else host.vec0_count
+        m = host.rows.shape[0]
+        if m == 0:
+            return 0
+        if not self._paths:
+            self.index.load(host.rows, host.rowids)
+        else:
+            self.index.append(host.rows, host.rowids)
+        base = len(self._paths)
+        self._paths.extend(host.file_paths)
+        self._lowered = None
+        self._image_ids = np.concatenate([self._image_ids, host.image_ids])
+        self._rowids = np.concatenate([self._rowids, host.rowids]) if base else host.rowids
+        for i, r in enumerate(host.rowids):
+            self._rowid_to_pos[int(r)] = base + i
+        self._mask_key = None
+        return m
+
+    def close(self) -> None:
+        self.index.close()
+
+    # ---- search -----------------------------------------------------------------------
+    def _embed(self, query: str, is_image: bool, what: str) -> Optional[np.ndarray]:
+        if self.embedder is None:
+            raise RuntimeError("no embedder configured: pass embedder=... or call search_embedding() "
+                               "with float32 vectors (the SigLIP model is outside this package)")
+        return self.embedder.image(query) if is_image else self.embedder.text(query)
+
+    def search(self, query: str, k: int = 10, is_image_path: bool = False,
+               query2: str = None, is_image_path2: bool = False,
+               weights: Tuple[float, float] = (0.5, 0.5),
+               negative_query: str = None, negative_is_image: bool = False,
+               negative_weight: float = 0.5,
+               negative_queries: List[str] = None, negative_is_images: List[bool] = None,
+               negative_weights: List[float] = None,
+               filter_folders: List[str] = None,
+               profile: bool = False,
+               show_duplicates: bool = False) -> Result:
+        """Same contract as image_database.py:1308-1337."""
+        # first / second positive query (:1340-1376)
+        if is_image_path and not os.path.exists(query):
+            print(f"Error: Image file {query} does not exist")
+            return []
+        e1 = self._embed(query, is_image_path, "query")
+        if e1 is None:
+            print("Error: Failed to generate embedding from image")
+            return []
+        e2 = None
+        if query2 is not None:
+            if is_image_path2 and not os.path.exists(query2):
+                print(f"Error: Image file {query2} does not exist")
+                return []
+            e2 = self._embed(query2, is_image_path2, "second query")
+            if e2 is None:
+                print("Error: Failed to generate embedding from second image")
+                return []
+        # negatives: legacy single first, then the list; missing image files are skipped (:1402-1451)
+        negs, neg_ws = [], []
+        if negative_query is not None:
+            if negative_is_image and not os.path.exists(negative_query):
+                print(f"Warning: Negative image file {negative_query} does not exist, ignoring negative prompt")
+            else:
+                v = self._embed(negative_query, negative_is_image, "negative")
+                if v is not None:
+                    negs.append(v)
+                    neg_ws.append(negative_weight)
+        if negative_queries is not None:
+            for i, nq in enumerate(negative_queries):
+                is_img = negative_is_images[i] if negative_is_images and i < len(negative_is_images) else False
+                w = negative_weights[i] if negative_weights and i < len(negative_weights) else negative_weight
+                if is_img and not os.path.exists(nq):
+                    print(f"Warning: Negative image file {nq} does not exist, skipping")
+                    continue
+                v = self._embed(nq, is_img, "negative")
+                if v is not None:
+                    negs.append(v)
+                    neg_ws.append(w)
+        return self.search_embedding(e1, k=k, embedding2=e2, weights=weights, negative_embeddings=negs,
+                                     negative_weights=neg_ws, filter_folders=filter_folders,
+                                     profile=profile, show_duplicates=show_duplicates)
+
+    def _install_mask(self, filter_folders: Optional[Sequence[str]]) -> bool:
+        if not filter_folders:
+            return False
+        key = tuple(filter_folders)
+        if key != self._mask_key:
+            if self._lowered is None:
+                self._lowered = [p.encode("utf-8").lower() for p in self._paths]
+            self.index.set_mask(like_prefix_mask(self._paths, filter_folders, self._lowered))
+            self._mask_key = key
+        return True
+
+    def search_embedding(self, embedding1, k: int = 10, embedding2=None,
+                         weights: Tuple[float, float] = (0.5, 0.5),
+                         negative_embeddings: Sequence = (), negative_weights: Sequence[float] = (),
+                         filter_folders: Optional[Sequence[str]] = None, profile: bool = False,
+                         show_duplicates: bool = False) -> Result:
+        """``search()`` after the embedding step: blend, negatives, guards, scan, top-k,
+        similarity conversion, duplicate filter (image_database.py:1378-1658)."""
+        import time
+        timings = {}
+        # guards (:1488-1500, :1532-1555).  The binary (sign-code) fallback used when
+        # vec0 is empty is a different, approximate path and is not provided here.
+        if self._binary_count <= 0:
+            print("Error: Database has no embeddings. Please run scan first.")
+            return []
+        if self._vec0_count <= 0:
+            raise NotImplementedError("vec0 is empty: the reference would fall back to its binary "
+                                      "sign-code search (image_database.py:1591-1629), which is out of scope")
+        try:
+            k = int(k)
+            t0 = time.time()
+            use_mask = self._install_mask(filter_folders)
+            timings["build_query"] = time.time() - t0
+            t0 = time.time()
+            if k < 0:
+                k = self.index.num_rows          # SQLite: negative LIMIT = no limit
+            if self.index.num_rows == 0:
+                return []
+            res = self.index.blend_search(embedding1, k, e2=embedding2, weights=weights,
+                                          negatives=negative_embeddings,
+                                          negative_weights=negative_weights, use_mask=use_mask)
+            rowids, dist = res.row(0)
+            if res.nan_rows[0] > 0 and self.nan_policy == "reference" and k > 0:
+                # SQLite stores a NaN distance as NULL, NULLs sort first, and the reference's
+                # `1.0 - distance` then raises inside its try block (:1588, :1637-1640)
+                raise TypeError("unsupported operand type(s) for -: 'float' and 'NoneType'")
+            top = [(self._paths[self._rowid_to_pos[int(r)]], 1.0 - float(d)) for r, d in zip(rowids, dist)]
+            timings["db_query"] = time.time() - t0
+            results = [(p, float(s)) for p, s in top]
+        except NotImplementedError:
+            raise
+        except Exception as e:                       # error envelope, :1637-1640
+            print(f"Error during search: {e}")
+            return []
+        if not show_duplicates and len(results) > 0:
+            t0 = time.time()
+            results = self._filter_duplicates(results, tolerance_bits=2)
+            timings["filter_duplicates"] = time.time() - t0
+        if profile and timings:
+            print("\n=== Search Performance Profile ===")
+            total = sum(timings.values())
+            for op, dur in sorted(timings.items(), key=lambda x: x[1], reverse=True):
+                pct = (dur / total * 100) if total > 0 else 0
+                print(f"  {op:25s}: {dur * 1000:7.2f}ms ({pct:5.1f}%)")
+            print(f"  {'TOTAL':25s}: {total * 1000:7.2f}ms")
+            print("=" * 40 + "\n")
+        return results
+
+    def _filter_duplicates(self, results: Result, tolerance_bits: int = 2) -> Result:
+        """Fetch the k results' stored sign codes (as the reference does per search,
+        image_database.py:1232-1255) and apply ``filter_duplicates``."""
+        conn = loader.connect(self.db_path)
+        try:
+            ids = {}
+            for path, _ in results:
+                row = conn.execute("SELECT id FROM images WHERE file_path = ?", (path,)).fetchone()
+                if row:
+                    ids[path] = row[0]
+            codes: Dict[str, np.ndarray] = {}
+            if ids:
+                id_list = list(ids.values())
+                by_id = {}
+                for lo in range(0, len(id_list), 500):      # stay under SQLite's bound-variable limit
+                    part = id_list[lo:lo + 500]
+                    marks = ",".join("?" * len(part))
+                    for image_id, blob in conn.execute(
+                            f"SELECT image_id, embedding FROM binary_embeddings WHERE image_id IN ({marks})", part):
+                        by_id[image_id] = np.frombuffer(blob, dtype=np.uint8)
+                codes = {p: by_id[i] for p, i in ids.items() if i in by_id}
+        finally:
+            conn.close()
+        before = len(results)
+        out = filter_duplicates(results, codes, tolerance_bits)
+        if len(out) < before:
+            print(f"Filtered out {before - len(out)} duplicate(s) (tolerance: {tolerance_bits} bits)")
+        return out

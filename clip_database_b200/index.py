@@ -1,0 +1,292 @@
+"""``GpuIndex`` — one GPU's resident float32 row store behind the C ABI.
+
+Thin, typed wrapper over ``include/clipdb.h``; all arithmetic happens in the
+CUDA library.  Host-array methods are synchronous (like the reference's
+``cursor.execute`` / ``fetchall`` pair, image_database.py:1582-1583); the
+``*_device`` methods take torch CUDA tensors, enqueue on the context's stream
+and do not synchronise.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+
+METRICS = {"cosine": _lib.METRIC_COSINE, "l2": _lib.METRIC_L2}
+
+
+@dataclass
+class SearchResult:
+    """Per query: ``rowids[q, :counts[q]]`` / ``distances[q, :counts[q]]`` sorted by
+    (distance ascending, rowid ascending); ``nan_rows[q]`` admitted rows whose
+    distance was NaN (excluded from the result, see clipdb.h)."""
+    rowids: np.ndarray      # int64 [nq, k]
+    distances: np.ndarray   # float32 [nq, k]
+    counts: np.ndarray      # int32 [nq]
+    nan_rows: np.ndarray    # int64 [nq]
+
+    def row(self, q: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+        m = int(self.counts[q])
+        return self.rowids[q, :m], self.distances[q, :m]
+
+
+def _metric(metric) -> int:
+    if isinstance(metric, str):
+        try:
+            return METRICS[metric.lower()]
+        except KeyError:
+            raise ValueError(f"unknown metric {metric!r}; expected one of {sorted(METRICS)}")
+    return int(metric)
+
+
+def _fptr(a: Optional[np.ndarray]):
+    if a is None:
+        return ctypes.cast(None, ctypes.POINTER(ctypes.c_float))
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+class GpuIndex:
+    def __init__(self, device: int = 0):
+        self._L = _lib.load()
+        self._ctx = ctypes.c_void_p()
+        rc = self._L.clipdb_create(int(device), ctypes.byref(self._ctx))
+        if rc != _lib.OK:
+            self._ctx = ctypes.c_void_p()
+            raise _lib.ClipdbError(rc, "clipdb_create failed (no usable CUDA device? there is no CPU fallback)")
+        self.device = int(device)
+        self._keepalive = []  # tensors borrowed by attach()
+
+    # ---- lifetime -----------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self._L.clipdb_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+            self._keepalive = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int) -> None:
+        _lib.check(self._ctx, rc)
+
+    # ---- plumbing -----------------------------------------------------------------
+    @property
+    def num_rows(self) -> int:
+        return int(self._L.clipdb_num_rows(self._ctx))
+
+    @property
+    def dim(self) -> int:
+        return int(self._L.clipdb_dim(self._ctx))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.clipdb_launch_count(self._ctx))
+
+    def set_option(self, name: str, value: int) -> None:
+        self._check(self._L.clipdb_set_option(self._ctx, name.encode(), int(value)))
+
+    def get_option(self, name: str) -> int:
+        v = ctypes.c_int64(0)
+        self._check(self._L.clipdb_get_option(self._ctx, name.encode(), ctypes.byref(v)))
+        return int(v.value)
+
+    def set_stream(self, cuda_stream: Optional[int]) -> None:
+        """Run on the given ``cudaStream_t`` (an int handle); ``None`` = the context's own."""
+        self._check(self._L.clipdb_set_stream(self._ctx, ctypes.c_void_p(cuda_stream or 0)))
+
+    def use_torch_stream(self) -> None:
+        import torch
+        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def synchronize(self) -> None:
+        self._check(self._L.clipdb_synchronize(self._ctx))
+
+    # ---- row store ------------------------------------------------------------------
+    def load(self, rows, rowids=None) -> None:
+        """Copy ``rows`` (numpy ``[n, dim]`` float32, or a torch tensor on any device)
+        into context-owned HBM.  ``rowids`` (int64, ascending = scan order) optional."""
+        if _is_torch(rows):
+            rows_t = rows.detach().contiguous().float()
+            n, dim = rows_t.shape
+            ids_t = None
+            if rowids is not None:
+                import torch
+                ids_t = torch.as_tensor(rowids, dtype=torch.int64).contiguous()
+            self._check(self._L.clipdb_load_rows(self._ctx, ctypes.c_void_p(rows_t.data_ptr()),
+                                                 ctypes.c_void_p(ids_t.data_ptr() if ids_t is not None else 0),
+                                                 n, dim))
+            return
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        if rows.ndim != 2:
+            raise ValueError("rows must be [n, dim]")
+        n, dim = rows.shape
+        ids = None
+        if rowids is not None:
+            ids = np.ascontiguousarray(rowids, dtype=np.int64)
+            if ids.shape != (n,):
+                raise ValueError("rowids must be [n]")
+        self._check(self._L.clipdb_load_rows(self._ctx, ctypes.c_void_p(rows.ctypes.data),
+                                             ctypes.c_void_p(ids.ctypes.data if ids is not None else 0),
+                                             n, dim))
+        self._keepalive = []
+
+    def append(self, rows, rowids=None) -> None:
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        if rows.ndim != 2 or (self.dim and rows.shape[1] != self.dim):
+            raise ValueError("rows must be [m, dim] with the store's dim")
+        ids = None
+        if rowids is not None:
+            ids = np.ascontiguousarray(rowids, dtype=np.int64)
+        self._check(self._L.clipdb_append_rows(self._ctx, ctypes.c_void_p(rows.ctypes.data),
+                                               ctypes.c_void_p(ids.ctypes.data if ids is not None else 0),
+                                               rows.shape[0]))
+
+    def update_row(self, position: int, row) -> None:
+        row = np.ascontiguousarray(row, dtype=np.float32)
+        if row.shape != (self.dim,):
+            raise ValueError("row must be [dim]")
+        self._check(self._L.clipdb_update_row(self._ctx, int(position), ctypes.c_void_p(row.ctypes.data)))
+
+    def attach(self, rows, rowids=None, rowid_base: int = 0) -> None:
+        """Borrow a torch CUDA tensor ``[n, dim]`` float32 (no copy).  Kept alive here."""
+        if not (_is_torch(rows) and rows.is_cuda and rows.is_contiguous() and rows.dtype.is_floating_point
+                and rows.element_size() == 4):
+            raise ValueError("attach() needs a contiguous float32 CUDA tensor")
+        n, dim = rows.shape
+        ids_ptr = 0
+        if rowids is not None:
+            if not (rowids.is_cuda and rowids.is_contiguous() and rowids.element_size() == 8):
+                raise ValueError("rowids must be a contiguous int64 CUDA tensor")
+            ids_ptr = rowids.data_ptr()
+        self._check(self._L.clipdb_attach_rows(self._ctx, ctypes.c_void_p(rows.data_ptr()),
+                                               ctypes.c_void_p(ids_ptr), n, dim, int(rowid_base)))
+        self._keepalive = [rows, rowids]
+
+    def set_mask(self, admitted) -> None:
+        """``admitted``: bool/uint8 array of length ``num_rows``; True = row takes part."""
+        bits = np.asarray(admitted).astype(bool)
+        if bits.shape != (self.num_rows,):
+            raise ValueError("mask must have one entry per row")
+        packed = np.packbits(bits, bitorder="little")
+        words = np.zeros((self.num_rows + 31) // 32, dtype=np.uint32)
+        words.view(np.uint8)[: packed.shape[0]] = packed
+        self._check(self._L.clipdb_set_mask(self._ctx, ctypes.c_void_p(words.ctypes.data), words.shape[0]))
+
+    def clear_mask(self) -> None:
+        self._check(self._L.clipdb_clear_mask(self._ctx))
+
+    # ---- query arithmetic -----------------------------------------------------------------
+    @staticmethod
+    def _pack_negatives(negatives, negative_weights, dim):
+        negs = [np.ascontiguousarray(v, dtype=np.float32).reshape(dim) for v in negatives]
+        ws = [float(w) for w in negative_weights]
+        if len(negs) != len(ws):
+            raise ValueError("one weight per negative")
+        if not negs:
+            return None, None, 0
+        return np.ascontiguousarray(np.stack(negs)), (ctypes.c_double * len(ws))(*ws), len(negs)
+
+    def blend(self, e1, e2=None, weights: Tuple[float, float] = (0.5, 0.5),
+              negatives: Sequence = (), negative_weights: Sequence[float] = ()
+              ) -> Tuple[np.ndarray, int]:
+        """K3 on the GPU.  Returns (float32[dim], CLIPDB_BLEND_* flags)."""
+        e1 = np.ascontiguousarray(e1, dtype=np.float32).ravel()
+        dim = e1.shape[0]
+        e2a = None if e2 is None else np.ascontiguousarray(e2, dtype=np.float32).reshape(dim)
+        negs, ws, n_neg = self._pack_negatives(negatives, negative_weights, dim)
+        out = np.empty(dim, dtype=np.float32)
+        flags = ctypes.c_int32(0)
+        self._check(self._L.clipdb_blend(self._ctx, _fptr(e1), _fptr(e2a), float(weights[0]),
+                                         float(weights[1]), _fptr(negs), ws, n_neg, dim, _fptr(out),
+                                         ctypes.byref(flags)))
+        return out, int(flags.value)
+
+    # ---- search ---------------------------------------------------------------------------
+    def _alloc_result(self, nq: int, k: int) -> SearchResult:
+        kc = max(k, 0)
+        return SearchResult(np.full((nq, kc), -1, dtype=np.int64),
+                            np.full((nq, kc), np.nan, dtype=np.float32),
+                            np.zeros(nq, dtype=np.int32), np.zeros(nq, dtype=np.int64))
+
+    def search(self, queries, k: int, metric="cosine", use_mask: bool = False) -> SearchResult:
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"queries must be [nq, {self.dim}]")
+        nq = q.shape[0]
+        res = self._alloc_result(nq, int(k))
+        self._check(self._L.clipdb_search(
+            self._ctx, _fptr(q), nq, int(k), _metric(metric), int(bool(use_mask)),
+            res.rowids.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), _fptr(res.distances),
+            res.counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+            res.nan_rows.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))))
+        return res
+
+    def blend_search(self, e1, k: int, e2=None, weights: Tuple[float, float] = (0.5, 0.5),
+                     negatives: Sequence = (), negative_weights: Sequence[float] = (),
+                     metric="cosine", use_mask: bool = False, return_query: bool = False):
+        """blend + scan + top-k in one host call; the blended query stays in HBM."""
+        e1 = np.ascontiguousarray(e1, dtype=np.float32).ravel()
+        dim = e1.shape[0]
+        if dim != self.dim:
+            raise ValueError(f"query must be [{self.dim}]")
+        e2a = None if e2 is None else np.ascontiguousarray(e2, dtype=np.float32).reshape(dim)
+        negs, ws, n_neg = self._pack_negatives(negatives, negative_weights, dim)
+        res = self._alloc_result(1, int(k))
+        qout = np.empty(dim, dtype=np.float32) if return_query else None
+        flags = ctypes.c_int32(0)
+        self._check(self._L.clipdb_blend_search(
+            self._ctx, _fptr(e1), _fptr(e2a), float(weights[0]), float(weights[1]), _fptr(negs), ws,
+            n_neg, int(k), _metric(metric), int(bool(use_mask)),
+            res.rowids.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), _fptr(res.distances),
+            res.counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+            res.nan_rows.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), _fptr(qout),
+            ctypes.byref(flags)))
+        if return_query:
+            return res, qout, int(flags.value)
+        return res
+
+    def search_device(self, d_queries, k: int, out_rowids, out_dist, out_n, out_nan=None,
+                      metric="cosine", use_mask: bool = False) -> None:
+        """Async: torch CUDA tensors in and out (queries ``[nq, dim]`` float32; outputs
+        int64 ``[nq, k]``, float32 ``[nq, k]``, int32 ``[nq]``, int64 ``[nq]``)."""
+        nq = d_queries.shape[0] if d_queries.dim() == 2 else 1
+        self._check(self._L.clipdb_search_device(
+            self._ctx, ctypes.c_void_p(d_queries.data_ptr()), nq, int(k), _metric(metric),
+            int(bool(use_mask)), ctypes.c_void_p(out_rowids.data_ptr()),
+            ctypes.c_void_p(out_dist.data_ptr()), ctypes.c_void_p(out_n.data_ptr()),
+            ctypes.c_void_p(out_nan.data_ptr() if out_nan is not None else 0)))
+
+    def blend_device(self, d_e1, d_e2, d_w, d_negs, d_neg_w, d_out, d_flags=None) -> None:
+        """Async batched K3: see clipdb_blend_device."""
+        batch, dim = d_e1.shape
+        n_neg = 0 if d_negs is None else d_negs.shape[1]
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr() if t is not None else 0)
+        self._check(self._L.clipdb_blend_device(self._ctx, ptr(d_e1), ptr(d_e2), ptr(d_w), ptr(d_negs),
+                                                ptr(d_neg_w), n_neg, dim, batch, ptr(d_out), ptr(d_flags)))
+
+    def merge_device(self, d_dist, d_rowids, d_counts, k: int, out_dist, out_rowids, out_n) -> None:
+        """Async shard merge of ``[lists, k]`` gathered results (clipdb_merge_device)."""
+        lists = d_dist.shape[0]
+        self._check(self._L.clipdb_merge_device(
+            self._ctx, ctypes.c_void_p(d_dist.data_ptr()), ctypes.c_void_p(d_rowids.data_ptr()),
+            ctypes.c_void_p(d_counts.data_ptr()), lists, int(k), ctypes.c_void_p(out_dist.data_ptr()),
+            ctypes.c_void_p(out_rowids.data_ptr()), ctypes.c_void_p(out_n.data_ptr())))

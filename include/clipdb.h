@@ -1,0 +1,175 @@
+/*
+ * clipdb.h — C ABI of the B200-native brute-force KNN path for CLIP-database.
+ *
+ * This is the drop-in boundary: everything the reference's search path gets
+ * from the third-party sqlite-vec extension + SQLite's ORDER BY/LIMIT sorter,
+ * plus the numpy query arithmetic that precedes it, behind plain C entry
+ * points (extern "C", pointers and sizes only, no torch / C++ types).
+ * `idb` = /root/reference/image_database.py.
+ *
+ * Conventions
+ *   - every function returns CLIPDB_OK (0) or a CLIPDB_ERR_* code; the message
+ *     for the last failure on a context is clipdb_last_error(ctx).  No C++
+ *     exception and no sticky CUDA error crosses this boundary.
+ *   - a context owns one GPU's resident row store, workspaces and a stream.
+ *     Calls on one context are serialised on its stream; several contexts
+ *     (one per GPU, or several per GPU) coexist; there is no global state.
+ *   - "host" entry points are synchronous like the reference (results are on
+ *     the host when they return); "*_device" entry points take device
+ *     pointers, enqueue on the context's stream and return without syncing.
+ *   - there is NO CPU fallback: without a CUDA device every call fails with
+ *     CLIPDB_ERR_CUDA.
+ */
+#ifndef CLIPDB_H
+#define CLIPDB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct clipdb_ctx clipdb_ctx;
+
+#define CLIPDB_OK               0
+#define CLIPDB_ERR_INVALID      1   /* bad argument */
+#define CLIPDB_ERR_CUDA         2   /* CUDA runtime / launch failure, or no device */
+#define CLIPDB_ERR_NOMEM        3   /* device or pinned-host allocation failed */
+#define CLIPDB_ERR_STATE        4   /* e.g. search before any rows were loaded */
+#define CLIPDB_ERR_UNSUPPORTED  5
+
+/* Distance kinds.  COSINE is what the reference asks for
+ * (`vec_distance_cosine(vec0.embedding, ?)`, idb:1567).  L2 is the metric a
+ * `vec0(embedding float[1152])` table declares by default (idb:290-294), which
+ * only sqlite-vec's MATCH form would use; shipped as a variant of the same scan. */
+#define CLIPDB_METRIC_COSINE    0
+#define CLIPDB_METRIC_L2        1
+
+/* bit flags reported by clipdb_blend (which fallback of idb:1390-1395 /
+ * idb:558-570 / idb:591-603 fired) */
+#define CLIPDB_BLEND_POSITIVE_ZERO_NORM  1  /* blend had zero norm -> first query used (idb:1393-1395) */
+#define CLIPDB_BLEND_NEGATIVE_ZERO_NORM  2  /* zero after negatives -> original restored (idb:560-570) */
+
+/* ABI version of this header (bumped on any signature change). */
+int clipdb_abi_version(void);
+
+/* ---- context -------------------------------------------------------------
+ * Replaces: sqlite3.connect + sqlite_vec.load(conn) per search (idb:1475-1484);
+ * here the store is loaded once and stays resident in HBM. */
+int  clipdb_create(int device, clipdb_ctx **out);
+void clipdb_destroy(clipdb_ctx *ctx);
+const char *clipdb_last_error(const clipdb_ctx *ctx);
+
+/* Run on a caller-provided CUDA stream (cudaStream_t passed as void*), e.g.
+ * torch's current stream so torch.cuda.Event brackets the kernels.  NULL
+ * restores the context's own stream. */
+int clipdb_set_stream(clipdb_ctx *ctx, void *cuda_stream);
+int clipdb_synchronize(clipdb_ctx *ctx);
+
+/* Tuning knobs for experiments ("scan_variant", "scan_ctas", ...).  Unknown
+ * names fail with CLIPDB_ERR_INVALID. */
+int clipdb_set_option(clipdb_ctx *ctx, const char *name, int64_t value);
+int clipdb_get_option(clipdb_ctx *ctx, const char *name, int64_t *value);
+
+/* Kernels launched by this context since creation (bench.py "gpu_launches"). */
+int64_t clipdb_launch_count(const clipdb_ctx *ctx);
+
+/* ---- resident row store ---------------------------------------------------
+ * Replaces: the vec0 virtual table's storage of one float32[dim] blob per
+ * rowid (DDL idb:290-294, writer idb:1164-1181).  Rows are given in scan order
+ * (ascending rowid); `rowids` may be NULL (rowid = rowid_base + position).
+ *
+ * clipdb_load_rows   copies n x dim float32 from a host OR device pointer into
+ *                    context-owned HBM (replaces any previous store).
+ * clipdb_append_rows appends (the scanner only ever INSERTs new rowids or
+ *                    UPDATEs in place, idb:1165-1175).
+ * clipdb_update_row  overwrites one stored row by position (UPDATE vec0 ...,
+ *                    idb:1165-1167).
+ * clipdb_attach_rows borrows caller-owned DEVICE memory without copying
+ *                    (dim % 4 == 0, 16-byte aligned); the caller keeps it
+ *                    alive until detach/destroy. */
+int clipdb_load_rows(clipdb_ctx *ctx, const float *rows, const int64_t *rowids,
+                     int64_t n, int32_t dim);
+int clipdb_append_rows(clipdb_ctx *ctx, const float *rows, const int64_t *rowids, int64_t n);
+int clipdb_update_row(clipdb_ctx *ctx, int64_t position, const float *row);
+int clipdb_attach_rows(clipdb_ctx *ctx, const float *d_rows, const int64_t *d_rowids,
+                       int64_t n, int32_t dim, int64_t rowid_base);
+int64_t clipdb_num_rows(const clipdb_ctx *ctx);
+int32_t clipdb_dim(const clipdb_ctx *ctx);
+
+/* Per-row admission bitset: bit (r & 31) of word (r >> 5) set = row r takes
+ * part in the search.  Restates the WHERE (file_path LIKE ...) pre-filter that
+ * is applied before the top-k (idb:1509-1530, 1571).  `words` is a host or
+ * device pointer to ceil(n/32) uint32; it is copied.  clipdb_clear_mask
+ * returns to "all rows". */
+int clipdb_set_mask(clipdb_ctx *ctx, const uint32_t *words, int64_t n_words);
+int clipdb_clear_mask(clipdb_ctx *ctx);
+
+/* ---- query arithmetic (K3) ------------------------------------------------
+ * Replaces the numpy float32 arithmetic of idb:1378-1398 (weighted blend +
+ * L2 normalise), idb:545-571 (one negative) and idb:573-604 (several
+ * negatives, subtracted in list order), including their zero-norm fallbacks.
+ *   e2 NULL           -> single positive query (no blend, idb:1397-1398)
+ *   w0, w1            -> the caller's raw weights; normalised as idb:1379-1383
+ *   negs              -> n_neg x dim float32, neg_w -> n_neg weights
+ * All pointers are HOST pointers; `out` receives dim floats; `out_flags`
+ * (nullable) receives CLIPDB_BLEND_* bits. */
+int clipdb_blend(clipdb_ctx *ctx, const float *e1, const float *e2, double w0, double w1,
+                 const float *negs, const double *neg_w, int32_t n_neg, int32_t dim,
+                 float *out, int32_t *out_flags);
+
+/* Batched device form: `batch` independent queries laid out contiguously
+ * (e1/e2: batch x dim; negs: batch x n_neg x dim; w: batch x 2 NORMALISED
+ * float32 weights; neg_w: batch x n_neg float32).  Async on the ctx stream. */
+int clipdb_blend_device(clipdb_ctx *ctx, const float *d_e1, const float *d_e2, const float *d_w,
+                        const float *d_negs, const float *d_neg_w, int32_t n_neg, int32_t dim,
+                        int32_t batch, float *d_out, int32_t *d_out_flags);
+
+/* ---- search (K1 + K2) -----------------------------------------------------
+ * Replaces the statement at idb:1564-1574 as executed at idb:1582-1583:
+ *     SELECT ..., vec_distance_cosine(vec0.embedding, ?) AS distance FROM vec0 ...
+ *     ORDER BY distance ASC LIMIT ?
+ * For each of the nq queries (nq x dim float32, HOST pointer) writes up to k
+ * results sorted by (distance ascending, scan position ascending) — SQLite's
+ * sorter order, exact ties in rowid order — into out_rowids / out_dist (each
+ * nq x k, row-major; entries past out_n[q] are untouched).
+ *   out_n[q]   = number of results = min(k, rows admitted with a non-NaN distance)
+ *   out_nan[q] = admitted rows whose distance was NaN (zero-norm row or query);
+ *                SQLite would turn those into NULLs that sort FIRST and make
+ *                the reference's `1.0 - distance` raise (idb:1588, 1637-1640);
+ *                they are excluded here and counted so the caller can apply
+ *                either policy.  Nullable.
+ * use_mask != 0 applies the bitset installed by clipdb_set_mask.
+ * k <= 0 -> out_n = 0 (SQLite: LIMIT 0).  k may exceed the row count. */
+int clipdb_search(clipdb_ctx *ctx, const float *queries, int32_t nq, int32_t k,
+                  int32_t metric, int32_t use_mask,
+                  int64_t *out_rowids, float *out_dist, int32_t *out_n, int64_t *out_nan);
+
+/* Same, device pointers in and out, enqueued on the ctx stream, no sync. */
+int clipdb_search_device(clipdb_ctx *ctx, const float *d_queries, int32_t nq, int32_t k,
+                         int32_t metric, int32_t use_mask,
+                         int64_t *d_out_rowids, float *d_out_dist, int32_t *d_out_n,
+                         int64_t *d_out_nan);
+
+/* blend + search in one host call (config 4: text+image 0.7/0.3 blend with a
+ * negative prompt, k=20); the blended query never leaves the GPU.  `out_query`
+ * (nullable) receives the blended vector. */
+int clipdb_blend_search(clipdb_ctx *ctx, const float *e1, const float *e2, double w0, double w1,
+                        const float *negs, const double *neg_w, int32_t n_neg,
+                        int32_t k, int32_t metric, int32_t use_mask,
+                        int64_t *out_rowids, float *out_dist, int32_t *out_n, int64_t *out_nan,
+                        float *out_query, int32_t *out_flags);
+
+/* ---- shard merge (multi-GPU) --------------------------------
+ * Merges `lists` per-shard result lists (each k entries, already sorted, shard
+ * order = rowid order; counts[l] valid entries in list l) into the global
+ * top-k with the comparator (distance, shard, position) == (distance, rowid).
+ * Device pointers (e.g. the output of an NCCL all-gather); async. */
+int clipdb_merge_device(clipdb_ctx *ctx, const float *d_dist, const int64_t *d_rowids,
+                        const int32_t *d_counts, int32_t lists, int32_t k,
+                        float *d_out_dist, int64_t *d_out_rowids, int32_t *d_out_n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLIPDB_H */

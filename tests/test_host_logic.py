@@ -1,0 +1,124 @@
+"""Host-side pieces of the drop-in: loader, folder mask, duplicate filter."""
+import os
+import sqlite3
+
+import numpy as np
+import pytest
+
+from clip_database_b200 import database, loader, synth
+from oracle import sql_harness
+
+DIM = 1152
+
+
+def test_loader_plain_and_shadow_agree(tmp_path):
+    rows = synth.unit_rows(2500, DIM, 21)
+    a, b = str(tmp_path / "a.db"), str(tmp_path / "b.db")
+    synth.write_reference_db(a, rows, rowid_start=5)
+    synth.write_reference_db(b, rows, rowid_start=5, vec0_layout="shadow")
+    ha, hb = loader.read_store(a), loader.read_store(b)
+    assert ha.source == "plain-table" and hb.source == "shadow-tables"
+    assert np.array_equal(ha.rows, rows) and np.array_equal(hb.rows, rows)
+    assert np.array_equal(ha.rowids, np.arange(5, 2505)) and np.array_equal(hb.rowids, ha.rowids)
+    assert ha.file_paths == hb.file_paths == synth.default_paths(2500)
+    assert ha.binary_count == 2500 and ha.vec0_count == 2500 and ha.dropped == 0
+
+
+def test_loader_applies_inner_joins(tmp_path):
+    """vec0 rows without an image_embeddings / images partner are not part of the
+    reference's result set (image_database.py:1569-1570)."""
+    rows = synth.unit_rows(300, DIM, 22)
+    db = str(tmp_path / "o.db")
+    synth.write_reference_db(db, rows, drop_mapping_for=[3, 100], drop_image_for=[10])
+    h = loader.read_store(db)
+    keep = np.delete(np.arange(300), [3, 10, 100])
+    assert h.dropped == 3 and h.vec0_count == 300
+    assert np.array_equal(h.rowids, keep + 1)
+    assert np.array_equal(h.rows, rows[keep])
+    # and that is exactly what SQLite returns for the statement
+    conn, _ = sql_harness.connect(db)
+    got = sql_harness.run_statement(conn, rows[0], -1, with_rowid=True)
+    assert sorted(r[1] for r in got) == (keep + 1).tolist()
+    conn.close()
+
+
+def test_loader_incremental(tmp_path):
+    rows = synth.unit_rows(120, DIM, 23)
+    db = str(tmp_path / "i.db")
+    synth.write_reference_db(db, rows)
+    h = loader.read_store(db, min_rowid=100)
+    assert np.array_equal(h.rowids, np.arange(101, 121)) and np.array_equal(h.rows, rows[100:])
+
+
+def test_loader_rejects_wrong_dim(tmp_path):
+    rows = synth.unit_rows(10, 64, 24)
+    db = str(tmp_path / "d.db")
+    synth.write_reference_db(db, rows)
+    with pytest.raises(ValueError):
+        loader.read_store(db, expect_dim=DIM)
+    assert loader.read_store(db).dim == 64
+
+
+@pytest.mark.parametrize("folders", [
+    ["/data/photos/b"], ["/DATA/Photos/A/"], ["/data/100%_done"], ["/data/100x_done", "/data/scans"],
+    ["/data/ph"], ["/nope"], ["/data/photos/é"], ["/data/photos/É"], ["/data/back\\slash"],
+])
+def test_folder_mask_equals_sqlite_like(tmp_path, folders):
+    """like_prefix_mask == the rows SQLite's LIKE ... ESCAPE admits for the reference's
+    pattern construction (ASCII-only case folding, escaped % and _)."""
+    paths = synth.default_paths(60)
+    paths[0] = "/data/100%_done/x.jpg"
+    paths[1] = "/data/100x_done/x.jpg"
+    paths[2] = "/data/100%xdone/x.jpg"
+    paths[3] = "/data/photos/é/x.jpg"
+    paths[4] = "/data/photos/É/x.jpg"
+    paths[5] = "/DATA/PHOTOS/B/upper.jpg"
+    paths[6] = "/data/photos/bb/x.jpg"
+    paths[7] = "/data/back\\slash/x.jpg"
+    paths[8] = "/data/ph"
+    db = str(tmp_path / "f.db")
+    conn = sqlite3.connect(db)
+    conn.execute("CREATE TABLE images (id INTEGER PRIMARY KEY, file_path TEXT)")
+    conn.executemany("INSERT INTO images VALUES (?, ?)", list(enumerate(paths)))
+    where, params = sql_harness.where_clause_and_params(folders)
+    got = {r[0] for r in conn.execute(f"SELECT i.id FROM images i {where}", params)}
+    conn.close()
+    mask = database.like_prefix_mask(paths, folders)
+    assert set(np.nonzero(mask)[0].tolist()) == got
+
+
+def test_duplicate_filter_equals_reference_restatement(tmp_path):
+    rng = np.random.default_rng(31)
+    rows = synth.unit_rows(400, DIM, 30)
+    # families of near-identical sign codes: flip 0..4 signs of a parent row
+    for child, parent, flips in [(10, 3, 0), (11, 3, 1), (12, 3, 2), (13, 3, 3), (50, 40, 2), (51, 50, 2),
+                                 (52, 51, 2), (90, 80, 4)]:
+        v = rows[parent].copy()
+        idx = rng.choice(DIM, size=flips, replace=False)
+        v[idx] = -v[idx]
+        rows[child] = v
+    db = str(tmp_path / "dup.db")
+    synth.write_reference_db(db, rows)
+    paths = synth.default_paths(400)
+    for trial in range(20):
+        pick = rng.permutation(120)[:40]
+        sims = np.sort(rng.random(40))[::-1]
+        if trial % 3 == 0:
+            sims[5:9] = sims[5]                       # equal similarities
+        if trial % 4 == 0:
+            sims = rng.random(40)                     # unsorted input: exercises the replace branch
+        results = [(paths[p], float(s)) for p, s in zip(pick, sims)]
+        if trial % 5 == 0:
+            results.append(("/not/in/db.jpg", 0.5))
+        codes = {paths[p]: (rows[p] >= 0).astype(np.uint8) for p in pick}
+        mine = database.filter_duplicates(list(results), codes, 2)
+        theirs = sql_harness.reference_filter_duplicates(db, list(results), 2)
+        assert mine == theirs
+
+
+def test_unit_rows_are_unit_and_seeded():
+    a, b = synth.unit_rows(50, DIM, 1), synth.unit_rows(50, DIM, 1)
+    assert np.array_equal(a, b)
+    assert np.allclose(np.linalg.norm(a, axis=1), 1.0, atol=1e-6)
+    h = synth.fp16_normalised(a)
+    assert np.all(np.abs(np.linalg.norm(h, axis=1) - 1.0) < 1e-3)
