@@ -13,6 +13,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -61,6 +62,13 @@ struct clipdb_ctx {
     Buffer d_blend_in, d_blend_flags;
     Buffer pinned;      // host staging (inputs, then results)
     Buffer pinned_aux;  // host staging for the blended query read-back
+
+    // scan-kernel event timing (clipdb_profile)
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;   // pairs: [2i] start, [2i+1] stop
+    size_t ev_used = 0;                 // events handed out since the last read
+    double prof_ms = 0.0;
+    int64_t prof_scans = 0;
 
     // options
     int64_t scan_variant = 0;  // 0 auto (TMA ring when dim == 1152), 1 TMA ring, 2 direct loads
@@ -205,6 +213,35 @@ int alloc_store(clipdb_ctx *c, int64_t cap, int32_t dim, bool with_ids) {
     return CLIPDB_OK;
 }
 
+// ---- scan-kernel event timing -----------------------------------------------------
+
+constexpr size_t PROFILE_MAX_PENDING = 4096;  // event pairs kept before folding into the totals
+
+int profile_fold(clipdb_ctx *c) {
+    if (c->ev_used == 0) return CLIPDB_OK;
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i + 1 < c->ev_used; i += 2) {
+        float ms = 0.f;
+        CU_TRY(c, cudaEventElapsedTime(&ms, c->ev_pool[i], c->ev_pool[i + 1]));
+        c->prof_ms += ms;
+        c->prof_scans++;
+    }
+    c->ev_used = 0;
+    return CLIPDB_OK;
+}
+
+int profile_mark(clipdb_ctx *c, bool start) {
+    if (!c->profiling) return CLIPDB_OK;
+    if (start && c->ev_used + 2 > 2 * PROFILE_MAX_PENDING) RC_TRY(profile_fold(c));
+    if (c->ev_used >= c->ev_pool.size()) {
+        cudaEvent_t e;
+        CU_TRY(c, cudaEventCreate(&e));
+        c->ev_pool.push_back(e);
+    }
+    CU_TRY(c, cudaEventRecord(c->ev_pool[c->ev_used++], c->stream));
+    return CLIPDB_OK;
+}
+
 // ---- kernel dispatch ------------------------------------------------------------
 
 template <int KPL, int METRIC, bool ALL>
@@ -244,7 +281,17 @@ int launch_scan_ldg(clipdb_ctx *c, const ScanArgs &a, int grid) {
 }
 
 template <int KPL, bool ALL>
+int launch_scan_metric_raw(clipdb_ctx *c, const ScanArgs &a, int metric, bool tma, int grid);
+
+template <int KPL, bool ALL>
 int launch_scan_metric(clipdb_ctx *c, const ScanArgs &a, int metric, bool tma, int grid) {
+    RC_TRY(profile_mark(c, true));
+    RC_TRY((launch_scan_metric_raw<KPL, ALL>(c, a, metric, tma, grid)));
+    return profile_mark(c, false);
+}
+
+template <int KPL, bool ALL>
+int launch_scan_metric_raw(clipdb_ctx *c, const ScanArgs &a, int metric, bool tma, int grid) {
     if (tma) {
         return metric == CLIPDB_METRIC_COSINE ? launch_scan_tma<KPL, METRIC_COSINE, ALL>(c, a, grid)
                                               : launch_scan_tma<KPL, METRIC_L2, ALL>(c, a, grid);
@@ -511,6 +558,7 @@ void clipdb_destroy(clipdb_ctx *c) {
         for (Buffer *b : bufs) free_buffer(*b);
         if (c->pinned.p) cudaFreeHost(c->pinned.p);
         if (c->pinned_aux.p) cudaFreeHost(c->pinned_aux.p);
+        for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
         if (c->own_stream) cudaStreamDestroy(c->own_stream);
         cudaGetLastError();
     }
@@ -523,6 +571,7 @@ int clipdb_set_stream(clipdb_ctx *c, void *cuda_stream) {
     if (!c) return CLIPDB_ERR_INVALID;
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
+    RC_TRY(profile_fold(c));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
     return CLIPDB_OK;
@@ -843,13 +892,18 @@ int clipdb_blend_search(clipdb_ctx *c, const float *e1, const float *e2, double 
     return CLIPDB_OK;
 }
 
-int clipdb_merge_device(clipdb_ctx *c, const float *d_dist, const int64_t *d_rowids,
-                        const int32_t *d_counts, int32_t lists, int32_t k, float *d_out_dist,
-                        int64_t *d_out_rowids, int32_t *d_out_n) {
+int clipdb_merge_strided_device(clipdb_ctx *c, const void *d_dist, int64_t dist_stride,
+                                const void *d_rowids, int64_t rowid_stride, const void *d_counts,
+                                int64_t count_stride, int32_t lists, int32_t k, float *d_out_dist,
+                                int64_t *d_out_rowids, int32_t *d_out_n) {
     if (!c) return CLIPDB_ERR_INVALID;
     std::lock_guard<std::mutex> lk(c->mu);
     if (!d_dist || !d_rowids || !d_counts || !d_out_dist || !d_out_rowids || !d_out_n || lists <= 0 || k < 0)
         return fail(c, CLIPDB_ERR_INVALID, "merge: bad argument");
+    if (dist_stride % 4 || rowid_stride % 8 || count_stride % 4 ||
+        (reinterpret_cast<uintptr_t>(d_rowids) & 7) || (reinterpret_cast<uintptr_t>(d_dist) & 3) ||
+        (reinterpret_cast<uintptr_t>(d_counts) & 3))
+        return fail(c, CLIPDB_ERR_INVALID, "merge: misaligned list layout");
     DeviceGuard g(c->device);
     if (k == 0) {
         CU_TRY(c, cudaMemsetAsync(d_out_n, 0, sizeof(int32_t), c->stream));
@@ -868,10 +922,45 @@ int clipdb_merge_device(clipdb_ctx *c, const float *d_dist, const int64_t *d_row
             configured_device = c->device;
         }
     }
-    merge_shards_kernel<<<1, MERGE_THREADS, smem, c->stream>>>(d_dist, d_rowids, d_counts, lists, k,
-                                                               d_out_dist, d_out_rowids, d_out_n);
+    ShardLists in{};
+    in.dist = static_cast<const uint8_t *>(d_dist);
+    in.rowids = static_cast<const uint8_t *>(d_rowids);
+    in.counts = static_cast<const uint8_t *>(d_counts);
+    in.dist_stride = dist_stride;
+    in.rowid_stride = rowid_stride;
+    in.count_stride = count_stride;
+    merge_shards_kernel<<<1, MERGE_THREADS, smem, c->stream>>>(in, lists, k, d_out_dist, d_out_rowids, d_out_n);
     CU_TRY(c, cudaGetLastError());
     c->launches++;
+    return CLIPDB_OK;
+}
+
+int clipdb_merge_device(clipdb_ctx *c, const float *d_dist, const int64_t *d_rowids,
+                        const int32_t *d_counts, int32_t lists, int32_t k, float *d_out_dist,
+                        int64_t *d_out_rowids, int32_t *d_out_n) {
+    return clipdb_merge_strided_device(c, d_dist, static_cast<int64_t>(k) * sizeof(float), d_rowids,
+                                       static_cast<int64_t>(k) * sizeof(int64_t), d_counts,
+                                       sizeof(int32_t), lists, k, d_out_dist, d_out_rowids, d_out_n);
+}
+
+int clipdb_profile(clipdb_ctx *c, int32_t enable) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    RC_TRY(profile_fold(c));
+    c->profiling = enable != 0;
+    c->prof_ms = 0.0;
+    c->prof_scans = 0;
+    return CLIPDB_OK;
+}
+
+int clipdb_profile_read(clipdb_ctx *c, double *scan_ms_total, int64_t *scans) {
+    if (!c || !scan_ms_total || !scans) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    RC_TRY(profile_fold(c));
+    *scan_ms_total = c->prof_ms;
+    *scans = c->prof_scans;
     return CLIPDB_OK;
 }
 

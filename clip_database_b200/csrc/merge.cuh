@@ -77,10 +77,29 @@ __global__ void decode_sorted_kernel(const uint64_t *__restrict__ keys, long lon
 
 // Shard merge (multi-GPU): `lists` sorted result lists of k (distance, rowid)
 // pairs, shard order = rowid order.  Key = (distance, list, position), which is
-// (distance, rowid) because shards are contiguous rowid ranges.
+// (distance, rowid) because shards are contiguous rowid ranges.  Each list l
+// lives at base + l * stride (bytes) for the three arrays, so the same kernel
+// reads separate [lists][k] arrays or the packed per-rank records an NCCL
+// all-gather delivers.
+struct ShardLists {
+    const uint8_t *dist;    // float32[k] per list
+    const uint8_t *rowids;  // int64[k] per list
+    const uint8_t *counts;  // int32 per list
+    long long dist_stride, rowid_stride, count_stride;
+};
+
+__device__ __forceinline__ const float *shard_dist(const ShardLists &s, int l) {
+    return reinterpret_cast<const float *>(s.dist + static_cast<long long>(l) * s.dist_stride);
+}
+__device__ __forceinline__ const int64_t *shard_rowids(const ShardLists &s, int l) {
+    return reinterpret_cast<const int64_t *>(s.rowids + static_cast<long long>(l) * s.rowid_stride);
+}
+__device__ __forceinline__ int shard_count(const ShardLists &s, int l) {
+    return *reinterpret_cast<const int32_t *>(s.counts + static_cast<long long>(l) * s.count_stride);
+}
+
 __global__ void __launch_bounds__(MERGE_THREADS) merge_shards_kernel(
-    const float *__restrict__ dist, const int64_t *__restrict__ rowids,
-    const int32_t *__restrict__ counts, int lists, int k, float *__restrict__ out_dist,
+    const ShardLists in, int lists, int k, float *__restrict__ out_dist,
     int64_t *__restrict__ out_rowids, int32_t *__restrict__ out_n) {
     extern __shared__ __align__(16) uint8_t merge_smem[];
     uint64_t *s = reinterpret_cast<uint64_t *>(merge_smem);
@@ -91,8 +110,10 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_shards_kernel(
         uint64_t key = KEY_EMPTY;
         if (i < total) {
             const int l = i / k, p = i - l * k;
-            const float d = dist[i];
-            if (p < counts[l] && d == d) key = make_key(d, static_cast<uint32_t>(i));
+            if (p < shard_count(in, l)) {
+                const float d = shard_dist(in, l)[p];
+                if (d == d) key = make_key(d, static_cast<uint32_t>(i));
+            }
         }
         s[i] = key;
     }
@@ -102,9 +123,10 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_shards_kernel(
         const int i = base + tid;
         const bool valid = i < k && i < padded && s[i] != KEY_EMPTY;
         if (valid) {
-            const uint32_t src = static_cast<uint32_t>(s[i] & 0xFFFFFFFFull);
-            out_dist[i] = dist[src];
-            out_rowids[i] = rowids[src];
+            const int src = static_cast<int>(s[i] & 0xFFFFFFFFull);
+            const int l = src / k, p = src - l * k;
+            out_dist[i] = shard_dist(in, l)[p];
+            out_rowids[i] = shard_rowids(in, l)[p];
         }
         found += __syncthreads_count(valid);
     }

@@ -118,6 +118,17 @@ class GpuIndex:
     def synchronize(self) -> None:
         self._check(self._L.clipdb_synchronize(self._ctx))
 
+    def profile(self, enable: bool) -> None:
+        """Bracket every scan kernel with CUDA events on the launching stream."""
+        self._check(self._L.clipdb_profile(self._ctx, int(bool(enable))))
+
+    def profile_read(self) -> Tuple[float, int]:
+        """(summed scan-kernel milliseconds, number of scans) since ``profile(True)``."""
+        ms = ctypes.c_double(0.0)
+        n = ctypes.c_int64(0)
+        self._check(self._L.clipdb_profile_read(self._ctx, ctypes.byref(ms), ctypes.byref(n)))
+        return float(ms.value), int(n.value)
+
     # ---- row store ------------------------------------------------------------------
     def load(self, rows, rowids=None) -> None:
         """Copy ``rows`` (numpy ``[n, dim]`` float32, or a torch tensor on any device)
@@ -282,6 +293,26 @@ class GpuIndex:
         ptr = lambda t: ctypes.c_void_p(t.data_ptr() if t is not None else 0)
         self._check(self._L.clipdb_blend_device(self._ctx, ptr(d_e1), ptr(d_e2), ptr(d_w), ptr(d_negs),
                                                 ptr(d_neg_w), n_neg, dim, batch, ptr(d_out), ptr(d_flags)))
+
+    def merge_records_device(self, records, k: int, off_rowids: int, off_dist: int, off_count: int,
+                             out_dist, out_rowids, out_n) -> None:
+        """Async shard merge of ``records``: a uint8 CUDA tensor ``[lists, record_bytes]`` holding
+        one packed per-rank result each (see ``sharded.RecordLayout``)."""
+        lists, rec = records.shape
+        base = records.data_ptr()
+        self._check(self._L.clipdb_merge_strided_device(
+            self._ctx, ctypes.c_void_p(base + off_dist), rec, ctypes.c_void_p(base + off_rowids), rec,
+            ctypes.c_void_p(base + off_count), rec, lists, int(k), ctypes.c_void_p(out_dist.data_ptr()),
+            ctypes.c_void_p(out_rowids.data_ptr()), ctypes.c_void_p(out_n.data_ptr())))
+
+    def search_into_record(self, d_query, k: int, record, off_rowids: int, off_dist: int, off_count: int,
+                           off_nan: int, metric="cosine", use_mask: bool = False) -> None:
+        """Async single-query search whose outputs land inside ``record`` (uint8 CUDA tensor)."""
+        base = record.data_ptr()
+        self._check(self._L.clipdb_search_device(
+            self._ctx, ctypes.c_void_p(d_query.data_ptr()), 1, int(k), _metric(metric), int(bool(use_mask)),
+            ctypes.c_void_p(base + off_rowids), ctypes.c_void_p(base + off_dist),
+            ctypes.c_void_p(base + off_count), ctypes.c_void_p(base + off_nan)))
 
     def merge_device(self, d_dist, d_rowids, d_counts, k: int, out_dist, out_rowids, out_n) -> None:
         """Async shard merge of ``[lists, k]`` gathered results (clipdb_merge_device)."""

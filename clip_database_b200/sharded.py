@@ -1,0 +1,136 @@
+"""Row-sharded multi-GPU search (no reference equivalent — the
+reference is one process, one thread).
+
+The embedding matrix is split into contiguous rowid ranges, one per rank / GPU.
+Every rank scans its shard for the (replicated) query and produces a local top-k;
+the only exchange is ONE all-gather of a packed k-entry record per rank
+(8 + 12k + 4 bytes, 252 B at k = 20), after which every rank merges the G lists
+with the same (distance, rowid) order.  Because shards are contiguous in rowid
+order, (distance, shard, position) == (distance, rowid), so the sharded answer is
+bit-identical to the unsharded one.
+
+``ShardedIndex`` is the orchestration (record layout, collective, merge order);
+the per-rank work is delegated to a backend.  The product backend is
+``CudaShardBackend`` (CUDA kernels through the C ABI, NCCL collective); tests
+drive the same orchestration over gloo with a CPU stand-in backend.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+
+def shard_bounds(n_total: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous row ranges [lo, hi) in scan order, sizes differing by at most one."""
+    return [(n_total * g // world, n_total * (g + 1) // world) for g in range(world)]
+
+
+@dataclass(frozen=True)
+class RecordLayout:
+    """Byte layout of one rank's packed result: nan(int64) | rowids(int64[k]) |
+    dist(float32[k]) | count(int32) | pad to 16."""
+    k: int
+
+    @property
+    def off_nan(self) -> int:
+        return 0
+
+    @property
+    def off_rowids(self) -> int:
+        return 8
+
+    @property
+    def off_dist(self) -> int:
+        return 8 + 8 * self.k
+
+    @property
+    def off_count(self) -> int:
+        return 8 + 12 * self.k
+
+    @property
+    def nbytes(self) -> int:
+        return (8 + 12 * self.k + 4 + 15) // 16 * 16
+
+
+class CudaShardBackend:
+    """Per-rank work on the GPU: local scan + top-k into a record, merge of gathered records."""
+
+    def __init__(self, index):
+        import torch
+        self.index = index
+        self.torch = torch
+        self.device = torch.device("cuda", index.device)
+        index.use_torch_stream()
+
+    def new_buffer(self, nbytes: int):
+        return self.torch.zeros(nbytes, dtype=self.torch.uint8, device=self.device)
+
+    def to_device(self, query: np.ndarray):
+        return self.torch.from_numpy(np.ascontiguousarray(query, dtype=np.float32)).to(self.device, non_blocking=True)
+
+    def local_search(self, d_query, k: int, record, lay: RecordLayout, use_mask: bool) -> None:
+        self.index.search_into_record(d_query, k, record, lay.off_rowids, lay.off_dist, lay.off_count,
+                                      lay.off_nan, use_mask=use_mask)
+
+    def merge(self, gathered, k: int, lay: RecordLayout, out_dist, out_rowids, out_n) -> None:
+        self.index.merge_records_device(gathered, k, lay.off_rowids, lay.off_dist, lay.off_count,
+                                        out_dist, out_rowids, out_n)
+
+    def new_outputs(self, k: int):
+        t = self.torch
+        return (t.empty(max(k, 1), dtype=t.float32, device=self.device),
+                t.empty(max(k, 1), dtype=t.int64, device=self.device),
+                t.zeros(1, dtype=t.int32, device=self.device))
+
+
+class ShardedIndex:
+    """One rank's view of a row-sharded store."""
+
+    def __init__(self, backend, group=None):
+        import torch.distributed as dist
+        self.backend = backend
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._k = None
+
+    def _prepare(self, k: int) -> None:
+        if self._k == k:
+            return
+        self.layout = RecordLayout(k)
+        self.record = self.backend.new_buffer(self.layout.nbytes)
+        self.gathered = self.backend.new_buffer(self.layout.nbytes * self.world).view(self.world, self.layout.nbytes)
+        self.out_dist, self.out_rowids, self.out_n = self.backend.new_outputs(k)
+        self._k = k
+
+    def search_device(self, d_query, k: int, use_mask: bool = False):
+        """Enqueue local scan -> all-gather -> merge.  Returns device tensors
+        (dist[k], rowids[k], n[1]) valid after the stream / collective completes;
+        every rank holds the same merged answer."""
+        self._prepare(k)
+        self.backend.local_search(d_query, k, self.record, self.layout, use_mask)
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(self.gathered.view(-1), self.record, group=self.group)
+            src = self.gathered
+        else:
+            src = self.record.view(1, -1)
+        self.backend.merge(src, k, self.layout, self.out_dist, self.out_rowids, self.out_n)
+        return self.out_dist, self.out_rowids, self.out_n
+
+    def nan_rows(self) -> int:
+        """Admitted rows with NaN distance over all shards for the last search."""
+        src = self.gathered if self.world > 1 else self.record.view(1, -1)
+        return int(src[:, :8].contiguous().view(-1).cpu().numpy().view(np.int64).sum())
+
+    def search(self, query: np.ndarray, k: int, use_mask: bool = False) -> Tuple[np.ndarray, np.ndarray]:
+        """Host query in, host (rowids, distances) out; synchronous."""
+        if k <= 0:
+            return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.float32)
+        d_query = self.backend.to_device(query)
+        dist, rowids, n = self.search_device(d_query, k, use_mask)
+        m = int(n.cpu()[0])
+        # copies: the output tensors are reused by the next search
+        return rowids[:m].cpu().numpy().copy(), dist[:m].cpu().numpy().copy()

@@ -169,6 +169,22 @@ int clipdb_merge_device(clipdb_ctx *ctx, const float *d_dist, const int64_t *d_r
                         const int32_t *d_counts, int32_t lists, int32_t k,
                         float *d_out_dist, int64_t *d_out_rowids, int32_t *d_out_n);
 
+/* Same with explicit byte strides between consecutive lists, so the lists can
+ * sit inside packed per-rank records (one NCCL all-gather instead of three). */
+int clipdb_merge_strided_device(clipdb_ctx *ctx, const void *d_dist, int64_t dist_stride,
+                                const void *d_rowids, int64_t rowid_stride,
+                                const void *d_counts, int64_t count_stride,
+                                int32_t lists, int32_t k,
+                                float *d_out_dist, int64_t *d_out_rowids, int32_t *d_out_n);
+
+/* ---- measurement ------------------------------------------------------------
+ * With profiling enabled every scan kernel (the dominant, HBM-bound launch) is
+ * bracketed by CUDA events on the launching stream; clipdb_profile_read syncs
+ * the stream and returns the summed scan-kernel time and the number of scans
+ * since profiling was (re)enabled.  bench.py derives roofline.achieved from it. */
+int clipdb_profile(clipdb_ctx *ctx, int32_t enable);
+int clipdb_profile_read(clipdb_ctx *ctx, double *scan_ms_total, int64_t *scans);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,108 @@
+"""The drop-in ``ImageDatabase.search()`` (GPU path) against the outputs of the
+reference's own ``search()`` recorded in tests/golden/reference_search.json."""
+import numpy as np
+import pytest
+
+from clip_database_b200 import synth
+from oracle import blend as oblend
+from oracle import ref
+
+import golden_cases
+from conftest import have_gpu, tol
+from test_golden_cpu import case_names
+
+pytestmark = pytest.mark.gpu
+
+
+class TableEmbedder:
+    """Stands in for the SigLIP model: query string -> seeded vector."""
+
+    def __init__(self, vectors):
+        self.vectors = vectors
+
+    def text(self, query):
+        return self.vectors[query]
+
+    def image(self, path):
+        return self.vectors[path]
+
+
+@pytest.mark.parametrize("name", case_names())
+def test_search_reproduces_reference_output(golden, name, tmp_path):
+    assert have_gpu(), "GPU tests selected but no CUDA device is visible"
+    from clip_database_b200 import ImageDatabase
+    case = next(c for c in golden["cases"] if c["name"] == name)
+    rows, paths, kwargs, vectors, drop_m, drop_i = golden_cases.inputs_for(case)
+    db_path = str(tmp_path / (name + ".db"))
+    synth.write_reference_db(db_path, rows, paths, drop_mapping_for=drop_m, drop_image_for=drop_i)
+    db = ImageDatabase(db_path, device=0, embedder=TableEmbedder(vectors))
+    try:
+        results = db.search("q1", **kwargs)
+    finally:
+        db.close()
+    pos = {p: i for i, p in enumerate(paths)}
+    got_pos = np.array([pos[p] for p, _ in results], dtype=np.int64)
+    got_sim = np.array([s for _, s in results], dtype=np.float64)
+    exp_pos = np.array(case["expected_positions"], dtype=np.int64)
+    exp_sim = np.array(case["expected_similarities"], dtype=np.float64)
+    assert got_pos.shape == exp_pos.shape
+    assert np.all(np.abs(got_sim - exp_sim) <= tol(1.0 - exp_sim))
+    diff = got_pos != exp_pos
+    if diff.any():
+        # ids may differ only where the reference's own distances tie within the tolerance
+        e1, e2, weights, negs, ws = golden_cases.embedding_call(kwargs, vectors)
+        q = oblend.compose_query(e1, e2, weights, negs, ws)
+        own = 1.0 - ref.distances(rows[got_pos[diff]], q).astype(np.float64)
+        assert np.all(np.abs(own - exp_sim[diff]) <= tol(1.0 - exp_sim[diff])), name
+
+
+def test_nan_policy_exclude(tmp_path):
+    from clip_database_b200 import ImageDatabase
+    rows = synth.unit_rows(2000, 1152, 1)
+    rows[5] = 0
+    q = synth.unit_rows(1, 1152, 2)[0]
+    db_path = str(tmp_path / "nan.db")
+    synth.write_reference_db(db_path, rows)
+    a = ImageDatabase(db_path, nan_policy="reference")
+    b = ImageDatabase(db_path, nan_policy="exclude")
+    try:
+        assert a.search_embedding(q, k=10, show_duplicates=True) == []
+        got = b.search_embedding(q, k=10, show_duplicates=True)
+        _, od, oseq, _ = ref.knn(rows, q, 10)
+        paths = synth.default_paths(2000)
+        assert [p for p, _ in got] == [paths[s] for s in oseq]
+    finally:
+        a.close()
+        b.close()
+
+
+def test_refresh_appends_new_rows(tmp_path):
+    import sqlite3
+    from clip_database_b200 import ImageDatabase
+    rows = synth.unit_rows(3000, 1152, 3)
+    db_path = str(tmp_path / "grow.db")
+    synth.write_reference_db(db_path, rows[:2000])
+    db = ImageDatabase(db_path)
+    try:
+        q = rows[2500]
+        first = db.search_embedding(q, k=5, show_duplicates=True)
+        assert first[0][1] < 0.5
+        # the scanner appends 1000 more images (same writer layout)
+        conn = sqlite3.connect(db_path)
+        paths = synth.default_paths(3000)
+        for i in range(2000, 3000):
+            conn.execute("INSERT INTO images (id, file_path, last_modified, file_hash) VALUES (?, ?, ?, ?)",
+                         (i + 1, paths[i], 1.0, "h"))
+            conn.execute("INSERT INTO vec0 (rowid, embedding) VALUES (?, ?)", (i + 1, rows[i].tobytes()))
+            conn.execute("INSERT INTO image_embeddings (rowid, image_id) VALUES (?, ?)", (i + 1, i + 1))
+            conn.execute("INSERT INTO binary_embeddings (image_id, embedding) VALUES (?, ?)",
+                         (i + 1, (rows[i] >= 0).astype(np.uint8).tobytes()))
+        conn.commit()
+        conn.close()
+        assert db.refresh() == 1000
+        second = db.search_embedding(q, k=5, show_duplicates=True)
+        assert second[0][0] == paths[2500] and abs(second[0][1] - 1.0) < 1e-6
+        _, od, oseq, _ = ref.knn(rows, q, 5)
+        assert [p for p, _ in second] == [paths[s] for s in oseq]
+    finally:
+        db.close()
