@@ -305,13 +305,24 @@ def main():
         d_blend = torch.empty((1, DIM), dtype=torch.float32, device=device)
     d_q = torch.from_numpy(host_q).to(device)
 
+    o_ids = torch.empty((1, k), dtype=torch.int64, device=device)
+    o_dist = torch.empty((1, k), dtype=torch.float32, device=device)
+    o_n = torch.zeros(1, dtype=torch.int32, device=device)
+    o_nan = torch.zeros(1, dtype=torch.int64, device=device)
+
+    def search_dev(q_vec):
+        if world == 1:
+            idx.search_device(q_vec.view(1, -1), k, o_ids, o_dist, o_n, o_nan)
+        else:
+            sharded.search_device(q_vec, k)     # local scan + all-gather + merge
+
     def step_device(i):
         j = i % n_q
         if args.workload == "blend":
             idx.blend_device(d_q[j:j + 1], d_q2[j:j + 1], d_w[j:j + 1], d_neg[j:j + 1], d_nw[j:j + 1], d_blend)
-            sharded.search_device(d_blend[0], k)
+            search_dev(d_blend[0])
         else:
-            sharded.search_device(d_q[j], k)
+            search_dev(d_q[j])
 
     def step_e2e(i):
         j = i % n_q

@@ -34,6 +34,7 @@ SIGNATURES = [
     ("clipdb_destroy", None, [_CTX]),
     ("clipdb_last_error", c_char_p, [_CTX]),
     ("clipdb_set_stream", c_int, [_CTX, c_void_p]),
+    ("clipdb_use_own_stream", c_int, [_CTX]),
     ("clipdb_synchronize", c_int, [_CTX]),
     ("clipdb_set_option", c_int, [_CTX, c_char_p, c_int64]),
     ("clipdb_get_option", c_int, [_CTX, c_char_p, _I64]),

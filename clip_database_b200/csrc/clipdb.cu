@@ -573,7 +573,17 @@ int clipdb_set_stream(clipdb_ctx *c, void *cuda_stream) {
     DeviceGuard g(c->device);
     RC_TRY(profile_fold(c));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
-    c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+    c->stream = static_cast<cudaStream_t>(cuda_stream);
+    return CLIPDB_OK;
+}
+
+int clipdb_use_own_stream(clipdb_ctx *c) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    RC_TRY(profile_fold(c));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    c->stream = c->own_stream;
     return CLIPDB_OK;
 }
 

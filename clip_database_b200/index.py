@@ -108,8 +108,12 @@ class GpuIndex:
         return int(v.value)
 
     def set_stream(self, cuda_stream: Optional[int]) -> None:
-        """Run on the given ``cudaStream_t`` (an int handle); ``None`` = the context's own."""
-        self._check(self._L.clipdb_set_stream(self._ctx, ctypes.c_void_p(cuda_stream or 0)))
+        """Run on the given ``cudaStream_t`` (an int handle; 0 = CUDA's legacy default stream);
+        ``None`` = back to the context's own stream."""
+        if cuda_stream is None:
+            self._check(self._L.clipdb_use_own_stream(self._ctx))
+        else:
+            self._check(self._L.clipdb_set_stream(self._ctx, ctypes.c_void_p(int(cuda_stream))))
 
     def use_torch_stream(self) -> None:
         import torch

@@ -61,9 +61,11 @@ void clipdb_destroy(clipdb_ctx *ctx);
 const char *clipdb_last_error(const clipdb_ctx *ctx);
 
 /* Run on a caller-provided CUDA stream (cudaStream_t passed as void*), e.g.
- * torch's current stream so torch.cuda.Event brackets the kernels.  NULL
- * restores the context's own stream. */
+ * torch's current stream so torch.cuda.Event brackets the kernels.  NULL is
+ * CUDA's legacy default stream (torch's default).  clipdb_use_own_stream
+ * returns to the non-blocking stream the context created for itself. */
 int clipdb_set_stream(clipdb_ctx *ctx, void *cuda_stream);
+int clipdb_use_own_stream(clipdb_ctx *ctx);
 int clipdb_synchronize(clipdb_ctx *ctx);
 
 /* Tuning knobs for experiments ("scan_variant", "scan_ctas", ...).  Unknown
