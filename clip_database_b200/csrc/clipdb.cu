@@ -57,7 +57,7 @@ struct clipdb_ctx {
     int64_t mask_words = 0;
 
     // workspaces (grown on demand)
-    Buffer cand_a, cand_b, nan_ctr, all_keys_a, all_keys_b, cub_tmp;
+    Buffer cand_a, cand_b, nan_ctr, tile_ctr, all_keys_a, all_keys_b, cub_tmp;
     Buffer d_query, d_out_rowids, d_out_dist, d_out_n, d_out_nan;
     Buffer d_blend_in, d_blend_flags;
     Buffer pinned;      // host staging (inputs, then results)
@@ -75,6 +75,9 @@ struct clipdb_ctx {
     int64_t scan_ctas = 0;     // 0 = one per SM (TMA) / ldg_ctas_per_sm per SM (direct)
     int64_t ldg_ctas_per_sm = 4;
     int64_t evict_first = 1;
+    int64_t scan_cfg = 0;      // ring shape (ScanCfg0..4); shapes other than 0 exist for k <= 32 cosine only
+    int64_t scan_assign = 2;   // SCAN_ASSIGN_* (dynamic: +5 % over static interleaving, profiles/r01_sweep2.json)
+    int64_t scan_chunk = 4;    // tiles per atomicAdd (dynamic assignment)
 };
 
 namespace {
@@ -244,19 +247,32 @@ int profile_mark(clipdb_ctx *c, bool start) {
 
 // ---- kernel dispatch ------------------------------------------------------------
 
-template <int KPL, int METRIC, bool ALL>
-int launch_scan_tma(clipdb_ctx *c, const ScanArgs &a, int grid) {
-    auto kern = scan_tma_kernel<KPL, METRIC, ALL>;
+template <typename CFG, int KPL, int METRIC, bool ALL>
+int launch_scan_tma_cfg(clipdb_ctx *c, const ScanArgs &a, int grid) {
+    auto kern = scan_tma_kernel<CFG, KPL, METRIC, ALL>;
     static thread_local int configured_device = -1;  // attribute is per device & per instantiation
     if (configured_device != c->device) {
-        CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       SCAN_SMEM_BYTES));
+        CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::SMEM_BYTES));
         configured_device = c->device;
     }
-    kern<<<grid, SCAN_THREADS, SCAN_SMEM_BYTES, c->stream>>>(a);
+    kern<<<grid, CFG::THREADS, CFG::SMEM_BYTES, c->stream>>>(a);
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     return CLIPDB_OK;
+}
+
+template <int KPL, int METRIC, bool ALL>
+int launch_scan_tma(clipdb_ctx *c, const ScanArgs &a, int grid) {
+    if (KPL == 1 && METRIC == METRIC_COSINE && !ALL) {  // experiment shapes
+        switch (c->scan_cfg) {
+            case 1: return launch_scan_tma_cfg<ScanCfg1, 1, METRIC_COSINE, false>(c, a, grid);
+            case 2: return launch_scan_tma_cfg<ScanCfg2, 1, METRIC_COSINE, false>(c, a, grid);
+            case 3: return launch_scan_tma_cfg<ScanCfg3, 1, METRIC_COSINE, false>(c, a, grid);
+            case 4: return launch_scan_tma_cfg<ScanCfg4, 1, METRIC_COSINE, false>(c, a, grid);
+            default: break;
+        }
+    }
+    return launch_scan_tma_cfg<ScanCfg0, KPL, METRIC, ALL>(c, a, grid);
 }
 
 template <int DIM_T, int KPL, int METRIC, bool ALL>
@@ -339,6 +355,13 @@ int search_one(clipdb_ctx *c, const float *d_query, int k, int metric, bool use_
     a.ld = c->ld;
     a.k = static_cast<int>(kk);
     a.evict_first = static_cast<int>(c->evict_first);
+    a.assign = static_cast<int>(c->scan_assign);
+    a.chunk_tiles = static_cast<int>(c->scan_chunk);
+    if (tma && a.assign == SCAN_ASSIGN_DYNAMIC) {
+        RC_TRY(ensure_device(c, c->tile_ctr, sizeof(unsigned int)));
+        a.tile_counter = static_cast<unsigned int *>(c->tile_ctr.p);
+        CU_TRY(c, cudaMemsetAsync(a.tile_counter, 0, sizeof(unsigned int), c->stream));
+    }
 
     DecodeArgs dec{};
     dec.rowids = c->rowids;
@@ -552,7 +575,7 @@ void clipdb_destroy(clipdb_ctx *c) {
         DeviceGuard g(c->device);
         cudaStreamSynchronize(c->stream);
         release_store(c);
-        Buffer *bufs[] = {&c->cand_a, &c->cand_b, &c->nan_ctr, &c->all_keys_a, &c->all_keys_b,
+        Buffer *bufs[] = {&c->cand_a, &c->cand_b, &c->nan_ctr, &c->tile_ctr, &c->all_keys_a, &c->all_keys_b,
                           &c->cub_tmp, &c->d_query, &c->d_out_rowids, &c->d_out_dist, &c->d_out_n,
                           &c->d_out_nan, &c->d_blend_in, &c->d_blend_flags};
         for (Buffer *b : bufs) free_buffer(*b);
@@ -601,6 +624,9 @@ static int64_t *option_slot(clipdb_ctx *c, const char *name) {
     if (!strcmp(name, "scan_ctas")) return &c->scan_ctas;
     if (!strcmp(name, "ldg_ctas_per_sm")) return &c->ldg_ctas_per_sm;
     if (!strcmp(name, "evict_first")) return &c->evict_first;
+    if (!strcmp(name, "scan_cfg")) return &c->scan_cfg;
+    if (!strcmp(name, "scan_assign")) return &c->scan_assign;
+    if (!strcmp(name, "scan_chunk")) return &c->scan_chunk;
     return nullptr;
 }
 

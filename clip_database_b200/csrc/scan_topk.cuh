@@ -10,12 +10,12 @@
 // Roofline: HBM.  Algorithmic bytes per query = n * dim * 4 (the row store is
 // read exactly once); ~1 flop per byte.  Two variants of the same arithmetic:
 //   scan_tma_kernel  dim == 1152 (the reference's only width).  Persistent,
-//                    one CTA per SM.  One producer thread streams 8-row tiles
-//                    (36,864 B, one contiguous span) global->shared with
-//                    cp.async.bulk (TMA engine, SASS UBLKCP) into a 6-stage
-//                    mbarrier ring; 16 consumer warps (two groups of 8 that
-//                    alternate tiles) read conflict-free LDS.128, reduce with
-//                    warp shuffles and maintain the candidate lists.
+//                    one CTA per SM.  One producer thread streams R-row tiles
+//                    (one contiguous R*4608-B span each) global->shared with
+//                    cp.async.bulk (TMA engine, SASS UBLKCP) into an mbarrier
+//                    ring; groups of R consumer warps take one row each with
+//                    conflict-free LDS.128, reduce with warp shuffles and
+//                    maintain the candidate lists.  Ring shape = ScanCfg<>.
 //   scan_ldg_kernel  any dim (multiple of 4, padded by the loader).  Each warp
 //                    grid-strides over rows with 128-bit streaming loads
 //                    (ld.global.nc.L1::no_allocate), query staged in shared.
@@ -31,15 +31,35 @@ constexpr int METRIC_L2 = 1;
 constexpr int SCAN_DIM = 1152;  // SigLIP 2 SO400M width, `embedding float[1152]` (idb:290-294)
 constexpr int SCAN_CHUNKS = SCAN_DIM / 128;  // float4 chunks per lane per row = 9
 constexpr int SCAN_ROW_BYTES = SCAN_DIM * 4;  // 4608 = 36 x 128 B
-constexpr int SCAN_GROUP_WARPS = 8;           // consumer warps per tile (= rows per tile)
-constexpr int SCAN_GROUPS = 2;                // consumer groups alternating tiles
-constexpr int SCAN_CONSUMER_WARPS = SCAN_GROUP_WARPS * SCAN_GROUPS;
-constexpr int SCAN_TILE_ROWS = SCAN_GROUP_WARPS;
-constexpr int SCAN_STAGES = 6;
-constexpr int SCAN_STAGE_BYTES = SCAN_TILE_ROWS * SCAN_ROW_BYTES;  // 36,864
-constexpr int SCAN_THREADS = (SCAN_CONSUMER_WARPS + 1) * 32;       // + producer warp
-constexpr int SCAN_SMEM_HEADER = 128;                              // barriers
-constexpr int SCAN_SMEM_BYTES = SCAN_SMEM_HEADER + SCAN_STAGES * SCAN_STAGE_BYTES;
+constexpr int SCAN_SMEM_HEADER = 1024;        // barriers + per-stage tile ids
+
+// Shape of the TMA ring.  A tile is R consecutive rows (one contiguous R*4608-byte
+// span, one bulk copy); a group of R consumer warps takes one row each; GROUPS
+// groups work on different tiles at the same time.
+template <int R, int STAGES_, int GROUPS_>
+struct ScanCfg {
+    static constexpr int TILE_ROWS = R;
+    static constexpr int GROUP_WARPS = R;
+    static constexpr int STAGES = STAGES_;
+    static constexpr int GROUPS = GROUPS_;
+    static constexpr int CONSUMER_WARPS = R * GROUPS_;
+    static constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;  // + producer warp
+    static constexpr int STAGE_BYTES = R * SCAN_ROW_BYTES;
+    static constexpr int SMEM_BYTES = SCAN_SMEM_HEADER + STAGES_ * STAGE_BYTES;
+    static_assert(GROUPS_ <= STAGES_, "each group needs its own stage in flight");
+    static_assert(SMEM_BYTES <= 227 * 1024, "ring exceeds shared memory");
+    static_assert(STAGES_ * 20 <= SCAN_SMEM_HEADER, "header too small");
+    static_assert(CONSUMER_WARPS * 32 * 4 * 8 <= STAGES_ * STAGE_BYTES, "sort scratch must fit the ring");
+};
+using ScanCfg0 = ScanCfg<8, 6, 2>;    // 36,864-B tiles, 6 stages, 16 consumer warps (default)
+using ScanCfg1 = ScanCfg<4, 12, 4>;   // 18,432-B tiles, 12 stages
+using ScanCfg2 = ScanCfg<16, 3, 1>;   // 73,728-B tiles, 3 stages
+using ScanCfg3 = ScanCfg<8, 4, 2>;    // as 0 with a shallower ring (147 KB)
+using ScanCfg4 = ScanCfg<8, 6, 1>;    // as 0 with 8 consumer warps
+
+constexpr int SCAN_ASSIGN_INTERLEAVED = 0;  // tile t -> CTA t mod grid
+constexpr int SCAN_ASSIGN_CONTIGUOUS = 1;   // CTA b owns one contiguous span of tiles
+constexpr int SCAN_ASSIGN_DYNAMIC = 2;      // chunks of tiles claimed with atomicAdd
 
 constexpr int LDG_WARPS = 8;
 constexpr int LDG_THREADS = LDG_WARPS * 32;
@@ -57,7 +77,17 @@ struct ScanArgs {
     int k;            // requested k, <= cand_stride
     int cand_stride;  // 32 * KPL
     int evict_first;  // stream rows with an L2 evict-first policy
+    int assign;       // SCAN_ASSIGN_*
+    int chunk_tiles;  // tiles claimed per atomicAdd (dynamic assignment)
+    unsigned int *tile_counter;  // zeroed before the launch (dynamic assignment)
 };
+
+// The exact finish (double sqrt, multiply, divide) is ~70 instructions.  A float32
+// estimate 1 - dot*rsqrt(aMag)*rsqrt(bMag) (4 instructions, |error| < 6e-7 for any
+// input with |cos| <= 1) decides first whether the row can possibly beat the current
+// k-th candidate; only rows within PREFILTER_MARGIN of it pay for the exact finish, so
+// results are unchanged.  NaN estimates compare false and take the exact path (counted).
+constexpr float PREFILTER_MARGIN = 4e-6f;
 
 // ---- per-warp candidate list ---------------------------------------------------
 // 32*KPL slots spread over the lanes' registers, unsorted; `thr` is the largest
@@ -69,11 +99,13 @@ template <int KPL>
 struct WarpTopK {
     uint64_t keys[KPL];
     uint64_t thr;
+    float thr_d;  // distance above which a row cannot enter (thr's distance + PREFILTER_MARGIN)
 
     __device__ __forceinline__ void init(int k, int lane) {
 #pragma unroll
         for (int j = 0; j < KPL; j++) keys[j] = (j * 32 + lane < k) ? KEY_EMPTY : KEY_DISABLED;
         thr = (k > 0) ? KEY_EMPTY : KEY_DISABLED;
+        thr_d = __int_as_float(0x7f800000);  // +inf: everything takes the exact path until the list is full
     }
 
     // key < thr on entry; key is warp-uniform
@@ -93,6 +125,8 @@ struct WarpTopK {
 #pragma unroll
         for (int j = 1; j < KPL; j++) m = umax64(m, keys[j]);
         thr = warp_max_u64(m);
+        thr_d = (thr == KEY_EMPTY) ? __int_as_float(0x7f800000)
+                                   : orderable_f32(static_cast<uint32_t>(thr >> 32)) + PREFILTER_MARGIN;
     }
 
     __device__ __forceinline__ void dump(uint64_t *dst, int lane) const {
@@ -135,9 +169,13 @@ __device__ __forceinline__ void accumulate(const float4 v, const float4 q, float
 
 // Row sums are complete in every lane: turn them into a key and offer it.
 template <int KPL, int METRIC, bool WRITE_ALL>
-__device__ __forceinline__ void offer_row(float s0, float s1, double sqrt_b, long long pos,
-                                          WarpTopK<KPL> &top, unsigned &nan_rows,
+__device__ __forceinline__ void offer_row(float s0, float s1, double sqrt_b, float rsqrt_b,
+                                          long long pos, WarpTopK<KPL> &top, unsigned &nan_rows,
                                           uint64_t *all_keys, int lane) {
+    if (!WRITE_ALL && METRIC == METRIC_COSINE) {
+        const float estimate = fmaf(-s0 * rsqrtf(s1), rsqrt_b, 1.0f);
+        if (estimate > top.thr_d) return;
+    }
     float d = finish_distance<METRIC>(s0, s1, sqrt_b);
     if (d != d) {
         nan_rows++;
@@ -169,26 +207,25 @@ __device__ __forceinline__ void emit_cta_list(uint64_t *scratch, int n_lists,
 }
 
 // ---- TMA-ring variant, dim == 1152 ------------------------------------------------
-template <int KPL, int METRIC, bool WRITE_ALL>
-__global__ void __launch_bounds__(SCAN_THREADS, 1) scan_tma_kernel(const ScanArgs a) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem);
-    uint64_t *empty_bar = full_bar + SCAN_STAGES;
-    uint8_t *ring = smem + SCAN_SMEM_HEADER;
+template <typename CFG, int KPL, int METRIC, bool WRITE_ALL>
+__global__ void __launch_bounds__(CFG::THREADS, 1) scan_tma_kernel(const ScanArgs a) {
+    constexpr int STAGES = CFG::STAGES;
+    constexpr int R = CFG::TILE_ROWS;
+    extern __shared__ __align__(128) uint8_t scan_smem[];
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(scan_smem);
+    uint64_t *empty_bar = full_bar + STAGES;
+    volatile int *tile_of = reinterpret_cast<volatile int *>(empty_bar + STAGES);  // -1 = no more tiles
+    uint8_t *ring = scan_smem + SCAN_SMEM_HEADER;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
-
-    const long long total_tiles = (a.n + SCAN_TILE_ROWS - 1) / SCAN_TILE_ROWS;
-    const long long first = blockIdx.x;
-    const long long step = gridDim.x;
-    const long long my_tiles = first < total_tiles ? (total_tiles - first + step - 1) / step : 0;
+    const int total_tiles = static_cast<int>((a.n + R - 1) / R);
 
     if (tid == 0) {
-        for (int s = 0; s < SCAN_STAGES; s++) {
+        for (int s = 0; s < STAGES; s++) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], SCAN_GROUP_WARPS);
+            mbar_init(&empty_bar[s], CFG::GROUP_WARPS);
         }
         mbar_fence_init();
     }
@@ -198,31 +235,56 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_tma_kernel(const ScanArg
     top.init(a.k, lane);
     unsigned nan_rows = 0;
 
-    if (warp == SCAN_CONSUMER_WARPS) {
+    if (warp == CFG::CONSUMER_WARPS) {
         // ===== producer: one thread feeds the ring =====
         if (lane == 0) {
             const uint64_t policy = l2_policy_evict_first();
-            for (long long it = 0; it < my_tiles; it++) {
-                const int s = static_cast<int>(it % SCAN_STAGES);
-                const uint32_t phase = static_cast<uint32_t>((it / SCAN_STAGES) & 1);
+            int s = 0;
+            uint32_t phase = 0;
+            auto push = [&](int tile) {
                 mbar_wait(&empty_bar[s], phase ^ 1u);
-                const long long row0 = (first + it * step) * SCAN_TILE_ROWS;
-                const long long left = a.n - row0;
-                const uint32_t bytes =
-                    static_cast<uint32_t>((left < SCAN_TILE_ROWS ? left : SCAN_TILE_ROWS) *
-                                          SCAN_ROW_BYTES);
-                mbar_arrive_expect_tx(&full_bar[s], bytes);
-                const float *src = a.rows + row0 * SCAN_DIM;
-                if (a.evict_first)
-                    bulk_copy_g2s_hint(ring + s * SCAN_STAGE_BYTES, src, bytes, &full_bar[s], policy);
-                else
-                    bulk_copy_g2s(ring + s * SCAN_STAGE_BYTES, src, bytes, &full_bar[s]);
+                tile_of[s] = tile;
+                if (tile >= 0) {
+                    const long long row0 = static_cast<long long>(tile) * R;
+                    const long long left = a.n - row0;
+                    const uint32_t bytes = static_cast<uint32_t>((left < R ? left : R) * SCAN_ROW_BYTES);
+                    mbar_arrive_expect_tx(&full_bar[s], bytes);
+                    const float *src = a.rows + row0 * SCAN_DIM;
+                    if (a.evict_first)
+                        bulk_copy_g2s_hint(ring + s * CFG::STAGE_BYTES, src, bytes, &full_bar[s], policy);
+                    else
+                        bulk_copy_g2s(ring + s * CFG::STAGE_BYTES, src, bytes, &full_bar[s]);
+                } else {
+                    mbar_arrive(&full_bar[s]);  // end marker: completes the phase without data
+                }
+                if (++s == STAGES) {
+                    s = 0;
+                    phase ^= 1u;
+                }
+            };
+            const int grid = static_cast<int>(gridDim.x), b = static_cast<int>(blockIdx.x);
+            if (a.assign == SCAN_ASSIGN_DYNAMIC) {
+                const unsigned chunk = static_cast<unsigned>(a.chunk_tiles > 0 ? a.chunk_tiles : 1);
+                unsigned next = atomicAdd(a.tile_counter, chunk);
+                while (next < static_cast<unsigned>(total_tiles)) {
+                    const unsigned base = next;
+                    next = atomicAdd(a.tile_counter, chunk);  // claimed ahead: latency hidden by the pushes
+                    for (unsigned j = 0; j < chunk && base + j < static_cast<unsigned>(total_tiles); j++)
+                        push(static_cast<int>(base + j));
+                }
+            } else if (a.assign == SCAN_ASSIGN_CONTIGUOUS) {
+                const int per = (total_tiles + grid - 1) / grid;
+                const int lo = b * per, hi = (lo + per < total_tiles) ? lo + per : total_tiles;
+                for (int t = lo; t < hi; t++) push(t);
+            } else {
+                for (int t = b; t < total_tiles; t += grid) push(t);
             }
+            for (int g = 0; g < CFG::GROUPS; g++) push(-1);  // one end marker per consumer group
         }
     } else {
-        // ===== consumers: group g takes tiles it == g (mod SCAN_GROUPS), warp wi row wi =====
-        const int group = warp / SCAN_GROUP_WARPS;
-        const int wi = warp % SCAN_GROUP_WARPS;
+        // ===== consumers: group g takes ring slots g, g+GROUPS, ...; warp wi takes row wi =====
+        const int group = warp / CFG::GROUP_WARPS;
+        const int wi = warp % CFG::GROUP_WARPS;
 
         float4 q[SCAN_CHUNKS];
         const float4 *q4 = reinterpret_cast<const float4 *>(a.query);
@@ -236,15 +298,18 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_tma_kernel(const ScanArg
             bsum = fmaf(q[j].w, q[j].w, bsum);
         }
         const double sqrt_b = sqrt(static_cast<double>(warp_sum(bsum)));
+        const float rsqrt_b = static_cast<float>(1.0 / sqrt_b);
 
-        for (long long it = group; it < my_tiles; it += SCAN_GROUPS) {
-            const int s = static_cast<int>(it % SCAN_STAGES);
-            const uint32_t phase = static_cast<uint32_t>((it / SCAN_STAGES) & 1);
-            const long long pos = (first + it * step) * SCAN_TILE_ROWS + wi;
+        int s = group;
+        uint32_t phase = 0;
+        for (;;) {
             mbar_wait(&full_bar[s], phase);
+            const int tile = tile_of[s];
+            if (tile < 0) break;
+            const long long pos = static_cast<long long>(tile) * R + wi;
             if (pos < a.n && row_admitted(a.mask, pos)) {
                 const float4 *src =
-                    reinterpret_cast<const float4 *>(ring + s * SCAN_STAGE_BYTES + wi * SCAN_ROW_BYTES);
+                    reinterpret_cast<const float4 *>(ring + s * CFG::STAGE_BYTES + wi * SCAN_ROW_BYTES);
                 float4 v[SCAN_CHUNKS];
 #pragma unroll
                 for (int j = 0; j < SCAN_CHUNKS; j++) v[j] = src[lane + 32 * j];
@@ -255,11 +320,16 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_tma_kernel(const ScanArg
                 if (lane == 0) mbar_arrive(&empty_bar[s]);  // row is in registers: free the slot
                 float t0 = warp_sum((s0[0] + s0[1]) + (s0[2] + s0[3]));
                 float t1 = (METRIC == METRIC_COSINE) ? warp_sum((s1[0] + s1[1]) + (s1[2] + s1[3])) : 0.f;
-                offer_row<KPL, METRIC, WRITE_ALL>(t0, t1, sqrt_b, pos, top, nan_rows, a.all_keys, lane);
+                offer_row<KPL, METRIC, WRITE_ALL>(t0, t1, sqrt_b, rsqrt_b, pos, top, nan_rows, a.all_keys, lane);
             } else {
                 if (WRITE_ALL && pos < a.n && lane == 0) a.all_keys[pos] = KEY_EMPTY;
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_bar[s]);
+            }
+            s += CFG::GROUPS;
+            if (s >= STAGES) {
+                s -= STAGES;
+                phase ^= 1u;
             }
         }
     }
@@ -271,17 +341,18 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_tma_kernel(const ScanArg
     // the ring can be reused as sort scratch
     __syncthreads();
     uint64_t *scratch = reinterpret_cast<uint64_t *>(ring);
-    if (warp < SCAN_CONSUMER_WARPS) top.dump(scratch + warp * 32 * KPL, lane);
+    if (warp < CFG::CONSUMER_WARPS) top.dump(scratch + warp * 32 * KPL, lane);
     __syncthreads();
-    emit_cta_list<KPL>(scratch, SCAN_CONSUMER_WARPS,
-                       a.cand + static_cast<size_t>(blockIdx.x) * a.cand_stride, tid, SCAN_THREADS);
+    emit_cta_list<KPL>(scratch, CFG::CONSUMER_WARPS,
+                       a.cand + static_cast<size_t>(blockIdx.x) * a.cand_stride, tid, CFG::THREADS);
 }
 
 // ---- direct-load variant, any dim -----------------------------------------------
 // DIM_T > 0: compile-time dim (query chunks in registers); DIM_T == 0: runtime dim.
 template <int DIM_T, int KPL, int METRIC, bool WRITE_ALL>
 __global__ void __launch_bounds__(LDG_THREADS) scan_ldg_kernel(const ScanArgs a) {
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t scan_smem[];
+    uint8_t *smem = scan_smem;
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
@@ -312,6 +383,7 @@ __global__ void __launch_bounds__(LDG_THREADS) scan_ldg_kernel(const ScanArgs a)
         bsum = fmaf(v.w, v.w, bsum);
     }
     const double sqrt_b = sqrt(static_cast<double>(warp_sum(bsum)));
+    const float rsqrt_b = static_cast<float>(1.0 / sqrt_b);
 
     WarpTopK<KPL> top;
     top.init(a.k, lane);
@@ -348,7 +420,7 @@ __global__ void __launch_bounds__(LDG_THREADS) scan_ldg_kernel(const ScanArgs a)
         }
         float t0 = warp_sum((s0[0] + s0[1]) + (s0[2] + s0[3]));
         float t1 = (METRIC == METRIC_COSINE) ? warp_sum((s1[0] + s1[1]) + (s1[2] + s1[3])) : 0.f;
-        offer_row<KPL, METRIC, WRITE_ALL>(t0, t1, sqrt_b, pos, top, nan_rows, a.all_keys, lane);
+        offer_row<KPL, METRIC, WRITE_ALL>(t0, t1, sqrt_b, rsqrt_b, pos, top, nan_rows, a.all_keys, lane);
     }
 
     if (nan_rows && lane == 0) atomicAdd(a.nan_rows, static_cast<unsigned long long>(nan_rows));

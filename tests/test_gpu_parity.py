@@ -107,6 +107,55 @@ def test_variants_agree_bit_for_bit_on_ids(config1):
     assert np.array_equal(a.distances, b.distances)
 
 
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("assign", [0, 1, 2])
+def test_ring_shapes_and_tile_schedulers_agree(gpu, config1, cfg, assign):
+    """Every ring shape / tile-assignment policy of the TMA kernel returns the same bits."""
+    rows, queries, idx = config1
+    base = idx.search(queries[:3], 20)
+    idx.set_option("scan_cfg", cfg)
+    idx.set_option("scan_assign", assign)
+    idx.set_option("scan_chunk", 3)
+    try:
+        got = idx.search(queries[:3], 20)
+        assert np.array_equal(got.rowids, base.rowids)
+        assert np.array_equal(got.distances, base.distances)
+        # ragged sizes: fewer tiles than CTAs, partial last tile
+        for n in (1, 5, 8, 9, 1183, 1185, 4099):
+            with gpu(0) as small:
+                small.load(rows[:n])
+                want = small.search(queries[0], 20)
+                small.set_option("scan_cfg", cfg)
+                small.set_option("scan_assign", assign)
+                small.set_option("scan_chunk", 3)
+                have = small.search(queries[0], 20)
+                assert np.array_equal(have.rowids, want.rowids) and np.array_equal(have.counts, want.counts)
+                assert np.array_equal(have.distances[:, :want.counts[0]], want.distances[:, :want.counts[0]])
+    finally:
+        idx.set_option("scan_cfg", 0)
+        idx.set_option("scan_assign", 2)
+        idx.set_option("scan_chunk", 4)
+
+
+def test_prefilter_never_changes_the_answer(gpu):
+    """Clustered data (many rows within 1e-6 of the k-th distance) must give the same ids as
+    the oracle: the float32 pre-filter only skips rows that provably cannot enter."""
+    rng = np.random.default_rng(17)
+    base = synth.unit_rows(1, DIM, 18)[0]
+    rows = base[None, :] + 1e-4 * rng.standard_normal((30_000, DIM), dtype=np.float32)
+    rows = (rows / np.linalg.norm(rows, axis=1, keepdims=True)).astype(np.float32)
+    q = base + 1e-4 * rng.standard_normal(DIM, dtype=np.float32)
+    with gpu(0) as idx:
+        idx.load(rows)
+        for variant in (1, 2):
+            idx.set_option("scan_variant", variant)
+            for k in (20, 100):
+                ids, d = idx.search(q, k).row(0)
+                full_ids, full_d = idx.search(q, rows.shape[0]).row(0)      # general path: no pre-filter
+                assert np.array_equal(ids, full_ids[:k])
+                assert np.array_equal(d, full_d[:k])
+
+
 def test_key_level_selection_is_bit_exact(config1):
     """Integer part of the path: with the GPU's own float32 distances for all rows
     (general-k path, k = n), every smaller k must equal the prefix of that full

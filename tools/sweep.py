@@ -56,18 +56,22 @@ def main():
         results.append(rec)
         print(json.dumps(rec), flush=True)
 
-    base = dict(scan_variant=1, scan_ctas=0, evict_first=1, ldg_ctas_per_sm=4)
+    base = dict(scan_variant=1, scan_ctas=0, evict_first=1, ldg_ctas_per_sm=4, scan_cfg=0, scan_assign=0,
+                scan_chunk=4)
     run("tma default", **base)
+    run("tma default (repeat)", **base)
     run("tma no-evict-hint", **{**base, "evict_first": 0})
+    for cfg in (0, 1, 2, 3, 4):
+        for assign in (0, 1, 2):
+            run(f"tma cfg={cfg} assign={assign}", **{**base, "scan_cfg": cfg, "scan_assign": assign})
+    for chunk in (1, 2, 8, 16):
+        run(f"tma dynamic chunk={chunk}", **{**base, "scan_assign": 2, "scan_chunk": chunk})
     run("tma k=100", k=100, **base)
-    run("tma k=128", k=128, **base)
-    run("tma k=1", k=1, **base)
+    run("tma k=100 dynamic", k=100, **{**base, "scan_assign": 2})
     run("general-k (k=1000)", k=1000, **base)
-    for ctas in (sms - 4, sms * 2):
-        run(f"tma ctas={ctas}", **{**base, "scan_ctas": ctas})
-    for per_sm in (2, 4, 6, 8):
-        run(f"ldg {per_sm} ctas/sm", **{**base, "scan_variant": 2, "ldg_ctas_per_sm": per_sm})
-    run("ldg k=100", k=100, **{**base, "scan_variant": 2, "ldg_ctas_per_sm": 4})
+    run("ldg 6 ctas/sm", **{**base, "scan_variant": 2, "ldg_ctas_per_sm": 6})
+    run("ldg 5 ctas/sm", **{**base, "scan_variant": 2, "ldg_ctas_per_sm": 5})
+    run("tma default (end)", **base)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump(results, open(args.out, "w"), indent=1)
 
