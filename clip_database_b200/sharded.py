@@ -63,12 +63,21 @@ class CudaShardBackend:
         self.torch = torch
         self.device = torch.device("cuda", index.device)
         index.use_torch_stream()
+        self._h_query = None
 
     def new_buffer(self, nbytes: int):
         return self.torch.zeros(nbytes, dtype=self.torch.uint8, device=self.device)
 
     def to_device(self, query: np.ndarray):
-        return self.torch.from_numpy(np.ascontiguousarray(query, dtype=np.float32)).to(self.device, non_blocking=True)
+        """Host query -> device through a pinned staging buffer (one async H2D)."""
+        t = self.torch
+        q = np.ascontiguousarray(query, dtype=np.float32).ravel()
+        if self._h_query is None or self._h_query.numel() != q.shape[0]:
+            self._h_query = t.empty(q.shape[0], dtype=t.float32).pin_memory()
+            self._d_query = t.empty(q.shape[0], dtype=t.float32, device=self.device)
+        self._h_query.numpy()[:] = q
+        self._d_query.copy_(self._h_query, non_blocking=True)
+        return self._d_query
 
     def local_search(self, d_query, k: int, record, lay: RecordLayout, use_mask: bool) -> None:
         self.index.search_into_record(d_query, k, record, lay.off_rowids, lay.off_dist, lay.off_count,
@@ -79,10 +88,28 @@ class CudaShardBackend:
                                         out_dist, out_rowids, out_n)
 
     def new_outputs(self, k: int):
+        """(dist[k], rowids[k], n[1]) as views into ONE packed device record, so the host
+        fetches a result with a single D2H copy (``fetch``)."""
         t = self.torch
-        return (t.empty(max(k, 1), dtype=t.float32, device=self.device),
-                t.empty(max(k, 1), dtype=t.int64, device=self.device),
-                t.zeros(1, dtype=t.int32, device=self.device))
+        lay = RecordLayout(max(k, 1))
+        self._out_lay = lay
+        self._out = t.zeros(lay.nbytes, dtype=t.uint8, device=self.device)
+        self._h_out = t.zeros(lay.nbytes, dtype=t.uint8).pin_memory()
+        kk = max(k, 1)
+        return (self._out[lay.off_dist:lay.off_dist + 4 * kk].view(t.float32),
+                self._out[lay.off_rowids:lay.off_rowids + 8 * kk].view(t.int64),
+                self._out[lay.off_count:lay.off_count + 4].view(t.int32))
+
+    def fetch(self, k: int):
+        """One async D2H of the packed result + stream sync -> (rowids, dist) numpy copies."""
+        lay = self._out_lay
+        self._h_out.copy_(self._out, non_blocking=True)
+        self.torch.cuda.current_stream(self.device).synchronize()
+        h = self._h_out.numpy()
+        m = int(h[lay.off_count:lay.off_count + 4].view(np.int32)[0])
+        ids = h[lay.off_rowids:lay.off_rowids + 8 * m].view(np.int64).copy()
+        d = h[lay.off_dist:lay.off_dist + 4 * m].view(np.float32).copy()
+        return ids, d
 
 
 class ShardedIndex:
@@ -131,6 +158,8 @@ class ShardedIndex:
             return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.float32)
         d_query = self.backend.to_device(query)
         dist, rowids, n = self.search_device(d_query, k, use_mask)
+        if hasattr(self.backend, "fetch"):
+            return self.backend.fetch(k)
         m = int(n.cpu()[0])
         # copies: the output tensors are reused by the next search
         return rowids[:m].cpu().numpy().copy(), dist[:m].cpu().numpy().copy()
