@@ -55,6 +55,9 @@ SIGNATURES = [
                                      c_void_p, c_void_p, c_void_p, c_void_p]),
     ("clipdb_blend_search", c_int, [_CTX, _F, _F, c_double, c_double, _F, _D, c_int32, c_int32,
                                     c_int32, c_int32, _I64, _F, _I32, _I64, _F, _I32]),
+    ("clipdb_enable_batch", c_int, [_CTX, c_int32]),
+    ("clipdb_search_batch_device", c_int, [_CTX, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                           c_void_p, c_void_p]),
     ("clipdb_merge_device", c_int, [_CTX, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                     c_void_p, c_void_p, c_void_p]),
     ("clipdb_merge_strided_device", c_int, [_CTX, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,

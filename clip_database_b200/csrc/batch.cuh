@@ -1,0 +1,460 @@
+// batch.cuh — K4: batched queries as a dense Q x D contraction on tcgen05 tensor cores,
+// a threshold-filter epilogue, and an exact float32 re-rank.
+//
+// No reference equivalent: the reference answers strictly one query at a time
+// (image_database.py:2070-2299).  BASELINE configs[2] (B = 256, k = 100, 10M rows) asks
+// for many concurrent sessions' queries to share one pass over the store.  Results must
+// equal the single-query path (scan_topk.cuh) exactly, so the tensor cores only
+// PRE-SELECT:
+//
+//   1. bf16 copy of the store D^ [n][1152] (+ fp32 1/||row||), bf16 queries Q^ [256][1152].
+//   2. score(q,row) = Q^ . D^ on tcgen05 (UMMA 128x256x16, fp32 accumulators in TMEM),
+//      operands staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) through a 4-stage
+//      mbarrier ring; warp-specialised: 1 TMA thread, 1 MMA thread, 4 epilogue warps
+//      reading the accumulators with tcgen05.ld while the next tile's MMAs run (two
+//      accumulator buffers = all 512 TMEM columns).
+//   3. pass A (every 16th tile): the epilogue dumps u = score/||row|| for a row sample;
+//      per query, tau = the k-th best sampled u  =>  at least k rows have u >= tau.
+//   4. pass B (all tiles): the epilogue keeps (q,row) iff u >= tau - 2E||q||, where
+//      E = 4.5e-3 bounds |cos^ - cos| for bf16-rounded operands (2^-8 from the two
+//      roundings, Cauchy-Schwarz over the 1152 terms, + accumulation slack).  Every row of
+//      the true top-k satisfies this (it has cos >= cos_k >= tau/||q|| - E), so the
+//      candidate set is a superset of the answer — a guarantee, not a heuristic.
+//   5. re-rank: each candidate's distance is recomputed with K1's exact float32/double
+//      arithmetic and the same 64-bit keys, so ids and distance bits equal the
+//      single-query path.  Queries whose candidate list overflows (or whose norm is
+//      zero) are flagged and re-run through the exact scan by the host.
+//
+// Roofline: 2*B*n*1152 flop per batch on the tensor pipe (5.9 TFLOP at B=256, n=10M) and
+// n*2304 B of HBM for the bf16 store; the re-rank reads ~candidates*4608 B.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "merge.cuh"
+#include "scan_topk.cuh"
+
+namespace clipdb {
+
+constexpr int BQ_N = 256;        // queries per pass (UMMA N)
+constexpr int BQ_M = 128;        // rows per tile (UMMA M, one TMEM lane per row)
+constexpr int BQ_BLOCK_K = 64;   // bf16 per k-block = one 128-byte swizzle row
+constexpr int BQ_K_BLOCKS = SCAN_DIM / BQ_BLOCK_K;  // 18
+constexpr int BQ_UMMA_K = 16;    // bf16 per tcgen05.mma
+constexpr int BQ_STAGES = 4;
+constexpr int BQ_A_BYTES = BQ_M * BQ_BLOCK_K * 2;   // 16,384
+constexpr int BQ_B_BYTES = BQ_N * BQ_BLOCK_K * 2;   // 32,768
+constexpr int BQ_STAGE_BYTES = BQ_A_BYTES + BQ_B_BYTES;
+constexpr int BQ_THREADS = 192;  // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 epilogue
+constexpr int BQ_HEADER = 2048;  // barriers, TMEM base, thresholds
+constexpr int BQ_SMEM_BYTES = BQ_HEADER + BQ_STAGES * BQ_STAGE_BYTES + 1024;  // + alignment slack
+constexpr int BQ_TMEM_COLS = 512;
+constexpr int BQ_SAMPLE_STRIDE = 16;  // pass A visits every 16th tile
+constexpr float BQ_COS_ERROR = 4.5e-3f;  // E: bound on |cos^ - cos| with bf16 operands
+
+// idesc for kind::f16: D=F32, A=B=BF16, both K-major, N=256, M=128 (cute::UMMA::InstrDescriptor)
+constexpr uint32_t BQ_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((BQ_N >> 3) << 17) | ((BQ_M >> 4) << 24);
+
+constexpr int BQ_FLAG_OVERFLOW = 1;    // candidate list overflowed its capacity
+constexpr int BQ_FLAG_BAD_QUERY = 2;   // zero / non-finite query norm
+
+// ---- PTX wrappers ---------------------------------------------------------------------
+
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1,
+                                            uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "r"(cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols));
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart
+// (cute::UMMA::SmemDescriptor: start>>4, LBO=1, SBO=64, version 1, layout SWIZZLE_128B=2)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// all previously issued MMAs of this thread arrive on `bar` when they complete
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- store / query preparation -----------------------------------------------------------
+
+// one warp per row: bf16 copy, 1/||row|| (float32), count of rows whose norm is 0 or not finite
+__global__ void __launch_bounds__(256) build_bf16_store_kernel(const float *__restrict__ rows, long long n,
+                                                               __nv_bfloat16 *__restrict__ out,
+                                                               float *__restrict__ inv_norm,
+                                                               unsigned long long *__restrict__ bad_rows) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    unsigned bad = 0;
+    for (long long r = warp; r < n; r += warps) {
+        const float4 *src = reinterpret_cast<const float4 *>(rows + r * SCAN_DIM);
+        uint2 *dst = reinterpret_cast<uint2 *>(out + r * SCAN_DIM);
+        float ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < SCAN_CHUNKS; j++) {
+            const float4 v = ldg_stream(src + lane + 32 * j);
+            ss = fmaf(v.x, v.x, ss);
+            ss = fmaf(v.y, v.y, ss);
+            ss = fmaf(v.z, v.z, ss);
+            ss = fmaf(v.w, v.w, ss);
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            uint2 packed;
+            packed.x = *reinterpret_cast<uint32_t *>(&lo);
+            packed.y = *reinterpret_cast<uint32_t *>(&hi);
+            dst[lane + 32 * j] = packed;
+        }
+        ss = warp_sum(ss);
+        const float inv = 1.0f / sqrtf(ss);
+        const bool ok = ss > 0.f && isfinite(inv) && isfinite(ss);
+        if (lane == 0) {
+            inv_norm[r] = ok ? inv : __int_as_float(0x7fc00000);  // NaN: never passes a >= test
+            if (!ok) bad++;
+        }
+    }
+    if (lane == 0 && bad) atomicAdd(bad_rows, static_cast<unsigned long long>(bad));
+}
+
+// one CTA per query slot (256 slots): bf16 copy (zeros past nq), ||q||
+__global__ void __launch_bounds__(128) prep_queries_kernel(const float *__restrict__ q, int nq,
+                                                           __nv_bfloat16 *__restrict__ qb,
+                                                           float *__restrict__ q_norm) {
+    __shared__ float red[4];
+    const int slot = blockIdx.x, tid = threadIdx.x;
+    float ss = 0.f;
+    for (int i = tid; i < SCAN_DIM; i += 128) {
+        const float v = slot < nq ? q[static_cast<size_t>(slot) * SCAN_DIM + i] : 0.f;
+        qb[static_cast<size_t>(slot) * SCAN_DIM + i] = __float2bfloat16_rn(v);
+        ss = fmaf(v, v, ss);
+    }
+    ss = warp_sum(ss);
+    if ((tid & 31) == 0) red[tid >> 5] = ss;
+    __syncthreads();
+    if (tid == 0) q_norm[slot] = sqrtf(red[0] + red[1] + red[2] + red[3]);
+}
+
+// ---- the contraction ---------------------------------------------------------------------------
+
+struct BatchGemmArgs {
+    const float *inv_norm;      // [n]
+    const float *thr;           // [256] FILTER: keep iff u >= thr[q]
+    float *scores;              // DUMP: [256][sample_rows]
+    unsigned int *cand_count;   // FILTER: [256]
+    unsigned int *cand_rows;    // FILTER: [256][cand_cap]
+    long long n;
+    long long sample_rows;      // DUMP: row capacity per query in `scores`
+    int total_tiles;            // ceil(n / 128)
+    int tile_stride;            // 1 (FILTER) or BQ_SAMPLE_STRIDE (DUMP)
+    int cand_cap;
+};
+
+template <bool DUMP>
+__global__ void __launch_bounds__(BQ_THREADS, 1) batch_gemm_kernel(const __grid_constant__ CUtensorMap map_rows,
+                                                                   const __grid_constant__ CUtensorMap map_q,
+                                                                   const BatchGemmArgs a) {
+    extern __shared__ __align__(16) uint8_t bq_smem_raw[];
+    // header: barriers | tmem base | thresholds ; tiles start at the next 1024-byte boundary
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(bq_smem_raw);
+    uint64_t *empty_bar = full_bar + BQ_STAGES;
+    uint64_t *tmem_full = empty_bar + BQ_STAGES;   // [2]
+    uint64_t *tmem_empty = tmem_full + 2;          // [2]
+    uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    float *thr_s = reinterpret_cast<float *>(bq_smem_raw + 1024);  // [256]
+    const uint32_t raw_addr = smem_u32(bq_smem_raw);
+    const uint32_t tiles_addr = (raw_addr + BQ_HEADER + 1023u) & ~1023u;
+    uint8_t *tiles = bq_smem_raw + (tiles_addr - raw_addr);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int eff_tiles = (a.total_tiles + a.tile_stride - 1) / a.tile_stride;   // tiles this launch visits
+    const int first = blockIdx.x, step = gridDim.x;
+
+    if (tid == 0) {
+        for (int s = 0; s < BQ_STAGES; s++) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; b++) {
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], 4);   // one arrive per epilogue warp
+        }
+        mbar_fence_init();
+    }
+    if (!DUMP)
+        for (int i = tid; i < BQ_N; i += BQ_THREADS) thr_s[i] = a.thr[i];
+    if (warp == 1) tmem_alloc(tmem_base_slot, BQ_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int s = 0;
+            uint32_t phase = 0;
+            for (int t = first; t < eff_tiles; t += step) {
+                const int row0 = t * a.tile_stride * BQ_M;
+                for (int kb = 0; kb < BQ_K_BLOCKS; kb++) {
+                    mbar_wait(&empty_bar[s], phase ^ 1u);
+                    mbar_arrive_expect_tx(&full_bar[s], BQ_STAGE_BYTES);
+                    uint8_t *stage = tiles + s * BQ_STAGE_BYTES;
+                    tma_load_2d(stage, &map_rows, kb * BQ_BLOCK_K, row0, &full_bar[s]);
+                    tma_load_2d(stage + BQ_A_BYTES, &map_q, kb * BQ_BLOCK_K, 0, &full_bar[s]);
+                    if (++s == BQ_STAGES) {
+                        s = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int s = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int t = first; t < eff_tiles; t += step, it++) {
+                const int acc = it & 1;
+                mbar_wait(&tmem_empty[acc], (static_cast<uint32_t>(it >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BQ_N);
+                for (int kb = 0; kb < BQ_K_BLOCKS; kb++) {
+                    mbar_wait(&full_bar[s], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = tiles_addr + s * BQ_STAGE_BYTES;
+                    const uint32_t b_addr = a_addr + BQ_A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BQ_BLOCK_K / BQ_UMMA_K; k++) {
+                        umma_bf16(tmem_d, umma_desc_sw128(a_addr + k * BQ_UMMA_K * 2),
+                                  umma_desc_sw128(b_addr + k * BQ_UMMA_K * 2), BQ_IDESC,
+                                  static_cast<uint32_t>((kb | k) != 0));
+                    }
+                    umma_commit(&empty_bar[s]);   // frees the smem stage when these MMAs retire
+                    if (++s == BQ_STAGES) {
+                        s = 0;
+                        phase ^= 1u;
+                    }
+                }
+                umma_commit(&tmem_full[acc]);     // accumulator complete
+            }
+        }
+    } else {
+        // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
+        const int lane_base = 32 * (warp & 3);
+        int it = 0;
+        for (int t = first; t < eff_tiles; t += step, it++) {
+            const int acc = it & 1;
+            const long long row = static_cast<long long>(t) * a.tile_stride * BQ_M + lane_base + lane;
+            const bool row_ok = row < a.n;
+            const float inv = row_ok ? __ldg(a.inv_norm + row) : 0.f;
+            mbar_wait(&tmem_full[acc], static_cast<uint32_t>(it >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_base) << 16) +
+                                   static_cast<uint32_t>(acc * BQ_N);
+#pragma unroll 1
+            for (int c = 0; c < BQ_N / 32; c++) {
+                uint32_t r[32];
+                tmem_ld32(taddr + c * 32, r);
+                tmem_ld_wait();
+                if (DUMP) {
+                    const long long srow = static_cast<long long>(t) * BQ_M + lane_base + lane;  // sample index
+                    if (srow < a.sample_rows) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const float u = row_ok ? __uint_as_float(r[j]) * inv : __int_as_float(0xff800000);
+                            a.scores[static_cast<long long>(c * 32 + j) * a.sample_rows + srow] = u;
+                        }
+                    }
+                } else if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float u = __uint_as_float(r[j]) * inv;
+                        if (u >= thr_s[c * 32 + j]) {
+                            const int q = c * 32 + j;
+                            const unsigned pos = atomicAdd(a.cand_count + q, 1u);
+                            if (pos < static_cast<unsigned>(a.cand_cap))
+                                a.cand_rows[static_cast<size_t>(q) * a.cand_cap + pos] = static_cast<unsigned>(row);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, BQ_TMEM_COLS);
+}
+
+// ---- thresholds: per query, tau = k-th best sampled u; thr = tau - 2E||q|| ------------------------
+template <int KPL>
+__global__ void __launch_bounds__(256) batch_threshold_kernel(const float *__restrict__ scores, long long sample_rows,
+                                                              const float *__restrict__ q_norm, int nq, int k,
+                                                              float *__restrict__ thr, int *__restrict__ flags) {
+    __shared__ uint64_t scratch[8 * 32 * KPL];
+    const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (q >= nq) {  // padding slots: never produce candidates
+        if (tid == 0) thr[q] = __int_as_float(0x7f800000);
+        return;
+    }
+    const float qn = q_norm[q];
+    WarpTopK<KPL> top;
+    top.init(k, lane);
+    const float *src = scores + static_cast<long long>(q) * sample_rows;
+    for (long long base = static_cast<long long>(warp) * 32; base < sample_rows; base += 256) {
+        const long long i = base + lane;
+        const float u = i < sample_rows ? src[i] : __int_as_float(0xff800000);
+        // best = largest u: order keys by -u.  One element per lane, offered one at a time
+        // (warp-uniform inserts); candidates are rare after the first few hundred rows.
+        const bool valid = u == u && u > __int_as_float(0xff800000);
+        const uint64_t key = valid ? make_key(-u, static_cast<uint32_t>(i)) : KEY_EMPTY;
+        unsigned pending = __ballot_sync(FULL_MASK, key < top.thr);
+        while (pending) {
+            const int src_lane = __ffs(pending) - 1;
+            const uint64_t kk = __shfl_sync(FULL_MASK, key, src_lane);
+            if (kk < top.thr) top.insert(kk, lane);
+            pending &= pending - 1;
+        }
+    }
+    top.dump(scratch + warp * 32 * KPL, lane);
+    __syncthreads();
+    block_bitonic_sort(scratch, 8 * 32 * KPL, tid, 256);
+    if (tid == 0) {
+        const uint64_t kth = scratch[k - 1];
+        int f = 0;
+        float t = __int_as_float(0x7f800000);
+        if (!(qn > 0.f) || !isfinite(qn)) {
+            f = BQ_FLAG_BAD_QUERY;
+        } else if (kth == KEY_EMPTY) {
+            t = __int_as_float(0xff800000);   // fewer than k finite samples: keep everything
+        } else {
+            const float tau = -orderable_f32(static_cast<uint32_t>(kth >> 32));
+            t = tau - 2.0f * BQ_COS_ERROR * qn;
+        }
+        thr[q] = t;
+        flags[q] = f;
+    }
+}
+
+// ---- exact re-rank: K1's arithmetic over each query's candidate rows ------------------------------
+struct RerankArgs {
+    const float *rows;            // fp32 store
+    const float *queries;         // [nq][1152] fp32
+    const unsigned int *cand_count;
+    const unsigned int *cand_rows;
+    int cand_cap;
+    int k;
+    int *flags;                   // |= BQ_FLAG_OVERFLOW
+    DecodeArgs dec;               // out arrays are [nq][k]; out_n/out_nan [nq]
+    const unsigned long long *bad_rows;  // rows of the store with NaN distance for any query
+    long long n;
+};
+
+template <int KPL>
+__global__ void __launch_bounds__(512) batch_rerank_kernel(const RerankArgs a) {
+    __shared__ uint64_t scratch[16 * 32 * KPL];
+    const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned total = a.cand_count[q];
+    const bool overflow = total > static_cast<unsigned>(a.cand_cap);
+    const unsigned count = overflow ? static_cast<unsigned>(a.cand_cap) : total;
+
+    float4 qv[SCAN_CHUNKS];
+    const float4 *q4 = reinterpret_cast<const float4 *>(a.queries + static_cast<size_t>(q) * SCAN_DIM);
+    float bsum = 0.f;
+#pragma unroll
+    for (int j = 0; j < SCAN_CHUNKS; j++) {
+        qv[j] = __ldg(q4 + lane + 32 * j);
+        bsum = fmaf(qv[j].x, qv[j].x, bsum);
+        bsum = fmaf(qv[j].y, qv[j].y, bsum);
+        bsum = fmaf(qv[j].z, qv[j].z, bsum);
+        bsum = fmaf(qv[j].w, qv[j].w, bsum);
+    }
+    const double sqrt_b = sqrt(static_cast<double>(warp_sum(bsum)));
+    const float rsqrt_b = static_cast<float>(1.0 / sqrt_b);
+
+    WarpTopK<KPL> top;
+    top.init(a.k, lane);
+    unsigned nan_rows = 0;
+    const unsigned int *list = a.cand_rows + static_cast<size_t>(q) * a.cand_cap;
+    for (unsigned i = warp; i < count; i += 16) {
+        const long long pos = list[i];
+        const float4 *src = reinterpret_cast<const float4 *>(a.rows + pos * SCAN_DIM);
+        float4 v[SCAN_CHUNKS];
+#pragma unroll
+        for (int j = 0; j < SCAN_CHUNKS; j++) v[j] = ldg_stream(src + lane + 32 * j);
+        float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < SCAN_CHUNKS; j++) accumulate<METRIC_COSINE>(v[j], qv[j], s0, s1);
+        const float t0 = warp_sum((s0[0] + s0[1]) + (s0[2] + s0[3]));
+        const float t1 = warp_sum((s1[0] + s1[1]) + (s1[2] + s1[3]));
+        offer_row<KPL, METRIC_COSINE, false>(t0, t1, sqrt_b, rsqrt_b, pos, top, nan_rows, nullptr, lane);
+    }
+    top.dump(scratch + warp * 32 * KPL, lane);
+    __syncthreads();
+    block_bitonic_sort(scratch, 16 * 32 * KPL, tid, 512);
+
+    DecodeArgs d = a.dec;
+    d.out_rowids += static_cast<size_t>(q) * a.k;
+    d.out_dist += static_cast<size_t>(q) * a.k;
+    int found = 0;
+    for (int base = 0; base < a.k; base += 512) {
+        const int i = base + tid;
+        const bool valid = i < a.k && scratch[i] != KEY_EMPTY;
+        if (valid) decode_one(d, i, scratch[i]);
+        found += __syncthreads_count(valid);
+    }
+    if (tid == 0) {
+        d.out_n[q] = found;
+        if (d.out_nan) d.out_nan[q] = static_cast<int64_t>(*a.bad_rows);
+        if (overflow) a.flags[q] |= BQ_FLAG_OVERFLOW;
+    }
+}
+
+}  // namespace clipdb

@@ -18,6 +18,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "../../include/clipdb.h"
+#include "batch.cuh"
 #include "blend.cuh"
 #include "merge.cuh"
 #include "scan_topk.cuh"
@@ -62,6 +63,14 @@ struct clipdb_ctx {
     Buffer d_blend_in, d_blend_flags;
     Buffer pinned;      // host staging (inputs, then results)
     Buffer pinned_aux;  // host staging for the blended query read-back
+
+    // batched path (K4): bf16 copy of the store + workspaces
+    bool batch_enabled = false;
+    Buffer bf16_rows, inv_norm, bad_rows, bq_queries, bq_qnorm, bq_scores, bq_thr, bq_flags, bq_count, bq_cand;
+    CUtensorMap map_rows, map_q;
+    int64_t bq_sample_rows = 0;
+    int64_t batch_min_nq = 16;      // clipdb_search switches to the batched path from this nq
+    int64_t batch_cand_cap = 32768; // candidate rows kept per query
 
     // scan-kernel event timing (clipdb_profile)
     bool profiling = false;
@@ -178,6 +187,9 @@ void release_store(clipdb_ctx *c) {
     if (c->mask) cudaFree(c->mask);
     c->mask = nullptr;
     c->mask_words = 0;
+    c->batch_enabled = false;   // the bf16 copy described the old rows
+    free_buffer(c->bf16_rows);
+    free_buffer(c->inv_norm);
 }
 
 // copy `m` rows of `dim` floats (host or device) into the store at row `at`
@@ -530,6 +542,162 @@ int stage_blend(clipdb_ctx *c, const float *e1, const float *e2, double w0, doub
     return CLIPDB_OK;
 }
 
+
+// ---- batched path (K4) ----------------------------------------------------------------
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+int encode_bf16_map(clipdb_ctx *c, CUtensorMap *map, void *base, uint64_t rows, uint32_t box_rows) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CU_TRY(c, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+        if (!p || qres != cudaDriverEntryPointSuccess)
+            return fail(c, CLIPDB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(SCAN_DIM), rows};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(SCAN_DIM) * 2};
+    const cuuint32_t box[2] = {BQ_BLOCK_K, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(c, CLIPDB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+    return CLIPDB_OK;
+}
+
+constexpr int64_t BATCH_MIN_ROWS = 65536;
+
+int batch_build_locked(clipdb_ctx *c) {
+    if (!c->rows || c->dim != SCAN_DIM || c->ld != SCAN_DIM)
+        return fail(c, CLIPDB_ERR_UNSUPPORTED, "batched path needs a loaded store with dim == %d", SCAN_DIM);
+    if (c->n < BATCH_MIN_ROWS)
+        return fail(c, CLIPDB_ERR_UNSUPPORTED, "batched path needs at least %lld rows", (long long)BATCH_MIN_ROWS);
+    const int64_t tiles = (c->n + BQ_M - 1) / BQ_M;
+    const int64_t eff = (tiles + BQ_SAMPLE_STRIDE - 1) / BQ_SAMPLE_STRIDE;
+    c->bq_sample_rows = eff * BQ_M;
+    RC_TRY(ensure_device(c, c->bf16_rows, static_cast<size_t>(c->n) * SCAN_DIM * 2));
+    RC_TRY(ensure_device(c, c->inv_norm, static_cast<size_t>(c->n) * sizeof(float)));
+    RC_TRY(ensure_device(c, c->bad_rows, sizeof(unsigned long long)));
+    RC_TRY(ensure_device(c, c->bq_queries, static_cast<size_t>(BQ_N) * SCAN_DIM * 2));
+    RC_TRY(ensure_device(c, c->bq_qnorm, BQ_N * sizeof(float)));
+    RC_TRY(ensure_device(c, c->bq_scores, static_cast<size_t>(BQ_N) * c->bq_sample_rows * sizeof(float)));
+    RC_TRY(ensure_device(c, c->bq_thr, BQ_N * sizeof(float)));
+    RC_TRY(ensure_device(c, c->bq_flags, BQ_N * sizeof(int32_t)));
+    RC_TRY(ensure_device(c, c->bq_count, BQ_N * sizeof(unsigned int)));
+    RC_TRY(ensure_device(c, c->bq_cand, static_cast<size_t>(BQ_N) * c->batch_cand_cap * sizeof(unsigned int)));
+    CU_TRY(c, cudaMemsetAsync(c->bad_rows.p, 0, sizeof(unsigned long long), c->stream));
+    build_bf16_store_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(
+        c->rows, c->n, static_cast<__nv_bfloat16 *>(c->bf16_rows.p), static_cast<float *>(c->inv_norm.p),
+        static_cast<unsigned long long *>(c->bad_rows.p));
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    RC_TRY(encode_bf16_map(c, &c->map_rows, c->bf16_rows.p, static_cast<uint64_t>(c->n), BQ_M));
+    RC_TRY(encode_bf16_map(c, &c->map_q, c->bq_queries.p, BQ_N, BQ_N));
+    CU_TRY(c, cudaFuncSetAttribute(batch_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BQ_SMEM_BYTES));
+    CU_TRY(c, cudaFuncSetAttribute(batch_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BQ_SMEM_BYTES));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    c->batch_enabled = true;
+    return CLIPDB_OK;
+}
+
+bool batch_eligible(const clipdb_ctx *c, int32_t nq, int32_t k, int32_t metric, int32_t use_mask) {
+    return c->batch_enabled && metric == CLIPDB_METRIC_COSINE && !use_mask && k >= 1 && k <= FUSED_K_MAX &&
+           k <= c->n && nq >= 1 && nq <= BQ_N;
+}
+
+template <int KPL>
+int batch_launch_tail(clipdb_ctx *c, const float *d_queries, int32_t nq, int32_t k, int64_t *d_out_rowids,
+                      float *d_out_dist, int32_t *d_out_n, int64_t *d_out_nan, int32_t *d_flags, bool threshold) {
+    if (threshold) {
+        batch_threshold_kernel<KPL><<<BQ_N, 256, 0, c->stream>>>(
+            static_cast<const float *>(c->bq_scores.p), c->bq_sample_rows, static_cast<const float *>(c->bq_qnorm.p),
+            nq, k, static_cast<float *>(c->bq_thr.p), d_flags);
+    } else {
+        RerankArgs r{};
+        r.rows = c->rows;
+        r.queries = d_queries;
+        r.cand_count = static_cast<const unsigned int *>(c->bq_count.p);
+        r.cand_rows = static_cast<const unsigned int *>(c->bq_cand.p);
+        r.cand_cap = static_cast<int>(c->batch_cand_cap);
+        r.k = k;
+        r.flags = d_flags;
+        r.dec.rowids = c->rowids;
+        r.dec.rowid_base = c->rowid_base;
+        r.dec.out_rowids = d_out_rowids;
+        r.dec.out_dist = d_out_dist;
+        r.dec.out_n = d_out_n;
+        r.dec.out_nan = d_out_nan;
+        r.dec.k = k;
+        r.bad_rows = static_cast<const unsigned long long *>(c->bad_rows.p);
+        r.n = c->n;
+        batch_rerank_kernel<KPL><<<nq, 512, 0, c->stream>>>(r);
+    }
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    return CLIPDB_OK;
+}
+
+int batch_search_device_locked(clipdb_ctx *c, const float *d_queries, int32_t nq, int32_t k,
+                               int64_t *d_out_rowids, float *d_out_dist, int32_t *d_out_n, int64_t *d_out_nan,
+                               int32_t *d_flags) {
+    if (!d_queries || !d_out_rowids || !d_out_dist || !d_out_n || !d_flags)
+        return fail(c, CLIPDB_ERR_INVALID, "search_batch: null pointer");
+    if (!batch_eligible(c, nq, k, CLIPDB_METRIC_COSINE, 0))
+        return fail(c, CLIPDB_ERR_STATE, "search_batch: batch store not enabled or arguments out of range "
+                                         "(1 <= nq <= 256, 1 <= k <= 128)");
+    const int kpl = k <= 32 ? 1 : (k <= 64 ? 2 : 4);
+    const int tiles = static_cast<int>((c->n + BQ_M - 1) / BQ_M);
+    prep_queries_kernel<<<BQ_N, 128, 0, c->stream>>>(d_queries, nq, static_cast<__nv_bfloat16 *>(c->bq_queries.p),
+                                                     static_cast<float *>(c->bq_qnorm.p));
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+
+    BatchGemmArgs g{};
+    g.inv_norm = static_cast<const float *>(c->inv_norm.p);
+    g.thr = static_cast<const float *>(c->bq_thr.p);
+    g.scores = static_cast<float *>(c->bq_scores.p);
+    g.cand_count = static_cast<unsigned int *>(c->bq_count.p);
+    g.cand_rows = static_cast<unsigned int *>(c->bq_cand.p);
+    g.n = c->n;
+    g.sample_rows = c->bq_sample_rows;
+    g.total_tiles = tiles;
+    g.cand_cap = static_cast<int>(c->batch_cand_cap);
+
+    // pass A: scores of the row sample -> per-query thresholds
+    g.tile_stride = BQ_SAMPLE_STRIDE;
+    const int eff = (tiles + BQ_SAMPLE_STRIDE - 1) / BQ_SAMPLE_STRIDE;
+    batch_gemm_kernel<true><<<eff < c->sm_count ? eff : c->sm_count, BQ_THREADS, BQ_SMEM_BYTES, c->stream>>>(
+        c->map_rows, c->map_q, g);
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    switch (kpl) {
+        case 1: RC_TRY((batch_launch_tail<1>(c, d_queries, nq, k, d_out_rowids, d_out_dist, d_out_n, d_out_nan, d_flags, true))); break;
+        case 2: RC_TRY((batch_launch_tail<2>(c, d_queries, nq, k, d_out_rowids, d_out_dist, d_out_n, d_out_nan, d_flags, true))); break;
+        default: RC_TRY((batch_launch_tail<4>(c, d_queries, nq, k, d_out_rowids, d_out_dist, d_out_n, d_out_nan, d_flags, true))); break;
+    }
+    // pass B: all tiles, keep (q,row) above the threshold
+    CU_TRY(c, cudaMemsetAsync(c->bq_count.p, 0, BQ_N * sizeof(unsigned int), c->stream));
+    g.tile_stride = 1;
+    RC_TRY(profile_mark(c, true));
+    batch_gemm_kernel<false><<<tiles < c->sm_count ? tiles : c->sm_count, BQ_THREADS, BQ_SMEM_BYTES, c->stream>>>(
+        c->map_rows, c->map_q, g);
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    RC_TRY(profile_mark(c, false));
+    // exact re-rank
+    switch (kpl) {
+        case 1: return batch_launch_tail<1>(c, d_queries, nq, k, d_out_rowids, d_out_dist, d_out_n, d_out_nan, d_flags, false);
+        case 2: return batch_launch_tail<2>(c, d_queries, nq, k, d_out_rowids, d_out_dist, d_out_n, d_out_nan, d_flags, false);
+        default: return batch_launch_tail<4>(c, d_queries, nq, k, d_out_rowids, d_out_dist, d_out_n, d_out_nan, d_flags, false);
+    }
+}
+
 }  // namespace
 
 // ================================ C ABI ==========================================
@@ -577,7 +745,9 @@ void clipdb_destroy(clipdb_ctx *c) {
         release_store(c);
         Buffer *bufs[] = {&c->cand_a, &c->cand_b, &c->nan_ctr, &c->tile_ctr, &c->all_keys_a, &c->all_keys_b,
                           &c->cub_tmp, &c->d_query, &c->d_out_rowids, &c->d_out_dist, &c->d_out_n,
-                          &c->d_out_nan, &c->d_blend_in, &c->d_blend_flags};
+                          &c->d_out_nan, &c->d_blend_in, &c->d_blend_flags, &c->bf16_rows, &c->inv_norm,
+                          &c->bad_rows, &c->bq_queries, &c->bq_qnorm, &c->bq_scores, &c->bq_thr, &c->bq_flags,
+                          &c->bq_count, &c->bq_cand};
         for (Buffer *b : bufs) free_buffer(*b);
         if (c->pinned.p) cudaFreeHost(c->pinned.p);
         if (c->pinned_aux.p) cudaFreeHost(c->pinned_aux.p);
@@ -627,6 +797,8 @@ static int64_t *option_slot(clipdb_ctx *c, const char *name) {
     if (!strcmp(name, "scan_cfg")) return &c->scan_cfg;
     if (!strcmp(name, "scan_assign")) return &c->scan_assign;
     if (!strcmp(name, "scan_chunk")) return &c->scan_chunk;
+    if (!strcmp(name, "batch_min_nq")) return &c->batch_min_nq;
+    if (!strcmp(name, "batch_cand_cap")) return &c->batch_cand_cap;
     return nullptr;
 }
 
@@ -874,11 +1046,33 @@ int clipdb_search(clipdb_ctx *c, const float *queries, int32_t nq, int32_t k, in
     memcpy(c->pinned.p, queries, qbytes);
     CU_TRY(c, cudaMemcpyAsync(c->d_query.p, c->pinned.p, qbytes, cudaMemcpyHostToDevice, c->stream));
     // the pinned buffer is reused for results: the H2D above is ordered before them on the stream
-    RC_TRY(search_device_locked(c, static_cast<const float *>(c->d_query.p), nq, k, metric, use_mask,
-                                static_cast<int64_t *>(c->d_out_rowids.p),
-                                static_cast<float *>(c->d_out_dist.p),
-                                static_cast<int32_t *>(c->d_out_n.p),
-                                static_cast<int64_t *>(c->d_out_nan.p)));
+    const float *dq = static_cast<const float *>(c->d_query.p);
+    int64_t *o_ids = static_cast<int64_t *>(c->d_out_rowids.p);
+    float *o_dist = static_cast<float *>(c->d_out_dist.p);
+    int32_t *o_n = static_cast<int32_t *>(c->d_out_n.p);
+    int64_t *o_nan = static_cast<int64_t *>(c->d_out_nan.p);
+    if (nq >= c->batch_min_nq && batch_eligible(c, nq < BQ_N ? nq : BQ_N, k, metric, use_mask)) {
+        // batched path: tensor-core pre-selection + exact re-rank, 256 queries per pass; queries
+        // it flags (candidate overflow, zero norm) are re-run through the exact scan
+        RC_TRY(ensure_device(c, c->bq_flags, static_cast<size_t>(nq > BQ_N ? nq : BQ_N) * sizeof(int32_t)));
+        int32_t *d_flags = static_cast<int32_t *>(c->bq_flags.p);
+        for (int32_t q0 = 0; q0 < nq; q0 += BQ_N) {
+            const int32_t m = nq - q0 < BQ_N ? nq - q0 : BQ_N;
+            RC_TRY(batch_search_device_locked(c, dq + static_cast<size_t>(q0) * c->dim, m, k, o_ids + q0 * kcols,
+                                              o_dist + q0 * kcols, o_n + q0, o_nan + q0, d_flags + q0));
+        }
+        std::vector<int32_t> flags(static_cast<size_t>(nq));
+        CU_TRY(c, cudaMemcpyAsync(flags.data(), d_flags, static_cast<size_t>(nq) * sizeof(int32_t),
+                                  cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        for (int32_t q = 0; q < nq; q++) {
+            if (!flags[q]) continue;
+            RC_TRY(search_device_locked(c, dq + static_cast<size_t>(q) * c->dim, 1, k, metric, use_mask,
+                                        o_ids + q * kcols, o_dist + q * kcols, o_n + q, o_nan + q));
+        }
+        return fetch_results(c, nq, kcols, out_rowids, out_dist, out_n, out_nan);
+    }
+    RC_TRY(search_device_locked(c, dq, nq, k, metric, use_mask, o_ids, o_dist, o_n, o_nan));
     return fetch_results(c, nq, kcols, out_rowids, out_dist, out_n, out_nan);
 }
 
@@ -926,6 +1120,29 @@ int clipdb_blend_search(clipdb_ctx *c, const float *e1, const float *e2, double 
     if (out_query) memcpy(out_query, h_aux, dim * sizeof(float));
     if (out_flags) memcpy(out_flags, h_aux + dim, sizeof(int32_t));
     return CLIPDB_OK;
+}
+
+int clipdb_enable_batch(clipdb_ctx *c, int32_t enable) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    if (!enable) {
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        c->batch_enabled = false;
+        Buffer *bufs[] = {&c->bf16_rows, &c->inv_norm, &c->bq_scores, &c->bq_cand};
+        for (Buffer *b : bufs) free_buffer(*b);
+        return CLIPDB_OK;
+    }
+    return batch_build_locked(c);
+}
+
+int clipdb_search_batch_device(clipdb_ctx *c, const float *d_queries, int32_t nq, int32_t k,
+                               int64_t *d_out_rowids, float *d_out_dist, int32_t *d_out_n,
+                               int64_t *d_out_nan, int32_t *d_flags) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    return batch_search_device_locked(c, d_queries, nq, k, d_out_rowids, d_out_dist, d_out_n, d_out_nan, d_flags);
 }
 
 int clipdb_merge_strided_device(clipdb_ctx *c, const void *d_dist, int64_t dist_stride,

@@ -290,6 +290,20 @@ class GpuIndex:
             ctypes.c_void_p(out_dist.data_ptr()), ctypes.c_void_p(out_n.data_ptr()),
             ctypes.c_void_p(out_nan.data_ptr() if out_nan is not None else 0)))
 
+    def enable_batch(self, enable: bool = True) -> None:
+        """Build (or drop) the bf16 copy of the store used by the tensor-core batched path.
+        Afterwards ``search()`` with 16 or more queries uses it; results are identical."""
+        self._check(self._L.clipdb_enable_batch(self._ctx, int(bool(enable))))
+
+    def search_batch_device(self, d_queries, k: int, out_rowids, out_dist, out_n, out_nan, flags) -> None:
+        """Async batched search (<= 256 queries): torch CUDA tensors; ``flags[q] != 0`` marks
+        queries that must be re-run with ``search_device`` (see clipdb.h)."""
+        nq = d_queries.shape[0]
+        self._check(self._L.clipdb_search_batch_device(
+            self._ctx, ctypes.c_void_p(d_queries.data_ptr()), nq, int(k), ctypes.c_void_p(out_rowids.data_ptr()),
+            ctypes.c_void_p(out_dist.data_ptr()), ctypes.c_void_p(out_n.data_ptr()),
+            ctypes.c_void_p(out_nan.data_ptr() if out_nan is not None else 0), ctypes.c_void_p(flags.data_ptr())))
+
     def blend_device(self, d_e1, d_e2, d_w, d_negs, d_neg_w, d_out, d_flags=None) -> None:
         """Async batched K3: see clipdb_blend_device."""
         batch, dim = d_e1.shape

@@ -162,6 +162,27 @@ int clipdb_blend_search(clipdb_ctx *ctx, const float *e1, const float *e2, doubl
                         int64_t *out_rowids, float *out_dist, int32_t *out_n, int64_t *out_nan,
                         float *out_query, int32_t *out_flags);
 
+/* ---- batched queries (K4, BASELINE configs[2]) ------------------------------
+ * No reference equivalent (the reference answers one query at a time,
+ * idb:2070-2299).  clipdb_enable_batch(1) builds a bf16 copy of the resident
+ * store (2 bytes per element next to the 4-byte one) so that batches of queries
+ * can be pre-selected by one tcgen05 tensor-core contraction and re-ranked with
+ * the exact single-query arithmetic; results are identical to clipdb_search.
+ * Requirements: dim == 1152, cosine, no mask, 1 <= k <= 128, >= 65536 rows.
+ * With the batch store enabled, clipdb_search uses this path by itself for
+ * nq >= 16 and transparently re-runs flagged queries through the exact scan.
+ *
+ * clipdb_search_batch_device: device pointers, async, nq <= 256 per call.
+ * d_flags[q] != 0 (CLIPDB_BATCH_*) marks queries whose result is NOT valid
+ * (candidate overflow, zero-norm query): the caller must re-run those with
+ * clipdb_search_device. */
+#define CLIPDB_BATCH_OVERFLOW   1
+#define CLIPDB_BATCH_BAD_QUERY  2
+int clipdb_enable_batch(clipdb_ctx *ctx, int32_t enable);
+int clipdb_search_batch_device(clipdb_ctx *ctx, const float *d_queries, int32_t nq, int32_t k,
+                               int64_t *d_out_rowids, float *d_out_dist, int32_t *d_out_n,
+                               int64_t *d_out_nan, int32_t *d_flags);
+
 /* ---- shard merge (multi-GPU) --------------------------------
  * Merges `lists` per-shard result lists (each k entries, already sorted, shard
  * order = rowid order; counts[l] valid entries in list l) into the global

@@ -1,0 +1,105 @@
+"""K4: the tensor-core batched path must return exactly what the single-query path returns."""
+import numpy as np
+import pytest
+
+from clip_database_b200 import synth
+
+from conftest import have_gpu
+
+pytestmark = pytest.mark.gpu
+DIM = 1152
+
+
+@pytest.fixture(scope="module")
+def store():
+    assert have_gpu()
+    from clip_database_b200 import GpuIndex
+    rows = synth.unit_rows(100_000, DIM, 1234)
+    rows[5] = 0                                  # a zero row: NaN distance for every query
+    exact = GpuIndex(0)
+    exact.load(rows, np.arange(1, rows.shape[0] + 1))
+    batched = GpuIndex(0)
+    batched.load(rows, np.arange(1, rows.shape[0] + 1))
+    batched.enable_batch()
+    yield rows, exact, batched
+    exact.close()
+    batched.close()
+
+
+def same(a, b):
+    assert np.array_equal(a.counts, b.counts)
+    assert np.array_equal(a.nan_rows, b.nan_rows)
+    assert np.array_equal(a.rowids, b.rowids)
+    assert np.array_equal(a.distances.view(np.uint32), b.distances.view(np.uint32))
+
+
+@pytest.mark.parametrize("nq,k", [(256, 100), (256, 20), (16, 100), (100, 1), (300, 64), (37, 128)])
+def test_batched_equals_exact(store, nq, k):
+    rows, exact, batched = store
+    queries = synth.unit_rows(nq, DIM, 99)
+    before = batched.launch_count
+    got = batched.search(queries, k)
+    launches = batched.launch_count - before
+    assert launches <= 6 * ((nq + 255) // 256) + 8, "batched path was not taken"
+    same(got, exact.search(queries, k))
+
+
+def test_batched_clustered_queries(store):
+    """Queries near stored rows: top results are far from the noise tail."""
+    rows, exact, batched = store
+    rng = np.random.default_rng(7)
+    picks = rng.choice(rows.shape[0], 64, replace=False)
+    picks = picks[picks != 5]
+    q = rows[picks] + 0.1 * rng.standard_normal((len(picks), DIM), dtype=np.float32) / np.sqrt(DIM)
+    q = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+    got = batched.search(q, 100)
+    same(got, exact.search(q, 100))
+    assert np.array_equal(got.rowids[:, 0], picks + 1)
+
+
+def test_batched_zero_query_falls_back(store):
+    rows, exact, batched = store
+    queries = synth.unit_rows(32, DIM, 5)
+    queries[7] = 0
+    got = batched.search(queries, 20)
+    same(got, exact.search(queries, 20))
+    assert got.counts[7] == 0 and got.nan_rows[7] == rows.shape[0]
+
+
+def test_batched_overflow_falls_back():
+    """Dense cluster + tiny candidate capacity: the filter overflows, the host re-runs the
+    flagged queries through the exact scan, and the answer is still exact."""
+    from clip_database_b200 import GpuIndex
+    rng = np.random.default_rng(3)
+    base = synth.unit_rows(1, DIM, 8)[0]
+    rows = base[None, :] + 0.02 * rng.standard_normal((70_001, DIM), dtype=np.float32) / np.sqrt(DIM)
+    rows = (rows / np.linalg.norm(rows, axis=1, keepdims=True)).astype(np.float32)
+    queries = rows[:24] + 0.001 * rng.standard_normal((24, DIM), dtype=np.float32)
+    with GpuIndex(0) as exact, GpuIndex(0) as batched:
+        exact.load(rows)
+        batched.load(rows)
+        batched.set_option("batch_cand_cap", 512)
+        batched.enable_batch()
+        same(batched.search(queries, 50), exact.search(queries, 50))
+
+
+def test_batch_device_entry_point(store):
+    import torch
+    rows, exact, batched = store
+    queries = synth.unit_rows(256, DIM, 42)
+    k = 100
+    dq = torch.from_numpy(queries).cuda()
+    o_id = torch.empty((256, k), dtype=torch.int64, device="cuda")
+    o_d = torch.empty((256, k), dtype=torch.float32, device="cuda")
+    o_n = torch.empty(256, dtype=torch.int32, device="cuda")
+    o_nan = torch.empty(256, dtype=torch.int64, device="cuda")
+    flags = torch.empty(256, dtype=torch.int32, device="cuda")
+    batched.use_torch_stream()
+    batched.search_batch_device(dq, k, o_id, o_d, o_n, o_nan, flags)
+    torch.cuda.synchronize()
+    batched.set_stream(None)
+    assert int(flags.abs().sum()) == 0
+    want = exact.search(queries, k)
+    assert np.array_equal(o_id.cpu().numpy(), want.rowids)
+    assert np.array_equal(o_d.cpu().numpy().view(np.uint32), want.distances.view(np.uint32))
+    assert np.array_equal(o_nan.cpu().numpy(), want.nan_rows)
