@@ -51,8 +51,10 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--k", type=int, default=20)
     ap.add_argument("--rows", type=int, default=0, help="rows per GPU (default 10M at N=1, 12.5M at N>1)")
-    ap.add_argument("--workload", default="single", choices=["single", "blend"],
-                    help="single: configs[1]; blend: configs[3] (0.7/0.3 blend + negative, then the scan)")
+    ap.add_argument("--workload", default="single", choices=["single", "blend", "batch"],
+                    help="single: configs[1]; blend: configs[3] (0.7/0.3 blend + negative, then the scan); "
+                         "batch: configs[2] (B queries per step through the tcgen05 contraction + fp32 re-rank)")
+    ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--variant", type=int, default=0, help="scan kernel: 0 auto, 1 TMA ring, 2 direct loads")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-rows", type=int, default=100_000)
@@ -256,6 +258,91 @@ def generate_rows(torch, device, n_rows, seed):
     return rows
 
 
+def run_batch_workload(args, torch, idx, rows, rows_per_gpu, device, rank, local_rank):
+    """BASELINE configs[2]: B = 256 queries per step, k = 100 (pass --k 100), one GPU.
+    metric = queries/s; roofline = tensor pipe (flops of the full-store contraction / the
+    filter-pass kernel's own duration)."""
+    B, k = args.batch, args.k
+    idx.enable_batch()
+    rng = np.random.default_rng(99)
+    n_sets = 4
+    host_q = rng.standard_normal((n_sets, B, DIM), dtype=np.float32)
+    host_q /= np.linalg.norm(host_q, axis=2, keepdims=True)
+    d_q = torch.from_numpy(host_q).to(device)
+    o_ids = torch.empty((B, k), dtype=torch.int64, device=device)
+    o_dist = torch.empty((B, k), dtype=torch.float32, device=device)
+    o_n = torch.zeros(B, dtype=torch.int32, device=device)
+    o_nan = torch.zeros(B, dtype=torch.int64, device=device)
+    flags = torch.zeros(B, dtype=torch.int32, device=device)
+    sampler = ClockSampler(local_rank)
+
+    for i in range(args.warmup):
+        idx.search_batch_device(d_q[i % n_sets], k, o_ids, o_dist, o_n, o_nan, flags)
+    torch.cuda.synchronize()
+    sampler.start()
+    launches0 = idx.launch_count
+    idx.profile(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        idx.search_batch_device(d_q[i % n_sets], k, o_ids, o_dist, o_n, o_nan, flags)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms_step = ev0.elapsed_time(ev1) / args.steps
+    gemm_ms, gemm_n = idx.profile_read()
+    idx.profile(False)
+    launches = idx.launch_count - launches0
+    flagged = int((flags != 0).sum())
+
+    for i in range(min(args.warmup, 3)):
+        idx.search(host_q[i % n_sets], k)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        last = idx.search(host_q[i % n_sets], k)
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    sampler.stop()
+    assert np.all(last.counts == k)
+
+    # spot check against the exact single-query path (same context, batch path bypassed by nq=1)
+    check = [idx.search(host_q[(args.steps - 1) % n_sets][j], k) for j in (0, B // 2, B - 1)]
+    for j, c in zip((0, B // 2, B - 1), check):
+        assert np.array_equal(c.rowids[0], last.rowids[j]) and np.array_equal(c.distances[0], last.distances[j])
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    flops = 2.0 * B * rows_per_gpu * DIM
+    gemm_avg = gemm_ms / max(gemm_n, 1)
+    line = {
+        "metric": "knn_batched_queries_per_s", "value": B * 1e3 / ms_step, "unit": "queries/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16 pre-select + f32 re-rank", "data": "synthetic",
+        "config": {"workload": "batched cosine KNN, B=%d queries per step, k=%d, %d x 1152 rows "
+                               "(BASELINE configs[2]): tcgen05 contraction + fp32 re-rank" % (B, k, rows_per_gpu),
+                   "rows_per_gpu": rows_per_gpu, "batch": B, "k": k, "dim": DIM,
+                   "store_bytes": {"fp32": rows_per_gpu * ROW_BYTES, "bf16": rows_per_gpu * DIM * 2},
+                   "l2": "inputs_larger_than_L2"},
+        "equivalent_scan_GBps_fp32": B * rows_per_gpu * ROW_BYTES / 1e9 / (ms_step / 1e3),
+        "e2e": {"value": B * 1e3 / e2e_ms, "unit": "queries/s", "h2d_bytes_per_step": B * ROW_BYTES,
+                "d2h_bytes_per_step": B * (k * 12 + 12) + B * 4, "ms_per_step": e2e_ms,
+                "api": "GpuIndex.search (clipdb_search, nq=%d)" % B},
+        "gpu_launches": int(launches), "flagged_queries_last_step": flagged,
+        "roofline": {"bound": "tensor", "kernel": "batch_gemm_kernel<filter>", "achieved": flops / 1e12 / (gemm_avg / 1e3),
+                     "peak": peak, "unit": "TFLOP/s", "frac": flops / 1e12 / (gemm_avg / 1e3) / peak,
+                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained", "flops_per_launch": flops,
+                     "avg_launch_ms": gemm_avg, "launches_timed": int(gemm_n),
+                     "hbm_GBps_bf16_store": rows_per_gpu * DIM * 2 / 1e9 / (gemm_avg / 1e3), "traffic": None},
+        "clocks": sampler.summary(),
+    }
+    print(json.dumps(line), flush=True)
+    idx.close()
+    return 0
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -289,6 +376,9 @@ def main():
     idx.set_option("scan_variant", args.variant)
     backend = CudaShardBackend(idx)          # puts the context on torch's current stream
     sharded = ShardedIndex(backend)
+
+    if args.workload == "batch":
+        return run_batch_workload(args, torch, idx, rows, rows_per_gpu, device, rank, local_rank)
 
     n_q = 64
     host_q = np.random.default_rng(99).standard_normal((n_q, DIM), dtype=np.float32)

@@ -16,10 +16,10 @@
 //   3. pass A (every 16th tile): the epilogue dumps u = score/||row|| for a row sample;
 //      per query, tau = the k-th best sampled u  =>  at least k rows have u >= tau.
 //   4. pass B (all tiles): the epilogue keeps (q,row) iff u >= tau - 2E||q||, where
-//      E = 4.5e-3 bounds |cos^ - cos| for bf16-rounded operands (2^-8 from the two
-//      roundings, Cauchy-Schwarz over the 1152 terms, + accumulation slack).  Every row of
-//      the true top-k satisfies this (it has cos >= cos_k >= tau/||q|| - E), so the
-//      candidate set is a superset of the answer — a guarantee, not a heuristic.
+//      E bounds |cos^ - cos| for bf16-rounded operands: the measured rounding-error norms
+//      of the rows (max over the store) and of the query, + accumulation slack (~2.6e-3).
+//      Every row of the true top-k satisfies this (it has cos >= cos_k >= tau/||q|| - E),
+//      so the candidate set is a superset of the answer — a guarantee, not a heuristic.
 //   5. re-rank: each candidate's distance is recomputed with K1's exact float32/double
 //      arithmetic and the same 64-bit keys, so ids and distance bits equal the
 //      single-query path.  Queries whose candidate list overflows (or whose norm is
@@ -52,7 +52,11 @@ constexpr int BQ_HEADER = 2048;  // barriers, TMEM base, thresholds
 constexpr int BQ_SMEM_BYTES = BQ_HEADER + BQ_STAGES * BQ_STAGE_BYTES + 1024;  // + alignment slack
 constexpr int BQ_TMEM_COLS = 512;
 constexpr int BQ_SAMPLE_STRIDE = 16;  // pass A visits every 16th tile
-constexpr float BQ_COS_ERROR = 4.5e-3f;  // E: bound on |cos^ - cos| with bf16 operands
+// |cos^ - cos| <= e_d + e_q (1 + e_d) + slack, where e_d = max over rows of ||d^ - d|| / ||d|| and
+// e_q = ||q^ - q|| / ||q|| are the MEASURED bf16 rounding-error norms (Cauchy-Schwarz on
+// q.(d^-d) + (q^-q).d^) and the slack covers the tensor core's fp32 accumulation of 1152 exact
+// bf16 x bf16 products (<= 1152 * 2^-23 relative to ||q^|| ||d^||) and the fp32 path's own 3e-7.
+constexpr float BQ_ACCUM_SLACK = 2.0e-4f;
 
 // idesc for kind::f16: D=F32, A=B=BF16, both K-major, N=256, M=128 (cute::UMMA::InstrDescriptor)
 constexpr uint32_t BQ_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((BQ_N >> 3) << 17) | ((BQ_M >> 4) << 24);
@@ -126,15 +130,17 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __global__ void __launch_bounds__(256) build_bf16_store_kernel(const float *__restrict__ rows, long long n,
                                                                __nv_bfloat16 *__restrict__ out,
                                                                float *__restrict__ inv_norm,
-                                                               unsigned long long *__restrict__ bad_rows) {
+                                                               unsigned long long *__restrict__ bad_rows,
+                                                               unsigned int *__restrict__ max_row_err_bits) {
     const int lane = threadIdx.x & 31;
     const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
     unsigned bad = 0;
+    float worst = 0.f;
     for (long long r = warp; r < n; r += warps) {
         const float4 *src = reinterpret_cast<const float4 *>(rows + r * SCAN_DIM);
         uint2 *dst = reinterpret_cast<uint2 *>(out + r * SCAN_DIM);
-        float ss = 0.f;
+        float ss = 0.f, es = 0.f;
 #pragma unroll
         for (int j = 0; j < SCAN_CHUNKS; j++) {
             const float4 v = ldg_stream(src + lane + 32 * j);
@@ -143,38 +149,60 @@ __global__ void __launch_bounds__(256) build_bf16_store_kernel(const float *__re
             ss = fmaf(v.z, v.z, ss);
             ss = fmaf(v.w, v.w, ss);
             __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            const float2 rl = __bfloat1622float2(lo), rh = __bfloat1622float2(hi);
+            es = fmaf(rl.x - v.x, rl.x - v.x, es);
+            es = fmaf(rl.y - v.y, rl.y - v.y, es);
+            es = fmaf(rh.x - v.z, rh.x - v.z, es);
+            es = fmaf(rh.y - v.w, rh.y - v.w, es);
             uint2 packed;
             packed.x = *reinterpret_cast<uint32_t *>(&lo);
             packed.y = *reinterpret_cast<uint32_t *>(&hi);
             dst[lane + 32 * j] = packed;
         }
         ss = warp_sum(ss);
+        es = warp_sum(es);
         const float inv = 1.0f / sqrtf(ss);
         const bool ok = ss > 0.f && isfinite(inv) && isfinite(ss);
         if (lane == 0) {
             inv_norm[r] = ok ? inv : __int_as_float(0x7fc00000);  // NaN: never passes a >= test
             if (!ok) bad++;
+            else worst = fmaxf(worst, sqrtf(es) * inv * 1.0001f);  // ||d^ - d|| / ||d||, rounded up
         }
     }
-    if (lane == 0 && bad) atomicAdd(bad_rows, static_cast<unsigned long long>(bad));
+    if (lane == 0) {
+        if (bad) atomicAdd(bad_rows, static_cast<unsigned long long>(bad));
+        atomicMax(max_row_err_bits, __float_as_uint(worst));  // non-negative floats order as uints
+    }
 }
 
 // one CTA per query slot (256 slots): bf16 copy (zeros past nq), ||q||
 __global__ void __launch_bounds__(128) prep_queries_kernel(const float *__restrict__ q, int nq,
                                                            __nv_bfloat16 *__restrict__ qb,
-                                                           float *__restrict__ q_norm) {
-    __shared__ float red[4];
+                                                           float *__restrict__ q_norm,
+                                                           float *__restrict__ q_err) {
+    __shared__ float red[8];
     const int slot = blockIdx.x, tid = threadIdx.x;
-    float ss = 0.f;
+    float ss = 0.f, es = 0.f;
     for (int i = tid; i < SCAN_DIM; i += 128) {
         const float v = slot < nq ? q[static_cast<size_t>(slot) * SCAN_DIM + i] : 0.f;
-        qb[static_cast<size_t>(slot) * SCAN_DIM + i] = __float2bfloat16_rn(v);
+        const __nv_bfloat16 b = __float2bfloat16_rn(v);
+        qb[static_cast<size_t>(slot) * SCAN_DIM + i] = b;
+        const float e = __bfloat162float(b) - v;
         ss = fmaf(v, v, ss);
+        es = fmaf(e, e, es);
     }
     ss = warp_sum(ss);
-    if ((tid & 31) == 0) red[tid >> 5] = ss;
+    es = warp_sum(es);
+    if ((tid & 31) == 0) {
+        red[tid >> 5] = ss;
+        red[4 + (tid >> 5)] = es;
+    }
     __syncthreads();
-    if (tid == 0) q_norm[slot] = sqrtf(red[0] + red[1] + red[2] + red[3]);
+    if (tid == 0) {
+        const float nrm = sqrtf(red[0] + red[1] + red[2] + red[3]);
+        q_norm[slot] = nrm;
+        q_err[slot] = nrm > 0.f ? sqrtf(red[4] + red[5] + red[6] + red[7]) / nrm * 1.0001f : 0.f;
+    }
 }
 
 // ---- the contraction ---------------------------------------------------------------------------
@@ -333,50 +361,86 @@ __global__ void __launch_bounds__(BQ_THREADS, 1) batch_gemm_kernel(const __grid_
     if (warp == 1) tmem_dealloc(tmem_base, BQ_TMEM_COLS);
 }
 
-// ---- thresholds: per query, tau = k-th best sampled u; thr = tau - 2E||q|| ------------------------
+// ---- per-query selection in two levels ----------------------------------------------------
+// Both the threshold step (k-th best sampled u) and the re-rank (k best exact distances) are
+// "top-k of one query's items".  Level 1: grid (query, part) — each CTA keeps warp-level
+// candidate lists over its share of the items and writes one sorted list of 32*KPL keys.
+// Level 2: one CTA per query sorts the parts' lists and either derives the threshold or
+// decodes the final result.  Keys make the outcome independent of how items were split.
+constexpr int BQ_SEL_WARPS = 8;
+constexpr int BQ_SEL_THREADS = BQ_SEL_WARPS * 32;
+constexpr int BQ_THR_PARTS = 8;      // parts per query over the sampled scores
+constexpr int BQ_RERANK_PARTS = 4;   // parts per query over the candidate rows
+
 template <int KPL>
-__global__ void __launch_bounds__(256) batch_threshold_kernel(const float *__restrict__ scores, long long sample_rows,
-                                                              const float *__restrict__ q_norm, int nq, int k,
-                                                              float *__restrict__ thr, int *__restrict__ flags) {
-    __shared__ uint64_t scratch[8 * 32 * KPL];
-    const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (q >= nq) {  // padding slots: never produce candidates
-        if (tid == 0) thr[q] = __int_as_float(0x7f800000);
-        return;
-    }
-    const float qn = q_norm[q];
+__device__ __forceinline__ void write_part_list(WarpTopK<KPL> &top, uint64_t *scratch, uint64_t *dst, int tid,
+                                                int warp, int lane) {
+    top.dump(scratch + warp * 32 * KPL, lane);
+    __syncthreads();
+    block_bitonic_sort(scratch, BQ_SEL_WARPS * 32 * KPL, tid, BQ_SEL_THREADS);
+    for (int i = tid; i < 32 * KPL; i += BQ_SEL_THREADS) dst[i] = scratch[i];
+}
+
+// level 1 over the sampled scores: best = largest u, so keys order by -u
+template <int KPL>
+__global__ void __launch_bounds__(BQ_SEL_THREADS) batch_sample_topk_kernel(const float *__restrict__ scores,
+                                                                           long long sample_rows, int k,
+                                                                           uint64_t *__restrict__ part_keys) {
+    __shared__ uint64_t scratch[BQ_SEL_WARPS * 32 * KPL];
+    const int q = blockIdx.x, part = blockIdx.y, parts = gridDim.y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long lo = sample_rows * part / parts, hi = sample_rows * (part + 1) / parts;
     WarpTopK<KPL> top;
     top.init(k, lane);
     const float *src = scores + static_cast<long long>(q) * sample_rows;
-    for (long long base = static_cast<long long>(warp) * 32; base < sample_rows; base += 256) {
+    for (long long base = lo + static_cast<long long>(warp) * 32; base < hi; base += BQ_SEL_THREADS) {
         const long long i = base + lane;
-        const float u = i < sample_rows ? src[i] : __int_as_float(0xff800000);
-        // best = largest u: order keys by -u.  One element per lane, offered one at a time
-        // (warp-uniform inserts); candidates are rare after the first few hundred rows.
+        const float u = i < hi ? src[i] : __int_as_float(0xff800000);
         const bool valid = u == u && u > __int_as_float(0xff800000);
         const uint64_t key = valid ? make_key(-u, static_cast<uint32_t>(i)) : KEY_EMPTY;
         unsigned pending = __ballot_sync(FULL_MASK, key < top.thr);
-        while (pending) {
+        while (pending) {  // warp-uniform inserts, one offered key at a time (rare after warm-up)
             const int src_lane = __ffs(pending) - 1;
             const uint64_t kk = __shfl_sync(FULL_MASK, key, src_lane);
             if (kk < top.thr) top.insert(kk, lane);
             pending &= pending - 1;
         }
     }
-    top.dump(scratch + warp * 32 * KPL, lane);
-    __syncthreads();
-    block_bitonic_sort(scratch, 8 * 32 * KPL, tid, 256);
+    write_part_list<KPL>(top, scratch, part_keys + (static_cast<size_t>(q) * parts + part) * (32 * KPL), tid, warp, lane);
+}
+
+// level 2 for thresholds: tau = k-th best sampled u; thr = tau - 2E||q||
+__global__ void __launch_bounds__(256) batch_threshold_finish_kernel(const uint64_t *__restrict__ part_keys,
+                                                                     int parts, int stride,
+                                                                     const float *__restrict__ q_norm,
+                                                                     const float *__restrict__ q_err,
+                                                                     const unsigned int *__restrict__ max_row_err_bits,
+                                                                     int nq, int k, float *__restrict__ thr,
+                                                                     int *__restrict__ flags) {
+    __shared__ uint64_t s[BQ_THR_PARTS * 128];
+    const int q = blockIdx.x, tid = threadIdx.x;
+    if (q >= nq) {  // padding slots never produce candidates
+        if (tid == 0) thr[q] = __int_as_float(0x7f800000);
+        return;
+    }
+    const int total = parts * stride, padded = next_pow2(total);
+    for (int i = tid; i < padded; i += 256)
+        s[i] = i < total ? part_keys[static_cast<size_t>(q) * total + i] : KEY_EMPTY;
+    block_bitonic_sort(s, padded, tid, 256);
     if (tid == 0) {
-        const uint64_t kth = scratch[k - 1];
+        const float qn = q_norm[q];
+        const uint64_t kth = s[k - 1];
         int f = 0;
         float t = __int_as_float(0x7f800000);
         if (!(qn > 0.f) || !isfinite(qn)) {
             f = BQ_FLAG_BAD_QUERY;
         } else if (kth == KEY_EMPTY) {
-            t = __int_as_float(0xff800000);   // fewer than k finite samples: keep everything
+            t = __int_as_float(0xff800000);  // fewer than k finite samples: keep everything
         } else {
             const float tau = -orderable_f32(static_cast<uint32_t>(kth >> 32));
-            t = tau - 2.0f * BQ_COS_ERROR * qn;
+            const float ed = __uint_as_float(*max_row_err_bits), eq = q_err[q];
+            const float bound = ed + eq * (1.0f + ed) + BQ_ACCUM_SLACK;   // E
+            t = tau - 2.0f * bound * qn;
         }
         thr[q] = t;
         flags[q] = f;
@@ -389,21 +453,21 @@ struct RerankArgs {
     const float *queries;         // [nq][1152] fp32
     const unsigned int *cand_count;
     const unsigned int *cand_rows;
+    uint64_t *part_keys;          // [nq][BQ_RERANK_PARTS][32*KPL]
     int cand_cap;
     int k;
     int *flags;                   // |= BQ_FLAG_OVERFLOW
     DecodeArgs dec;               // out arrays are [nq][k]; out_n/out_nan [nq]
     const unsigned long long *bad_rows;  // rows of the store with NaN distance for any query
-    long long n;
 };
 
 template <int KPL>
-__global__ void __launch_bounds__(512) batch_rerank_kernel(const RerankArgs a) {
-    __shared__ uint64_t scratch[16 * 32 * KPL];
-    const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+__global__ void __launch_bounds__(BQ_SEL_THREADS) batch_rerank_kernel(const RerankArgs a) {
+    __shared__ uint64_t scratch[BQ_SEL_WARPS * 32 * KPL];
+    const int q = blockIdx.x, part = blockIdx.y, parts = gridDim.y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned total = a.cand_count[q];
-    const bool overflow = total > static_cast<unsigned>(a.cand_cap);
-    const unsigned count = overflow ? static_cast<unsigned>(a.cand_cap) : total;
+    const unsigned count = total > static_cast<unsigned>(a.cand_cap) ? static_cast<unsigned>(a.cand_cap) : total;
 
     float4 qv[SCAN_CHUNKS];
     const float4 *q4 = reinterpret_cast<const float4 *>(a.queries + static_cast<size_t>(q) * SCAN_DIM);
@@ -423,7 +487,8 @@ __global__ void __launch_bounds__(512) batch_rerank_kernel(const RerankArgs a) {
     top.init(a.k, lane);
     unsigned nan_rows = 0;
     const unsigned int *list = a.cand_rows + static_cast<size_t>(q) * a.cand_cap;
-    for (unsigned i = warp; i < count; i += 16) {
+    const unsigned stride = static_cast<unsigned>(parts * BQ_SEL_WARPS);
+    for (unsigned i = part * BQ_SEL_WARPS + warp; i < count; i += stride) {
         const long long pos = list[i];
         const float4 *src = reinterpret_cast<const float4 *>(a.rows + pos * SCAN_DIM);
         float4 v[SCAN_CHUNKS];
@@ -436,24 +501,32 @@ __global__ void __launch_bounds__(512) batch_rerank_kernel(const RerankArgs a) {
         const float t1 = warp_sum((s1[0] + s1[1]) + (s1[2] + s1[3]));
         offer_row<KPL, METRIC_COSINE, false>(t0, t1, sqrt_b, rsqrt_b, pos, top, nan_rows, nullptr, lane);
     }
-    top.dump(scratch + warp * 32 * KPL, lane);
-    __syncthreads();
-    block_bitonic_sort(scratch, 16 * 32 * KPL, tid, 512);
+    write_part_list<KPL>(top, scratch, a.part_keys + (static_cast<size_t>(q) * parts + part) * (32 * KPL), tid, warp,
+                         lane);
+}
 
+// level 2 for the re-rank: merge the parts, decode the k best
+__global__ void __launch_bounds__(256) batch_rerank_finish_kernel(const RerankArgs a, int parts, int stride) {
+    __shared__ uint64_t s[BQ_RERANK_PARTS * 128];
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const int total = parts * stride, padded = next_pow2(total);
+    for (int i = tid; i < padded; i += 256)
+        s[i] = i < total ? a.part_keys[static_cast<size_t>(q) * total + i] : KEY_EMPTY;
+    block_bitonic_sort(s, padded, tid, 256);
     DecodeArgs d = a.dec;
     d.out_rowids += static_cast<size_t>(q) * a.k;
     d.out_dist += static_cast<size_t>(q) * a.k;
     int found = 0;
-    for (int base = 0; base < a.k; base += 512) {
+    for (int base = 0; base < a.k; base += 256) {
         const int i = base + tid;
-        const bool valid = i < a.k && scratch[i] != KEY_EMPTY;
-        if (valid) decode_one(d, i, scratch[i]);
+        const bool valid = i < a.k && i < padded && s[i] != KEY_EMPTY;
+        if (valid) decode_one(d, i, s[i]);
         found += __syncthreads_count(valid);
     }
     if (tid == 0) {
         d.out_n[q] = found;
         if (d.out_nan) d.out_nan[q] = static_cast<int64_t>(*a.bad_rows);
-        if (overflow) a.flags[q] |= BQ_FLAG_OVERFLOW;
+        if (a.cand_count[q] > static_cast<unsigned>(a.cand_cap)) a.flags[q] |= BQ_FLAG_OVERFLOW;
     }
 }
 

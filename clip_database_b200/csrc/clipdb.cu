@@ -66,7 +66,7 @@ struct clipdb_ctx {
 
     // batched path (K4): bf16 copy of the store + workspaces
     bool batch_enabled = false;
-    Buffer bf16_rows, inv_norm, bad_rows, bq_queries, bq_qnorm, bq_scores, bq_thr, bq_flags, bq_count, bq_cand;
+    Buffer bf16_rows, inv_norm, bad_rows, bq_queries, bq_qnorm, bq_scores, bq_thr, bq_flags, bq_count, bq_cand, bq_parts, bq_qerr, row_err;
     CUtensorMap map_rows, map_q;
     int64_t bq_sample_rows = 0;
     int64_t batch_min_nq = 16;      // clipdb_search switches to the batched path from this nq
@@ -586,15 +586,19 @@ int batch_build_locked(clipdb_ctx *c) {
     RC_TRY(ensure_device(c, c->bad_rows, sizeof(unsigned long long)));
     RC_TRY(ensure_device(c, c->bq_queries, static_cast<size_t>(BQ_N) * SCAN_DIM * 2));
     RC_TRY(ensure_device(c, c->bq_qnorm, BQ_N * sizeof(float)));
+    RC_TRY(ensure_device(c, c->bq_qerr, BQ_N * sizeof(float)));
+    RC_TRY(ensure_device(c, c->row_err, sizeof(unsigned int)));
+    CU_TRY(c, cudaMemsetAsync(c->row_err.p, 0, sizeof(unsigned int), c->stream));
     RC_TRY(ensure_device(c, c->bq_scores, static_cast<size_t>(BQ_N) * c->bq_sample_rows * sizeof(float)));
     RC_TRY(ensure_device(c, c->bq_thr, BQ_N * sizeof(float)));
     RC_TRY(ensure_device(c, c->bq_flags, BQ_N * sizeof(int32_t)));
     RC_TRY(ensure_device(c, c->bq_count, BQ_N * sizeof(unsigned int)));
     RC_TRY(ensure_device(c, c->bq_cand, static_cast<size_t>(BQ_N) * c->batch_cand_cap * sizeof(unsigned int)));
+    RC_TRY(ensure_device(c, c->bq_parts, static_cast<size_t>(BQ_N) * BQ_THR_PARTS * 128 * sizeof(uint64_t)));
     CU_TRY(c, cudaMemsetAsync(c->bad_rows.p, 0, sizeof(unsigned long long), c->stream));
     build_bf16_store_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(
         c->rows, c->n, static_cast<__nv_bfloat16 *>(c->bf16_rows.p), static_cast<float *>(c->inv_norm.p),
-        static_cast<unsigned long long *>(c->bad_rows.p));
+        static_cast<unsigned long long *>(c->bad_rows.p), static_cast<unsigned int *>(c->row_err.p));
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     RC_TRY(encode_bf16_map(c, &c->map_rows, c->bf16_rows.p, static_cast<uint64_t>(c->n), BQ_M));
@@ -614,16 +618,23 @@ bool batch_eligible(const clipdb_ctx *c, int32_t nq, int32_t k, int32_t metric, 
 template <int KPL>
 int batch_launch_tail(clipdb_ctx *c, const float *d_queries, int32_t nq, int32_t k, int64_t *d_out_rowids,
                       float *d_out_dist, int32_t *d_out_n, int64_t *d_out_nan, int32_t *d_flags, bool threshold) {
+    uint64_t *parts = static_cast<uint64_t *>(c->bq_parts.p);
     if (threshold) {
-        batch_threshold_kernel<KPL><<<BQ_N, 256, 0, c->stream>>>(
-            static_cast<const float *>(c->bq_scores.p), c->bq_sample_rows, static_cast<const float *>(c->bq_qnorm.p),
-            nq, k, static_cast<float *>(c->bq_thr.p), d_flags);
+        batch_sample_topk_kernel<KPL><<<dim3(nq, BQ_THR_PARTS), BQ_SEL_THREADS, 0, c->stream>>>(
+            static_cast<const float *>(c->bq_scores.p), c->bq_sample_rows, k, parts);
+        CU_TRY(c, cudaGetLastError());
+        c->launches++;
+        batch_threshold_finish_kernel<<<BQ_N, 256, 0, c->stream>>>(
+            parts, BQ_THR_PARTS, 32 * KPL, static_cast<const float *>(c->bq_qnorm.p),
+            static_cast<const float *>(c->bq_qerr.p), static_cast<const unsigned int *>(c->row_err.p), nq, k,
+            static_cast<float *>(c->bq_thr.p), d_flags);
     } else {
         RerankArgs r{};
         r.rows = c->rows;
         r.queries = d_queries;
         r.cand_count = static_cast<const unsigned int *>(c->bq_count.p);
         r.cand_rows = static_cast<const unsigned int *>(c->bq_cand.p);
+        r.part_keys = parts;
         r.cand_cap = static_cast<int>(c->batch_cand_cap);
         r.k = k;
         r.flags = d_flags;
@@ -635,8 +646,10 @@ int batch_launch_tail(clipdb_ctx *c, const float *d_queries, int32_t nq, int32_t
         r.dec.out_nan = d_out_nan;
         r.dec.k = k;
         r.bad_rows = static_cast<const unsigned long long *>(c->bad_rows.p);
-        r.n = c->n;
-        batch_rerank_kernel<KPL><<<nq, 512, 0, c->stream>>>(r);
+        batch_rerank_kernel<KPL><<<dim3(nq, BQ_RERANK_PARTS), BQ_SEL_THREADS, 0, c->stream>>>(r);
+        CU_TRY(c, cudaGetLastError());
+        c->launches++;
+        batch_rerank_finish_kernel<<<nq, 256, 0, c->stream>>>(r, BQ_RERANK_PARTS, 32 * KPL);
     }
     CU_TRY(c, cudaGetLastError());
     c->launches++;
@@ -654,7 +667,7 @@ int batch_search_device_locked(clipdb_ctx *c, const float *d_queries, int32_t nq
     const int kpl = k <= 32 ? 1 : (k <= 64 ? 2 : 4);
     const int tiles = static_cast<int>((c->n + BQ_M - 1) / BQ_M);
     prep_queries_kernel<<<BQ_N, 128, 0, c->stream>>>(d_queries, nq, static_cast<__nv_bfloat16 *>(c->bq_queries.p),
-                                                     static_cast<float *>(c->bq_qnorm.p));
+                                                     static_cast<float *>(c->bq_qnorm.p), static_cast<float *>(c->bq_qerr.p));
     CU_TRY(c, cudaGetLastError());
     c->launches++;
 
@@ -747,7 +760,7 @@ void clipdb_destroy(clipdb_ctx *c) {
                           &c->cub_tmp, &c->d_query, &c->d_out_rowids, &c->d_out_dist, &c->d_out_n,
                           &c->d_out_nan, &c->d_blend_in, &c->d_blend_flags, &c->bf16_rows, &c->inv_norm,
                           &c->bad_rows, &c->bq_queries, &c->bq_qnorm, &c->bq_scores, &c->bq_thr, &c->bq_flags,
-                          &c->bq_count, &c->bq_cand};
+                          &c->bq_count, &c->bq_cand, &c->bq_parts, &c->bq_qerr, &c->row_err};
         for (Buffer *b : bufs) free_buffer(*b);
         if (c->pinned.p) cudaFreeHost(c->pinned.p);
         if (c->pinned_aux.p) cudaFreeHost(c->pinned_aux.p);

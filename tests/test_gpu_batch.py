@@ -40,7 +40,7 @@ def test_batched_equals_exact(store, nq, k):
     before = batched.launch_count
     got = batched.search(queries, k)
     launches = batched.launch_count - before
-    assert launches <= 6 * ((nq + 255) // 256) + 8, "batched path was not taken"
+    assert launches <= 8 * ((nq + 255) // 256) + 8, "batched path was not taken"
     same(got, exact.search(queries, k))
 
 
