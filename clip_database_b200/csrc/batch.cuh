@@ -393,17 +393,26 @@ __global__ void __launch_bounds__(BQ_SEL_THREADS) batch_sample_topk_kernel(const
     WarpTopK<KPL> top;
     top.init(k, lane);
     const float *src = scores + static_cast<long long>(q) * sample_rows;
-    for (long long base = lo + static_cast<long long>(warp) * 32; base < hi; base += BQ_SEL_THREADS) {
-        const long long i = base + lane;
-        const float u = i < hi ? src[i] : __int_as_float(0xff800000);
-        const bool valid = u == u && u > __int_as_float(0xff800000);
-        const uint64_t key = valid ? make_key(-u, static_cast<uint32_t>(i)) : KEY_EMPTY;
-        unsigned pending = __ballot_sync(FULL_MASK, key < top.thr);
-        while (pending) {  // warp-uniform inserts, one offered key at a time (rare after warm-up)
-            const int src_lane = __ffs(pending) - 1;
-            const uint64_t kk = __shfl_sync(FULL_MASK, key, src_lane);
-            if (kk < top.thr) top.insert(kk, lane);
-            pending &= pending - 1;
+    constexpr int U = 8;  // independent loads in flight per lane (the loop is latency-bound otherwise)
+    for (long long base = lo + static_cast<long long>(warp) * (32 * U); base < hi; base += BQ_SEL_WARPS * 32 * U) {
+        float u[U];
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            const long long i = base + j * 32 + lane;
+            u[j] = i < hi ? __ldg(src + i) : __int_as_float(0xff800000);
+        }
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            const long long i = base + j * 32 + lane;
+            const bool valid = u[j] == u[j] && u[j] > __int_as_float(0xff800000);
+            const uint64_t key = valid ? make_key(-u[j], static_cast<uint32_t>(i)) : KEY_EMPTY;
+            unsigned pending = __ballot_sync(FULL_MASK, key < top.thr);
+            while (pending) {  // warp-uniform inserts, one offered key at a time (rare after warm-up)
+                const int src_lane = __ffs(pending) - 1;
+                const uint64_t kk = __shfl_sync(FULL_MASK, key, src_lane);
+                if (kk < top.thr) top.insert(kk, lane);
+                pending &= pending - 1;
+            }
         }
     }
     write_part_list<KPL>(top, scratch, part_keys + (static_cast<size_t>(q) * parts + part) * (32 * KPL), tid, warp, lane);
@@ -487,19 +496,40 @@ __global__ void __launch_bounds__(BQ_SEL_THREADS) batch_rerank_kernel(const Rera
     top.init(a.k, lane);
     unsigned nan_rows = 0;
     const unsigned int *list = a.cand_rows + static_cast<size_t>(q) * a.cand_cap;
-    const unsigned stride = static_cast<unsigned>(parts * BQ_SEL_WARPS);
-    for (unsigned i = part * BQ_SEL_WARPS + warp; i < count; i += stride) {
-        const long long pos = list[i];
-        const float4 *src = reinterpret_cast<const float4 *>(a.rows + pos * SCAN_DIM);
-        float4 v[SCAN_CHUNKS];
+    // a warp takes 32 candidates at a time (one coalesced index load) and keeps two rows'
+    // loads in flight: the gather is latency-bound, not bandwidth-bound
+    const unsigned chunk_stride = static_cast<unsigned>(parts * BQ_SEL_WARPS) * 32u;
+    for (unsigned c0 = (part * BQ_SEL_WARPS + warp) * 32u; c0 < count; c0 += chunk_stride) {
+        const unsigned mine = c0 + lane < count ? list[c0 + lane] : 0u;
+        const int m = count - c0 < 32u ? static_cast<int>(count - c0) : 32;
+        for (int e = 0; e < m; e += 2) {
+            const long long pos0 = __shfl_sync(FULL_MASK, mine, e);
+            const bool two = e + 1 < m;
+            const long long pos1 = __shfl_sync(FULL_MASK, mine, two ? e + 1 : e);
+            const float4 *src0 = reinterpret_cast<const float4 *>(a.rows + pos0 * SCAN_DIM);
+            const float4 *src1 = reinterpret_cast<const float4 *>(a.rows + pos1 * SCAN_DIM);
+            float4 v0[SCAN_CHUNKS], v1[SCAN_CHUNKS];
 #pragma unroll
-        for (int j = 0; j < SCAN_CHUNKS; j++) v[j] = ldg_stream(src + lane + 32 * j);
-        float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int j = 0; j < SCAN_CHUNKS; j++) v0[j] = ldg_stream(src0 + lane + 32 * j);
 #pragma unroll
-        for (int j = 0; j < SCAN_CHUNKS; j++) accumulate<METRIC_COSINE>(v[j], qv[j], s0, s1);
-        const float t0 = warp_sum((s0[0] + s0[1]) + (s0[2] + s0[3]));
-        const float t1 = warp_sum((s1[0] + s1[1]) + (s1[2] + s1[3]));
-        offer_row<KPL, METRIC_COSINE, false>(t0, t1, sqrt_b, rsqrt_b, pos, top, nan_rows, nullptr, lane);
+            for (int j = 0; j < SCAN_CHUNKS; j++) v1[j] = ldg_stream(src1 + lane + 32 * j);
+            {
+                float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int j = 0; j < SCAN_CHUNKS; j++) accumulate<METRIC_COSINE>(v0[j], qv[j], s0, s1);
+                const float t0 = warp_sum((s0[0] + s0[1]) + (s0[2] + s0[3]));
+                const float t1 = warp_sum((s1[0] + s1[1]) + (s1[2] + s1[3]));
+                offer_row<KPL, METRIC_COSINE, false>(t0, t1, sqrt_b, rsqrt_b, pos0, top, nan_rows, nullptr, lane);
+            }
+            if (two) {
+                float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int j = 0; j < SCAN_CHUNKS; j++) accumulate<METRIC_COSINE>(v1[j], qv[j], s0, s1);
+                const float t0 = warp_sum((s0[0] + s0[1]) + (s0[2] + s0[3]));
+                const float t1 = warp_sum((s1[0] + s1[1]) + (s1[2] + s1[3]));
+                offer_row<KPL, METRIC_COSINE, false>(t0, t1, sqrt_b, rsqrt_b, pos1, top, nan_rows, nullptr, lane);
+            }
+        }
     }
     write_part_list<KPL>(top, scratch, a.part_keys + (static_cast<size_t>(q) * parts + part) * (32 * KPL), tid, warp,
                          lane);
