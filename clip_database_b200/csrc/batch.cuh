@@ -13,8 +13,9 @@
 //      mbarrier ring; warp-specialised: 1 TMA thread, 1 MMA thread, 4 epilogue warps
 //      reading the accumulators with tcgen05.ld while the next tile's MMAs run (two
 //      accumulator buffers = all 512 TMEM columns).
-//   3. pass A (every 16th tile): the epilogue dumps u = score/||row|| for a row sample;
-//      per query, tau = the k-th best sampled u  =>  at least k rows have u >= tau.
+//   3. pass A (every 16th tile): the epilogue reduces u = score/||row|| to one maximum per
+//      (query, 32-row group) with a warp transpose-reduce; per query, tau = the k-th largest
+//      group maximum  =>  at least k distinct rows have u >= tau.
 //   4. pass B (all tiles): the epilogue keeps (q,row) iff u >= tau - 2E||q||, where
 //      E bounds |cos^ - cos| for bf16-rounded operands: the measured rounding-error norms
 //      of the rows (max over the store) and of the query, + accumulation slack (~2.6e-3).
@@ -210,11 +211,11 @@ __global__ void __launch_bounds__(128) prep_queries_kernel(const float *__restri
 struct BatchGemmArgs {
     const float *inv_norm;      // [n]
     const float *thr;           // [256] FILTER: keep iff u >= thr[q]
-    float *scores;              // DUMP: [256][sample_rows]
+    float *scores;              // DUMP: [sample_groups][256] group maxima of u
     unsigned int *cand_count;   // FILTER: [256]
     unsigned int *cand_rows;    // FILTER: [256][cand_cap]
     long long n;
-    long long sample_rows;      // DUMP: row capacity per query in `scores`
+    long long sample_groups;    // DUMP: number of 32-row groups (= 4 per sampled tile)
     int total_tiles;            // ceil(n / 128)
     int tile_stride;            // 1 (FILTER) or BQ_SAMPLE_STRIDE (DUMP)
     int cand_cap;
@@ -329,14 +330,23 @@ __global__ void __launch_bounds__(BQ_THREADS, 1) batch_gemm_kernel(const __grid_
                 tmem_ld32(taddr + c * 32, r);
                 tmem_ld_wait();
                 if (DUMP) {
-                    const long long srow = static_cast<long long>(t) * BQ_M + lane_base + lane;  // sample index
-                    if (srow < a.sample_rows) {
+                    // max over this warp's 32 rows for each of the 32 columns, column L ending in lane L
+                    float m[32];
 #pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            const float u = row_ok ? __uint_as_float(r[j]) * inv : __int_as_float(0xff800000);
-                            a.scores[static_cast<long long>(c * 32 + j) * a.sample_rows + srow] = u;
+                    for (int j = 0; j < 32; j++)
+                        m[j] = row_ok ? __uint_as_float(r[j]) * inv : __int_as_float(0xff800000);
+#pragma unroll
+                    for (int half = 16; half >= 1; half >>= 1) {
+                        const bool upper = (lane & half) != 0;
+#pragma unroll
+                        for (int j = 0; j < half; j++) {
+                            const float send = upper ? m[j] : m[j + half];
+                            const float keep = upper ? m[j + half] : m[j];
+                            m[j] = fmaxf(keep, __shfl_xor_sync(FULL_MASK, send, half));  // fmaxf drops NaN
                         }
                     }
+                    const long long group = static_cast<long long>(t) * 4 + (warp & 3);
+                    if (group < a.sample_groups) a.scores[group * BQ_N + c * 32 + lane] = m[0];
                 } else if (row_ok) {
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
@@ -361,6 +371,233 @@ __global__ void __launch_bounds__(BQ_THREADS, 1) batch_gemm_kernel(const __grid_
     if (warp == 1) tmem_dealloc(tmem_base, BQ_TMEM_COLS);
 }
 
+// ---- the contraction, CTA-pair form (cta_group::2) ------------------------------------------------
+// Two CTAs of a cluster (one TPC) work on 256 rows x 256 queries: each loads its own 128
+// rows of D^ and HALF of the query block (128 queries), and the leader's single thread issues
+// UMMA 256x256x16 that reads both CTAs' shared memory and writes each CTA's TMEM.  Per 128
+// rows an SM now ingests 295 KB of rows + 295 KB of queries instead of 295 + 590 KB: the
+// 1-CTA kernel is bound by that ingest (ncu: 69 GB through the SMs' L2 ports at 11.9 TB/s,
+// tensor pipe 61 % busy), not by HBM or the tensor pipe.
+constexpr int BP_STAGES = 6;
+constexpr int BP_A_BYTES = BQ_M * BQ_BLOCK_K * 2;          // 16,384: this CTA's 128 rows
+constexpr int BP_B_BYTES = (BQ_N / 2) * BQ_BLOCK_K * 2;    // 16,384: this CTA's 128 queries
+constexpr int BP_STAGE_BYTES = BP_A_BYTES + BP_B_BYTES;
+constexpr int BP_SMEM_BYTES = BQ_HEADER + BP_STAGES * BP_STAGE_BYTES + 1024;
+constexpr uint32_t BP_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((BQ_N >> 3) << 17) | ((256u >> 4) << 24);
+constexpr uint32_t BP_PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> CTA 0
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t *dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "r"(cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols));
+}
+// TMA load whose completion bytes are credited to the LEADER CTA's barrier
+__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & BP_PEER_MASK), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// when the MMAs issued so far retire, arrive on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_on_cta(uint64_t *bar, uint32_t cta) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+template <bool DUMP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
+    batch_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__ CUtensorMap map_qhalf,
+                           const BatchGemmArgs a) {
+    extern __shared__ __align__(16) uint8_t bq_smem_raw[];
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(bq_smem_raw);   // waited on in the leader only
+    uint64_t *empty_bar = full_bar + BP_STAGES;
+    uint64_t *tmem_full = empty_bar + BP_STAGES;   // [2]
+    uint64_t *tmem_empty = tmem_full + 2;          // [2], the leader's copy counts both CTAs' epilogues
+    uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    float *thr_s = reinterpret_cast<float *>(bq_smem_raw + 1024);
+    const uint32_t raw_addr = smem_u32(bq_smem_raw);
+    const uint32_t tiles_addr = (raw_addr + BQ_HEADER + 1023u) & ~1023u;
+    uint8_t *tiles = bq_smem_raw + (tiles_addr - raw_addr);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1, pairs = gridDim.x >> 1;
+    const int total_pair_tiles = (a.total_tiles + 1) / 2;                       // 256 rows each
+    const int eff_tiles = (total_pair_tiles + a.tile_stride - 1) / a.tile_stride;
+
+    if (tid == 0) {
+        for (int s = 0; s < BP_STAGES; s++) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; b++) {
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], 8);   // 4 epilogue warps in each of the two CTAs
+        }
+        mbar_fence_init();
+    }
+    if (!DUMP)
+        for (int i = tid; i < BQ_N; i += BQ_THREADS) thr_s[i] = a.thr[i];
+    if (warp == 1) tmem_alloc_pair(tmem_base_slot, BQ_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();    // the peer's barriers exist before anything signals them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs) =====
+        if (lane == 0) {
+            int s = 0;
+            uint32_t phase = 0;
+            for (int t = pair; t < eff_tiles; t += pairs) {
+                const int row0 = (t * a.tile_stride * 2 + static_cast<int>(rank)) * BQ_M;
+                for (int kb = 0; kb < BQ_K_BLOCKS; kb++) {
+                    mbar_wait(&empty_bar[s], phase ^ 1u);
+                    if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * BP_STAGE_BYTES);  // both CTAs' bytes
+                    uint8_t *stage = tiles + s * BP_STAGE_BYTES;
+                    tma_load_2d_pair(stage, &map_rows, kb * BQ_BLOCK_K, row0, &full_bar[s]);
+                    tma_load_2d_pair(stage + BP_A_BYTES, &map_qhalf, kb * BQ_BLOCK_K, static_cast<int>(rank) * (BQ_N / 2),
+                                     &full_bar[s]);
+                    if (++s == BP_STAGES) {
+                        s = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA only) =====
+        if (leader && lane == 0) {
+            int s = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int t = pair; t < eff_tiles; t += pairs, it++) {
+                const int acc = it & 1;
+                mbar_wait_cluster(&tmem_empty[acc], (static_cast<uint32_t>(it >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BQ_N);
+                for (int kb = 0; kb < BQ_K_BLOCKS; kb++) {
+                    mbar_wait_cluster(&full_bar[s], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = tiles_addr + s * BP_STAGE_BYTES;
+                    const uint32_t b_addr = a_addr + BP_A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BQ_BLOCK_K / BQ_UMMA_K; k++) {
+                        umma_bf16_pair(tmem_d, umma_desc_sw128(a_addr + k * BQ_UMMA_K * 2),
+                                       umma_desc_sw128(b_addr + k * BQ_UMMA_K * 2), BP_IDESC,
+                                       static_cast<uint32_t>((kb | k) != 0));
+                    }
+                    umma_commit_pair(&empty_bar[s]);   // frees this stage in both CTAs
+                    if (++s == BP_STAGES) {
+                        s = 0;
+                        phase ^= 1u;
+                    }
+                }
+                umma_commit_pair(&tmem_full[acc]);     // accumulators complete in both CTAs
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs): warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
+        const int lane_base = 32 * (warp & 3);
+        int it = 0;
+        for (int t = pair; t < eff_tiles; t += pairs, it++) {
+            const int acc = it & 1;
+            const long long t128 = static_cast<long long>(t) * a.tile_stride * 2 + rank;   // 128-row tile index
+            const long long row = t128 * BQ_M + lane_base + lane;
+            const bool row_ok = row < a.n;
+            const float inv = row_ok ? __ldg(a.inv_norm + row) : 0.f;
+            mbar_wait(&tmem_full[acc], static_cast<uint32_t>(it >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_base) << 16) +
+                                   static_cast<uint32_t>(acc * BQ_N);
+#pragma unroll 1
+            for (int c = 0; c < BQ_N / 32; c++) {
+                uint32_t r[32];
+                tmem_ld32(taddr + c * 32, r);
+                tmem_ld_wait();
+                if (DUMP) {
+                    float m[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j++)
+                        m[j] = row_ok ? __uint_as_float(r[j]) * inv : __int_as_float(0xff800000);
+#pragma unroll
+                    for (int half = 16; half >= 1; half >>= 1) {
+                        const bool upper = (lane & half) != 0;
+#pragma unroll
+                        for (int j = 0; j < half; j++) {
+                            const float send = upper ? m[j] : m[j + half];
+                            const float keep = upper ? m[j + half] : m[j];
+                            m[j] = fmaxf(keep, __shfl_xor_sync(FULL_MASK, send, half));
+                        }
+                    }
+                    const long long group = (static_cast<long long>(t) * 2 + rank) * 4 + (warp & 3);
+                    if (group < a.sample_groups) a.scores[group * BQ_N + c * 32 + lane] = m[0];
+                } else if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float u = __uint_as_float(r[j]) * inv;
+                        if (u >= thr_s[c * 32 + j]) {
+                            const int q = c * 32 + j;
+                            const unsigned pos = atomicAdd(a.cand_count + q, 1u);
+                            if (pos < static_cast<unsigned>(a.cand_cap))
+                                a.cand_rows[static_cast<size_t>(q) * a.cand_cap + pos] = static_cast<unsigned>(row);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_on_cta(&tmem_empty[acc], 0);   // the leader's barrier
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();    // no CTA leaves (or frees TMEM) while its peer may still touch it
+    if (warp == 1) tmem_dealloc_pair(tmem_base, BQ_TMEM_COLS);
+}
+
 // ---- per-query selection in two levels ----------------------------------------------------
 // Both the threshold step (k-th best sampled u) and the re-rank (k best exact distances) are
 // "top-k of one query's items".  Level 1: grid (query, part) — each CTA keeps warp-level
@@ -369,7 +606,7 @@ __global__ void __launch_bounds__(BQ_THREADS, 1) batch_gemm_kernel(const __grid_
 // decodes the final result.  Keys make the outcome independent of how items were split.
 constexpr int BQ_SEL_WARPS = 8;
 constexpr int BQ_SEL_THREADS = BQ_SEL_WARPS * 32;
-constexpr int BQ_THR_PARTS = 8;      // parts per query over the sampled scores
+constexpr int BQ_THR_PARTS = 2;      // parts per query over the sampled group maxima
 constexpr int BQ_RERANK_PARTS = 4;   // parts per query over the candidate rows
 
 template <int KPL>
@@ -381,25 +618,24 @@ __device__ __forceinline__ void write_part_list(WarpTopK<KPL> &top, uint64_t *sc
     for (int i = tid; i < 32 * KPL; i += BQ_SEL_THREADS) dst[i] = scratch[i];
 }
 
-// level 1 over the sampled scores: best = largest u, so keys order by -u
+// level 1 over the sampled group maxima scores[group][256]: best = largest u, keys order by -u
 template <int KPL>
 __global__ void __launch_bounds__(BQ_SEL_THREADS) batch_sample_topk_kernel(const float *__restrict__ scores,
-                                                                           long long sample_rows, int k,
+                                                                           long long groups, int k,
                                                                            uint64_t *__restrict__ part_keys) {
     __shared__ uint64_t scratch[BQ_SEL_WARPS * 32 * KPL];
     const int q = blockIdx.x, part = blockIdx.y, parts = gridDim.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const long long lo = sample_rows * part / parts, hi = sample_rows * (part + 1) / parts;
+    const long long lo = groups * part / parts, hi = groups * (part + 1) / parts;
     WarpTopK<KPL> top;
     top.init(k, lane);
-    const float *src = scores + static_cast<long long>(q) * sample_rows;
-    constexpr int U = 8;  // independent loads in flight per lane (the loop is latency-bound otherwise)
+    constexpr int U = 8;  // independent loads in flight per lane
     for (long long base = lo + static_cast<long long>(warp) * (32 * U); base < hi; base += BQ_SEL_WARPS * 32 * U) {
         float u[U];
 #pragma unroll
         for (int j = 0; j < U; j++) {
             const long long i = base + j * 32 + lane;
-            u[j] = i < hi ? __ldg(src + i) : __int_as_float(0xff800000);
+            u[j] = i < hi ? __ldg(scores + i * BQ_N + q) : __int_as_float(0xff800000);
         }
 #pragma unroll
         for (int j = 0; j < U; j++) {

@@ -67,10 +67,12 @@ struct clipdb_ctx {
     // batched path (K4): bf16 copy of the store + workspaces
     bool batch_enabled = false;
     Buffer bf16_rows, inv_norm, bad_rows, bq_queries, bq_qnorm, bq_scores, bq_thr, bq_flags, bq_count, bq_cand, bq_parts, bq_qerr, row_err;
-    CUtensorMap map_rows, map_q;
-    int64_t bq_sample_rows = 0;
+    CUtensorMap map_rows, map_q, map_qhalf;
+    int64_t bq_sample_groups = 0;       // capacity of bq_scores in groups
+    int64_t bq_sample_groups_used = 0;  // groups the last pass A wrote
     int64_t batch_min_nq = 16;      // clipdb_search switches to the batched path from this nq
     int64_t batch_cand_cap = 32768; // candidate rows kept per query
+    int64_t batch_cta_pair = 1;     // 1: cta_group::2 contraction (CTA pairs), 0: single-CTA kernel
 
     // scan-kernel event timing (clipdb_profile)
     bool profiling = false;
@@ -580,7 +582,10 @@ int batch_build_locked(clipdb_ctx *c) {
         return fail(c, CLIPDB_ERR_UNSUPPORTED, "batched path needs at least %lld rows", (long long)BATCH_MIN_ROWS);
     const int64_t tiles = (c->n + BQ_M - 1) / BQ_M;
     const int64_t eff = (tiles + BQ_SAMPLE_STRIDE - 1) / BQ_SAMPLE_STRIDE;
-    c->bq_sample_rows = eff * BQ_M;
+    // one maximum per (sampled 128-row tile, epilogue warp); the CTA-pair kernel samples whole
+    // 256-row pair tiles (every 8th), so size for whichever visits more tiles
+    const int64_t eff_pair = ((tiles + 1) / 2 + BQ_SAMPLE_STRIDE / 2 - 1) / (BQ_SAMPLE_STRIDE / 2);
+    c->bq_sample_groups = (eff * 4 > eff_pair * 8 ? eff * 4 : eff_pair * 8);
     RC_TRY(ensure_device(c, c->bf16_rows, static_cast<size_t>(c->n) * SCAN_DIM * 2));
     RC_TRY(ensure_device(c, c->inv_norm, static_cast<size_t>(c->n) * sizeof(float)));
     RC_TRY(ensure_device(c, c->bad_rows, sizeof(unsigned long long)));
@@ -589,12 +594,12 @@ int batch_build_locked(clipdb_ctx *c) {
     RC_TRY(ensure_device(c, c->bq_qerr, BQ_N * sizeof(float)));
     RC_TRY(ensure_device(c, c->row_err, sizeof(unsigned int)));
     CU_TRY(c, cudaMemsetAsync(c->row_err.p, 0, sizeof(unsigned int), c->stream));
-    RC_TRY(ensure_device(c, c->bq_scores, static_cast<size_t>(BQ_N) * c->bq_sample_rows * sizeof(float)));
+    RC_TRY(ensure_device(c, c->bq_scores, static_cast<size_t>(BQ_N) * c->bq_sample_groups * sizeof(float)));
     RC_TRY(ensure_device(c, c->bq_thr, BQ_N * sizeof(float)));
     RC_TRY(ensure_device(c, c->bq_flags, BQ_N * sizeof(int32_t)));
     RC_TRY(ensure_device(c, c->bq_count, BQ_N * sizeof(unsigned int)));
     RC_TRY(ensure_device(c, c->bq_cand, static_cast<size_t>(BQ_N) * c->batch_cand_cap * sizeof(unsigned int)));
-    RC_TRY(ensure_device(c, c->bq_parts, static_cast<size_t>(BQ_N) * BQ_THR_PARTS * 128 * sizeof(uint64_t)));
+    RC_TRY(ensure_device(c, c->bq_parts, static_cast<size_t>(BQ_N) * 8 * 128 * sizeof(uint64_t)));
     CU_TRY(c, cudaMemsetAsync(c->bad_rows.p, 0, sizeof(unsigned long long), c->stream));
     build_bf16_store_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(
         c->rows, c->n, static_cast<__nv_bfloat16 *>(c->bf16_rows.p), static_cast<float *>(c->inv_norm.p),
@@ -603,6 +608,9 @@ int batch_build_locked(clipdb_ctx *c) {
     c->launches++;
     RC_TRY(encode_bf16_map(c, &c->map_rows, c->bf16_rows.p, static_cast<uint64_t>(c->n), BQ_M));
     RC_TRY(encode_bf16_map(c, &c->map_q, c->bq_queries.p, BQ_N, BQ_N));
+    RC_TRY(encode_bf16_map(c, &c->map_qhalf, c->bq_queries.p, BQ_N, BQ_N / 2));
+    CU_TRY(c, cudaFuncSetAttribute(batch_gemm_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_BYTES));
+    CU_TRY(c, cudaFuncSetAttribute(batch_gemm_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_BYTES));
     CU_TRY(c, cudaFuncSetAttribute(batch_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BQ_SMEM_BYTES));
     CU_TRY(c, cudaFuncSetAttribute(batch_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BQ_SMEM_BYTES));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
@@ -621,7 +629,7 @@ int batch_launch_tail(clipdb_ctx *c, const float *d_queries, int32_t nq, int32_t
     uint64_t *parts = static_cast<uint64_t *>(c->bq_parts.p);
     if (threshold) {
         batch_sample_topk_kernel<KPL><<<dim3(nq, BQ_THR_PARTS), BQ_SEL_THREADS, 0, c->stream>>>(
-            static_cast<const float *>(c->bq_scores.p), c->bq_sample_rows, k, parts);
+            static_cast<const float *>(c->bq_scores.p), c->bq_sample_groups_used, k, parts);
         CU_TRY(c, cudaGetLastError());
         c->launches++;
         batch_threshold_finish_kernel<<<BQ_N, 256, 0, c->stream>>>(
@@ -678,17 +686,29 @@ int batch_search_device_locked(clipdb_ctx *c, const float *d_queries, int32_t nq
     g.cand_count = static_cast<unsigned int *>(c->bq_count.p);
     g.cand_rows = static_cast<unsigned int *>(c->bq_cand.p);
     g.n = c->n;
-    g.sample_rows = c->bq_sample_rows;
+    g.sample_groups = c->bq_sample_groups;
     g.total_tiles = tiles;
     g.cand_cap = static_cast<int>(c->batch_cand_cap);
 
-    // pass A: scores of the row sample -> per-query thresholds
-    g.tile_stride = BQ_SAMPLE_STRIDE;
-    const int eff = (tiles + BQ_SAMPLE_STRIDE - 1) / BQ_SAMPLE_STRIDE;
-    batch_gemm_kernel<true><<<eff < c->sm_count ? eff : c->sm_count, BQ_THREADS, BQ_SMEM_BYTES, c->stream>>>(
-        c->map_rows, c->map_q, g);
+    // pass A: group maxima over a tile sample -> per-query thresholds
+    const bool pair = c->batch_cta_pair != 0 && (c->sm_count % 2 == 0);
+    const int pair_grid = c->sm_count & ~1;
+    if (pair) {
+        g.tile_stride = BQ_SAMPLE_STRIDE / 2;          // in 256-row pair tiles
+        const int eff = ((tiles + 1) / 2 + g.tile_stride - 1) / g.tile_stride;
+        g.sample_groups = static_cast<long long>(eff) * 8;
+        const int grid = 2 * eff < pair_grid ? 2 * eff : pair_grid;
+        batch_gemm_pair_kernel<true><<<grid, BQ_THREADS, BP_SMEM_BYTES, c->stream>>>(c->map_rows, c->map_qhalf, g);
+    } else {
+        g.tile_stride = BQ_SAMPLE_STRIDE;
+        const int eff = (tiles + BQ_SAMPLE_STRIDE - 1) / BQ_SAMPLE_STRIDE;
+        g.sample_groups = static_cast<long long>(eff) * 4;
+        batch_gemm_kernel<true><<<eff < c->sm_count ? eff : c->sm_count, BQ_THREADS, BQ_SMEM_BYTES, c->stream>>>(
+            c->map_rows, c->map_q, g);
+    }
     CU_TRY(c, cudaGetLastError());
     c->launches++;
+    c->bq_sample_groups_used = g.sample_groups;
     switch (kpl) {
         case 1: RC_TRY((batch_launch_tail<1>(c, d_queries, nq, k, d_out_rowids, d_out_dist, d_out_n, d_out_nan, d_flags, true))); break;
         case 2: RC_TRY((batch_launch_tail<2>(c, d_queries, nq, k, d_out_rowids, d_out_dist, d_out_n, d_out_nan, d_flags, true))); break;
@@ -698,8 +718,14 @@ int batch_search_device_locked(clipdb_ctx *c, const float *d_queries, int32_t nq
     CU_TRY(c, cudaMemsetAsync(c->bq_count.p, 0, BQ_N * sizeof(unsigned int), c->stream));
     g.tile_stride = 1;
     RC_TRY(profile_mark(c, true));
-    batch_gemm_kernel<false><<<tiles < c->sm_count ? tiles : c->sm_count, BQ_THREADS, BQ_SMEM_BYTES, c->stream>>>(
-        c->map_rows, c->map_q, g);
+    if (pair) {
+        const int ptiles = (tiles + 1) / 2;
+        const int grid = 2 * ptiles < pair_grid ? 2 * ptiles : pair_grid;
+        batch_gemm_pair_kernel<false><<<grid, BQ_THREADS, BP_SMEM_BYTES, c->stream>>>(c->map_rows, c->map_qhalf, g);
+    } else {
+        batch_gemm_kernel<false><<<tiles < c->sm_count ? tiles : c->sm_count, BQ_THREADS, BQ_SMEM_BYTES, c->stream>>>(
+            c->map_rows, c->map_q, g);
+    }
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     RC_TRY(profile_mark(c, false));
@@ -812,6 +838,7 @@ static int64_t *option_slot(clipdb_ctx *c, const char *name) {
     if (!strcmp(name, "scan_chunk")) return &c->scan_chunk;
     if (!strcmp(name, "batch_min_nq")) return &c->batch_min_nq;
     if (!strcmp(name, "batch_cand_cap")) return &c->batch_cand_cap;
+    if (!strcmp(name, "batch_cta_pair")) return &c->batch_cta_pair;
     return nullptr;
 }
 

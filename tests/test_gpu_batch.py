@@ -44,6 +44,17 @@ def test_batched_equals_exact(store, nq, k):
     same(got, exact.search(queries, k))
 
 
+def test_single_cta_contraction_kernel_agrees(store):
+    """batch_cta_pair=0 selects the 1-CTA tcgen05 kernel; same answers as the CTA-pair one."""
+    rows, exact, batched = store
+    queries = synth.unit_rows(256, DIM, 123)
+    batched.set_option("batch_cta_pair", 0)
+    try:
+        same(batched.search(queries, 100), exact.search(queries, 100))
+    finally:
+        batched.set_option("batch_cta_pair", 1)
+
+
 def test_batched_clustered_queries(store):
     """Queries near stored rows: top results are far from the noise tail."""
     rows, exact, batched = store
