@@ -127,6 +127,18 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // ---- store / query preparation -----------------------------------------------------------
 
+// The bf16 copy is stored PRE-TILED: block (tile T, k-block kb) = 128 rows x 64 bf16 = one
+// contiguous 16 KB span at ((T*18 + kb) * 128 + r) * 64, i.e. exactly one TMA box.  Every
+// operand load is then a sequential 16 KB burst and the whole store streams in address order
+// (a row-major copy makes each box 128 separate 128-byte pieces 2304 B apart, which held the
+// contraction to ~50 % of DRAM efficiency).
+__device__ __forceinline__ size_t tiled_offset(long long row, int k) {  // element offset of (row, k)
+    const long long tile = row / BQ_M;
+    const int r = static_cast<int>(row - tile * BQ_M);
+    const int kb = k / BQ_BLOCK_K, kk = k - kb * BQ_BLOCK_K;
+    return ((static_cast<size_t>(tile) * BQ_K_BLOCKS + kb) * BQ_M + r) * BQ_BLOCK_K + kk;
+}
+
 // one warp per row: bf16 copy, 1/||row|| (float32), count of rows whose norm is 0 or not finite
 __global__ void __launch_bounds__(256) build_bf16_store_kernel(const float *__restrict__ rows, long long n,
                                                                __nv_bfloat16 *__restrict__ out,
@@ -140,7 +152,6 @@ __global__ void __launch_bounds__(256) build_bf16_store_kernel(const float *__re
     float worst = 0.f;
     for (long long r = warp; r < n; r += warps) {
         const float4 *src = reinterpret_cast<const float4 *>(rows + r * SCAN_DIM);
-        uint2 *dst = reinterpret_cast<uint2 *>(out + r * SCAN_DIM);
         float ss = 0.f, es = 0.f;
 #pragma unroll
         for (int j = 0; j < SCAN_CHUNKS; j++) {
@@ -158,7 +169,7 @@ __global__ void __launch_bounds__(256) build_bf16_store_kernel(const float *__re
             uint2 packed;
             packed.x = *reinterpret_cast<uint32_t *>(&lo);
             packed.y = *reinterpret_cast<uint32_t *>(&hi);
-            dst[lane + 32 * j] = packed;
+            *reinterpret_cast<uint2 *>(out + tiled_offset(r, (lane + 32 * j) * 4)) = packed;
         }
         ss = warp_sum(ss);
         es = warp_sum(es);
@@ -266,12 +277,12 @@ __global__ void __launch_bounds__(BQ_THREADS, 1) batch_gemm_kernel(const __grid_
             int s = 0;
             uint32_t phase = 0;
             for (int t = first; t < eff_tiles; t += step) {
-                const int row0 = t * a.tile_stride * BQ_M;
+                const int tile128 = t * a.tile_stride;
                 for (int kb = 0; kb < BQ_K_BLOCKS; kb++) {
                     mbar_wait(&empty_bar[s], phase ^ 1u);
                     mbar_arrive_expect_tx(&full_bar[s], BQ_STAGE_BYTES);
                     uint8_t *stage = tiles + s * BQ_STAGE_BYTES;
-                    tma_load_2d(stage, &map_rows, kb * BQ_BLOCK_K, row0, &full_bar[s]);
+                    tma_load_2d(stage, &map_rows, 0, (tile128 * BQ_K_BLOCKS + kb) * BQ_M, &full_bar[s]);
                     tma_load_2d(stage + BQ_A_BYTES, &map_q, kb * BQ_BLOCK_K, 0, &full_bar[s]);
                     if (++s == BQ_STAGES) {
                         s = 0;
@@ -491,12 +502,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
             int s = 0;
             uint32_t phase = 0;
             for (int t = pair; t < eff_tiles; t += pairs) {
-                const int row0 = (t * a.tile_stride * 2 + static_cast<int>(rank)) * BQ_M;
+                const int tile128 = t * a.tile_stride * 2 + static_cast<int>(rank);
                 for (int kb = 0; kb < BQ_K_BLOCKS; kb++) {
                     mbar_wait(&empty_bar[s], phase ^ 1u);
                     if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * BP_STAGE_BYTES);  // both CTAs' bytes
                     uint8_t *stage = tiles + s * BP_STAGE_BYTES;
-                    tma_load_2d_pair(stage, &map_rows, kb * BQ_BLOCK_K, row0, &full_bar[s]);
+                    tma_load_2d_pair(stage, &map_rows, 0, (tile128 * BQ_K_BLOCKS + kb) * BQ_M, &full_bar[s]);
                     tma_load_2d_pair(stage + BP_A_BYTES, &map_qhalf, kb * BQ_BLOCK_K, static_cast<int>(rank) * (BQ_N / 2),
                                      &full_bar[s]);
                     if (++s == BP_STAGES) {

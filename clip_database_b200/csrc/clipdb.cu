@@ -552,7 +552,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                   CUtensorMapFloatOOBfill);
 
-int encode_bf16_map(clipdb_ctx *c, CUtensorMap *map, void *base, uint64_t rows, uint32_t box_rows) {
+int encode_bf16_map(clipdb_ctx *c, CUtensorMap *map, void *base, uint64_t rows, uint32_t box_rows,
+                    uint32_t row_elems = SCAN_DIM) {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void *p = nullptr;
@@ -562,8 +563,8 @@ int encode_bf16_map(clipdb_ctx *c, CUtensorMap *map, void *base, uint64_t rows, 
             return fail(c, CLIPDB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
         fn = reinterpret_cast<EncodeTiledFn>(p);
     }
-    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(SCAN_DIM), rows};
-    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(SCAN_DIM) * 2};
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(row_elems), rows};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(row_elems) * 2};
     const cuuint32_t box[2] = {BQ_BLOCK_K, box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr,
@@ -586,7 +587,12 @@ int batch_build_locked(clipdb_ctx *c) {
     // 256-row pair tiles (every 8th), so size for whichever visits more tiles
     const int64_t eff_pair = ((tiles + 1) / 2 + BQ_SAMPLE_STRIDE / 2 - 1) / (BQ_SAMPLE_STRIDE / 2);
     c->bq_sample_groups = (eff * 4 > eff_pair * 8 ? eff * 4 : eff_pair * 8);
-    RC_TRY(ensure_device(c, c->bf16_rows, static_cast<size_t>(c->n) * SCAN_DIM * 2));
+    // pre-tiled bf16 copy: whole 128-row tiles (the last one zero padded)
+    const size_t bf16_bytes = static_cast<size_t>(tiles) * BQ_M * SCAN_DIM * 2;
+    RC_TRY(ensure_device(c, c->bf16_rows, bf16_bytes));
+    if (c->n % BQ_M)
+        CU_TRY(c, cudaMemsetAsync(static_cast<uint8_t *>(c->bf16_rows.p) + static_cast<size_t>(tiles - 1) * BQ_M * SCAN_DIM * 2,
+                                  0, static_cast<size_t>(BQ_M) * SCAN_DIM * 2, c->stream));
     RC_TRY(ensure_device(c, c->inv_norm, static_cast<size_t>(c->n) * sizeof(float)));
     RC_TRY(ensure_device(c, c->bad_rows, sizeof(unsigned long long)));
     RC_TRY(ensure_device(c, c->bq_queries, static_cast<size_t>(BQ_N) * SCAN_DIM * 2));
@@ -606,7 +612,8 @@ int batch_build_locked(clipdb_ctx *c) {
         static_cast<unsigned long long *>(c->bad_rows.p), static_cast<unsigned int *>(c->row_err.p));
     CU_TRY(c, cudaGetLastError());
     c->launches++;
-    RC_TRY(encode_bf16_map(c, &c->map_rows, c->bf16_rows.p, static_cast<uint64_t>(c->n), BQ_M));
+    RC_TRY(encode_bf16_map(c, &c->map_rows, c->bf16_rows.p, static_cast<uint64_t>(tiles) * BQ_K_BLOCKS * BQ_M, BQ_M,
+                           BQ_BLOCK_K));
     RC_TRY(encode_bf16_map(c, &c->map_q, c->bq_queries.p, BQ_N, BQ_N));
     RC_TRY(encode_bf16_map(c, &c->map_qhalf, c->bq_queries.p, BQ_N, BQ_N / 2));
     CU_TRY(c, cudaFuncSetAttribute(batch_gemm_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_BYTES));
