@@ -232,6 +232,33 @@ struct BatchGemmArgs {
     int cand_cap;
 };
 
+// Filter 32 accumulator columns of one row.  The common case (no column reaches its
+// threshold: ~99 % of chunks) costs one FMUL + one predicate-accumulating FSETP per element
+// with no branches; only chunks with a hit take the slow path with the atomics.  The
+// epilogue must stay well under the ~9,200 cycles the tensor pipe needs per 128-row tile:
+// the first version (a branch per element, ~3,000 instructions per thread per tile) made
+// the whole contraction epilogue-bound (profiles/r01_batch_gemm_ncu.md).
+__device__ __forceinline__ void filter_chunk(const uint32_t (&r)[32], float inv, const float *thr, bool row_ok,
+                                             long long row, int q0, const BatchGemmArgs &a) {
+    bool any0 = false, any1 = false;
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+        any0 |= __uint_as_float(r[j]) * inv >= thr[j];
+        any1 |= __uint_as_float(r[j + 1]) * inv >= thr[j + 1];
+    }
+    if ((any0 || any1) && row_ok) {
+#pragma unroll   // static indices: r[] must stay in registers
+        for (int j = 0; j < 32; j++) {
+            if (__uint_as_float(r[j]) * inv >= thr[j]) {
+                const int q = q0 + j;
+                const unsigned pos = atomicAdd(a.cand_count + q, 1u);
+                if (pos < static_cast<unsigned>(a.cand_cap))
+                    a.cand_rows[static_cast<size_t>(q) * a.cand_cap + pos] = static_cast<unsigned>(row);
+            }
+        }
+    }
+}
+
 template <bool DUMP>
 __global__ void __launch_bounds__(BQ_THREADS, 1) batch_gemm_kernel(const __grid_constant__ CUtensorMap map_rows,
                                                                    const __grid_constant__ CUtensorMap map_q,
@@ -358,17 +385,8 @@ __global__ void __launch_bounds__(BQ_THREADS, 1) batch_gemm_kernel(const __grid_
                     }
                     const long long group = static_cast<long long>(t) * 4 + (warp & 3);
                     if (group < a.sample_groups) a.scores[group * BQ_N + c * 32 + lane] = m[0];
-                } else if (row_ok) {
-#pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const float u = __uint_as_float(r[j]) * inv;
-                        if (u >= thr_s[c * 32 + j]) {
-                            const int q = c * 32 + j;
-                            const unsigned pos = atomicAdd(a.cand_count + q, 1u);
-                            if (pos < static_cast<unsigned>(a.cand_cap))
-                                a.cand_rows[static_cast<size_t>(q) * a.cand_cap + pos] = static_cast<unsigned>(row);
-                        }
-                    }
+                } else {
+                    filter_chunk(r, inv, thr_s + c * 32, row_ok, row, c * 32, a);
                 }
             }
             tc_fence_before();
@@ -439,7 +457,10 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
 __device__ __forceinline__ void mbar_arrive_on_cta(uint64_t *bar, uint32_t cta) {
     uint32_t remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+    // default semantics (release at CTA scope): what is being ordered is this warp's TMEM reads,
+    // already complete (tcgen05.wait::ld + fence); a cluster-scope release would also wait for
+    // the filter's global atomics to drain (ERRBAR, visible in the first profile)
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
@@ -584,17 +605,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
                     }
                     const long long group = (static_cast<long long>(t) * 2 + rank) * 4 + (warp & 3);
                     if (group < a.sample_groups) a.scores[group * BQ_N + c * 32 + lane] = m[0];
-                } else if (row_ok) {
-#pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const float u = __uint_as_float(r[j]) * inv;
-                        if (u >= thr_s[c * 32 + j]) {
-                            const int q = c * 32 + j;
-                            const unsigned pos = atomicAdd(a.cand_count + q, 1u);
-                            if (pos < static_cast<unsigned>(a.cand_cap))
-                                a.cand_rows[static_cast<size_t>(q) * a.cand_cap + pos] = static_cast<unsigned>(row);
-                        }
-                    }
+                } else {
+                    filter_chunk(r, inv, thr_s + c * 32, row_ok, row, c * 32, a);
                 }
             }
             tc_fence_before();
