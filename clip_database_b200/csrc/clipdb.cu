@@ -70,7 +70,8 @@ struct clipdb_ctx {
     CUtensorMap map_rows, map_q, map_qhalf;
     int64_t bq_sample_groups = 0;       // capacity of bq_scores in groups
     int64_t bq_sample_groups_used = 0;  // groups the last pass A wrote
-    int64_t batch_min_nq = 16;      // clipdb_search switches to the batched path from this nq
+    int64_t batch_min_nq = 2;       // clipdb_search switches to the batched path from this nq (one batch
+                                    // costs about one single-query scan, whatever its size)
     int64_t batch_cand_cap = 32768; // candidate rows kept per query
     int64_t batch_cta_pair = 1;     // 1: cta_group::2 contraction (CTA pairs), 0: single-CTA kernel
 

@@ -292,7 +292,7 @@ class GpuIndex:
 
     def enable_batch(self, enable: bool = True) -> None:
         """Build (or drop) the bf16 copy of the store used by the tensor-core batched path.
-        Afterwards ``search()`` with 16 or more queries uses it; results are identical."""
+        Afterwards ``search()`` with 2 or more queries uses it; results are identical."""
         self._check(self._L.clipdb_enable_batch(self._ctx, int(bool(enable))))
 
     def search_batch_device(self, d_queries, k: int, out_rowids, out_dist, out_n, out_nan, flags) -> None:

@@ -170,7 +170,8 @@ int clipdb_blend_search(clipdb_ctx *ctx, const float *e1, const float *e2, doubl
  * the exact single-query arithmetic; results are identical to clipdb_search.
  * Requirements: dim == 1152, cosine, no mask, 1 <= k <= 128, >= 65536 rows.
  * With the batch store enabled, clipdb_search uses this path by itself for
- * nq >= 16 and transparently re-runs flagged queries through the exact scan.
+ * nq >= 2 (option "batch_min_nq") and transparently re-runs flagged queries
+ * through the exact scan.
  *
  * clipdb_search_batch_device: device pointers, async, nq <= 256 per call.
  * d_flags[q] != 0 (CLIPDB_BATCH_*) marks queries whose result is NOT valid

@@ -33,7 +33,7 @@ def same(a, b):
     assert np.array_equal(a.distances.view(np.uint32), b.distances.view(np.uint32))
 
 
-@pytest.mark.parametrize("nq,k", [(256, 100), (256, 20), (16, 100), (100, 1), (300, 64), (37, 128)])
+@pytest.mark.parametrize("nq,k", [(256, 100), (256, 20), (16, 100), (100, 1), (300, 64), (37, 128), (2, 20)])
 def test_batched_equals_exact(store, nq, k):
     rows, exact, batched = store
     queries = synth.unit_rows(nq, DIM, 99)
