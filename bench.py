@@ -238,7 +238,7 @@ def run_reference_arm(args):
         "e2e": {"value": gbps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -338,13 +338,33 @@ def run_batch_workload(args, torch, idx, rows, rows_per_gpu, device, rank, local
                      "hbm_GBps_bf16_store": rows_per_gpu * DIM * 2 / 1e9 / (gemm_avg / 1e3), "traffic": None},
         "clocks": sampler.summary(),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     idx.close()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Keep a private handle on the real stdout for the ONE JSON line and point fd 1 at
+    stderr, so banners printed by libraries (e.g. NCCL's version line) cannot pollute it."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse_args()
+    claim_stdout()
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -531,7 +551,7 @@ def main():
                            % (provider, args.cpu_sample_rows, args.cpu_sample_queries)),
                 "queries_per_s_extrapolated_to_config": 1.0 / (sec * total_rows / args.cpu_sample_rows),
                 "cpu": cpu_model(), **extra}
-        print(json.dumps(line), flush=True)
+        emit(line)
 
     idx.close()
     if world > 1:

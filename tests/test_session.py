@@ -1,0 +1,68 @@
+"""Grammar of the interactive session (image_database.py:2110-2239), host logic only."""
+from clip_database_b200.session import Command, SearchRequest, SessionState, parse_line, run_session
+
+
+def test_plain_text_and_image_queries():
+    st = SessionState()
+    r = parse_line("  a red car ", st)
+    assert isinstance(r, SearchRequest) and r.query == "a red car" and not r.is_image_path and r.query2 is None
+    r = parse_line("image: /tmp/x.jpg", st)
+    assert r.query == "/tmp/x.jpg" and r.is_image_path
+    r = parse_line("IMAGE:/tmp/x.jpg", st)
+    assert r.query == "/tmp/x.jpg" and r.is_image_path
+
+
+def test_combined_and_negative_forms():
+    st = SessionState()
+    r = parse_line("image:/a.jpg + sunset over water", st)
+    assert (r.query, r.is_image_path, r.query2, r.is_image_path2) == ("/a.jpg", True, "sunset over water", False)
+    r = parse_line("colourful design - grey monochrome", st)
+    assert r.query == "colourful design" and r.negative_query == "grey monochrome" and r.negative_queries is None
+    r = parse_line("design - grey - image:/n.png - abstract", st)
+    assert r.query == "design" and r.negative_query is None
+    assert r.negative_queries == ["grey", "/n.png", "abstract"]
+    assert r.negative_is_images == [False, True, False] and r.negative_weights == [0.5, 0.5, 0.5]
+    r = parse_line("a + b + c - image:/neg.jpg", st)
+    assert (r.query, r.query2) == ("a", "b + c") and r.negative_query == "/neg.jpg" and r.negative_is_image
+    # a hyphen without surrounding spaces is not a negative
+    r = parse_line("black-and-white photo", st)
+    assert r.query == "black-and-white photo" and r.negative_query is None
+
+
+def test_state_commands(tmp_path):
+    st = SessionState()
+    assert parse_line("k: 25", st).kind == "k" and st.k == 25
+    assert parse_line("k:abc", st).kind == "error" and st.k == 25
+    d = tmp_path / "photos"
+    d.mkdir()
+    assert "Added" in parse_line(f"folder:{d}", st).message and st.filter_folders == [str(d)]
+    assert "already" in parse_line(f"folder:{d}", st).message and len(st.filter_folders) == 1
+    assert "does not exist" in parse_line("folder:/definitely/not/here", st).message
+    assert parse_line("folder:clear", st).kind == "folder" and st.filter_folders == []
+    parse_line("duplicates:show", st)
+    assert st.show_duplicates
+    parse_line("Duplicates:HIDE", st)
+    assert not st.show_duplicates
+    assert parse_line("duplicates:maybe", st).kind == "error"
+    assert parse_line("", st).kind == "empty"
+    for word in ("quit", "EXIT", "q"):
+        assert parse_line(word, st).kind == "quit"
+
+
+def test_session_loop_calls_search_with_reference_kwargs():
+    calls = []
+
+    class FakeDb:
+        def search(self, query, **kw):
+            calls.append((query, kw))
+            return [("/p/a.jpg", 0.91234), ("/p/b.jpg", 0.5)] if query != "nothing" else []
+
+    lines = iter(["k:3", "duplicates:show", "cat + image:/d.jpg - dog", "nothing", "quit"])
+    out = []
+    run_session(FakeDb(), SessionState(weights=(0.7, 0.3)), read=lambda _: next(lines), write=out.append)
+    assert len(calls) == 2
+    q, kw = calls[0]
+    assert q == "cat" and kw["k"] == 3 and kw["query2"] == "/d.jpg" and kw["is_image_path2"]
+    assert kw["negative_query"] == "dog" and kw["weights"] == (0.7, 0.3) and kw["show_duplicates"]
+    assert kw["filter_folders"] is None
+    assert any("0.9123: /p/a.jpg" in o for o in out) and "No results found." in out
