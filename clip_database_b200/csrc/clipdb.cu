@@ -1193,21 +1193,22 @@ int clipdb_search_batch_device(clipdb_ctx *c, const float *d_queries, int32_t nq
     return batch_search_device_locked(c, d_queries, nq, k, d_out_rowids, d_out_dist, d_out_n, d_out_nan, d_flags);
 }
 
-int clipdb_merge_strided_device(clipdb_ctx *c, const void *d_dist, int64_t dist_stride,
-                                const void *d_rowids, int64_t rowid_stride, const void *d_counts,
-                                int64_t count_stride, int32_t lists, int32_t k, float *d_out_dist,
-                                int64_t *d_out_rowids, int32_t *d_out_n) {
+int clipdb_merge_batch_device(clipdb_ctx *c, const void *d_dist, int64_t dist_stride, int64_t dist_qstride,
+                              const void *d_rowids, int64_t rowid_stride, int64_t rowid_qstride,
+                              const void *d_counts, int64_t count_stride, int64_t count_qstride, int32_t lists,
+                              int32_t nq, int32_t k, float *d_out_dist, int64_t *d_out_rowids, int32_t *d_out_n) {
     if (!c) return CLIPDB_ERR_INVALID;
     std::lock_guard<std::mutex> lk(c->mu);
-    if (!d_dist || !d_rowids || !d_counts || !d_out_dist || !d_out_rowids || !d_out_n || lists <= 0 || k < 0)
+    if (!d_dist || !d_rowids || !d_counts || !d_out_dist || !d_out_rowids || !d_out_n || lists <= 0 || k < 0 || nq < 0)
         return fail(c, CLIPDB_ERR_INVALID, "merge: bad argument");
-    if (dist_stride % 4 || rowid_stride % 8 || count_stride % 4 ||
-        (reinterpret_cast<uintptr_t>(d_rowids) & 7) || (reinterpret_cast<uintptr_t>(d_dist) & 3) ||
-        (reinterpret_cast<uintptr_t>(d_counts) & 3))
+    if (dist_stride % 4 || rowid_stride % 8 || count_stride % 4 || dist_qstride % 4 || rowid_qstride % 8 ||
+        count_qstride % 4 || (reinterpret_cast<uintptr_t>(d_rowids) & 7) ||
+        (reinterpret_cast<uintptr_t>(d_dist) & 3) || (reinterpret_cast<uintptr_t>(d_counts) & 3))
         return fail(c, CLIPDB_ERR_INVALID, "merge: misaligned list layout");
     DeviceGuard g(c->device);
+    if (nq == 0) return CLIPDB_OK;
     if (k == 0) {
-        CU_TRY(c, cudaMemsetAsync(d_out_n, 0, sizeof(int32_t), c->stream));
+        CU_TRY(c, cudaMemsetAsync(d_out_n, 0, static_cast<size_t>(nq) * sizeof(int32_t), c->stream));
         return CLIPDB_OK;
     }
     const int64_t total = static_cast<int64_t>(lists) * k;
@@ -1230,10 +1231,21 @@ int clipdb_merge_strided_device(clipdb_ctx *c, const void *d_dist, int64_t dist_
     in.dist_stride = dist_stride;
     in.rowid_stride = rowid_stride;
     in.count_stride = count_stride;
-    merge_shards_kernel<<<1, MERGE_THREADS, smem, c->stream>>>(in, lists, k, d_out_dist, d_out_rowids, d_out_n);
+    in.dist_qstride = dist_qstride;
+    in.rowid_qstride = rowid_qstride;
+    in.count_qstride = count_qstride;
+    merge_shards_kernel<<<nq, MERGE_THREADS, smem, c->stream>>>(in, lists, k, d_out_dist, d_out_rowids, d_out_n);
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     return CLIPDB_OK;
+}
+
+int clipdb_merge_strided_device(clipdb_ctx *c, const void *d_dist, int64_t dist_stride,
+                                const void *d_rowids, int64_t rowid_stride, const void *d_counts,
+                                int64_t count_stride, int32_t lists, int32_t k, float *d_out_dist,
+                                int64_t *d_out_rowids, int32_t *d_out_n) {
+    return clipdb_merge_batch_device(c, d_dist, dist_stride, 0, d_rowids, rowid_stride, 0, d_counts, count_stride, 0,
+                                     lists, 1, k, d_out_dist, d_out_rowids, d_out_n);
 }
 
 int clipdb_merge_device(clipdb_ctx *c, const float *d_dist, const int64_t *d_rowids,

@@ -82,36 +82,41 @@ __global__ void decode_sorted_kernel(const uint64_t *__restrict__ keys, long lon
 // reads separate [lists][k] arrays or the packed per-rank records an NCCL
 // all-gather delivers.
 struct ShardLists {
-    const uint8_t *dist;    // float32[k] per list
-    const uint8_t *rowids;  // int64[k] per list
-    const uint8_t *counts;  // int32 per list
-    long long dist_stride, rowid_stride, count_stride;
+    const uint8_t *dist;    // float32[k] per (list, query)
+    const uint8_t *rowids;  // int64[k] per (list, query)
+    const uint8_t *counts;  // int32 per (list, query)
+    long long dist_stride, rowid_stride, count_stride;     // bytes between consecutive lists
+    long long dist_qstride, rowid_qstride, count_qstride;  // bytes between consecutive queries
 };
 
-__device__ __forceinline__ const float *shard_dist(const ShardLists &s, int l) {
-    return reinterpret_cast<const float *>(s.dist + static_cast<long long>(l) * s.dist_stride);
+__device__ __forceinline__ const float *shard_dist(const ShardLists &s, int l, int q) {
+    return reinterpret_cast<const float *>(s.dist + static_cast<long long>(l) * s.dist_stride +
+                                           static_cast<long long>(q) * s.dist_qstride);
 }
-__device__ __forceinline__ const int64_t *shard_rowids(const ShardLists &s, int l) {
-    return reinterpret_cast<const int64_t *>(s.rowids + static_cast<long long>(l) * s.rowid_stride);
+__device__ __forceinline__ const int64_t *shard_rowids(const ShardLists &s, int l, int q) {
+    return reinterpret_cast<const int64_t *>(s.rowids + static_cast<long long>(l) * s.rowid_stride +
+                                             static_cast<long long>(q) * s.rowid_qstride);
 }
-__device__ __forceinline__ int shard_count(const ShardLists &s, int l) {
-    return *reinterpret_cast<const int32_t *>(s.counts + static_cast<long long>(l) * s.count_stride);
+__device__ __forceinline__ int shard_count(const ShardLists &s, int l, int q) {
+    return *reinterpret_cast<const int32_t *>(s.counts + static_cast<long long>(l) * s.count_stride +
+                                              static_cast<long long>(q) * s.count_qstride);
 }
 
+// grid.x = query; outputs are [nq][k] / [nq]
 __global__ void __launch_bounds__(MERGE_THREADS) merge_shards_kernel(
     const ShardLists in, int lists, int k, float *__restrict__ out_dist,
     int64_t *__restrict__ out_rowids, int32_t *__restrict__ out_n) {
     extern __shared__ __align__(16) uint8_t merge_smem[];
     uint64_t *s = reinterpret_cast<uint64_t *>(merge_smem);
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, q = blockIdx.x;
     const int total = lists * k;
     const int padded = next_pow2(total);
     for (int i = tid; i < padded; i += MERGE_THREADS) {
         uint64_t key = KEY_EMPTY;
         if (i < total) {
             const int l = i / k, p = i - l * k;
-            if (p < shard_count(in, l)) {
-                const float d = shard_dist(in, l)[p];
+            if (p < shard_count(in, l, q)) {
+                const float d = shard_dist(in, l, q)[p];
                 if (d == d) key = make_key(d, static_cast<uint32_t>(i));
             }
         }
@@ -125,12 +130,12 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_shards_kernel(
         if (valid) {
             const int src = static_cast<int>(s[i] & 0xFFFFFFFFull);
             const int l = src / k, p = src - l * k;
-            out_dist[i] = shard_dist(in, l)[p];
-            out_rowids[i] = shard_rowids(in, l)[p];
+            out_dist[static_cast<size_t>(q) * k + i] = shard_dist(in, l, q)[p];
+            out_rowids[static_cast<size_t>(q) * k + i] = shard_rowids(in, l, q)[p];
         }
         found += __syncthreads_count(valid);
     }
-    if (tid == 0) *out_n = found;
+    if (tid == 0) out_n[q] = found;
 }
 
 }  // namespace clipdb

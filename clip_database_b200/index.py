@@ -63,6 +63,7 @@ class GpuIndex:
             raise _lib.ClipdbError(rc, "clipdb_create failed (no usable CUDA device? there is no CPU fallback)")
         self.device = int(device)
         self._keepalive = []  # tensors borrowed by attach()
+        self.batch_enabled = False
 
     # ---- lifetime -----------------------------------------------------------------
     def close(self) -> None:
@@ -294,6 +295,33 @@ class GpuIndex:
         """Build (or drop) the bf16 copy of the store used by the tensor-core batched path.
         Afterwards ``search()`` with 2 or more queries uses it; results are identical."""
         self._check(self._L.clipdb_enable_batch(self._ctx, int(bool(enable))))
+        self.batch_enabled = bool(enable)
+
+    def search_ptrs(self, q_ptr: int, nq: int, k: int, p_rowids: int, p_dist: int, p_n: int, p_nan: int,
+                    metric="cosine", use_mask: bool = False) -> None:
+        """Async exact search on raw device addresses (outputs nq x k row-major)."""
+        self._check(self._L.clipdb_search_device(
+            self._ctx, ctypes.c_void_p(q_ptr), nq, int(k), _metric(metric), int(bool(use_mask)),
+            ctypes.c_void_p(p_rowids), ctypes.c_void_p(p_dist), ctypes.c_void_p(p_n), ctypes.c_void_p(p_nan)))
+
+    def search_batch_ptrs(self, q_ptr: int, nq: int, k: int, p_rowids: int, p_dist: int, p_n: int, p_nan: int,
+                          p_flags: int) -> None:
+        """Async batched (tensor-core) search on raw device addresses, nq <= 256."""
+        self._check(self._L.clipdb_search_batch_device(
+            self._ctx, ctypes.c_void_p(q_ptr), nq, int(k), ctypes.c_void_p(p_rowids), ctypes.c_void_p(p_dist),
+            ctypes.c_void_p(p_n), ctypes.c_void_p(p_nan), ctypes.c_void_p(p_flags)))
+
+    def merge_batch_records_device(self, records, nq: int, k: int, off_rowids: int, off_dist: int, off_count: int,
+                                   out_dist, out_rowids, out_n) -> None:
+        """Async merge of gathered per-rank BATCH records ``[lists, record_bytes]`` (uint8 CUDA tensor):
+        within a record, query q's arrays sit q*k*8 / q*k*4 / q*4 bytes after the given offsets."""
+        lists, rec = records.shape
+        base = records.data_ptr()
+        self._check(self._L.clipdb_merge_batch_device(
+            self._ctx, ctypes.c_void_p(base + off_dist), rec, 4 * k, ctypes.c_void_p(base + off_rowids), rec, 8 * k,
+            ctypes.c_void_p(base + off_count), rec, 4, lists, int(nq), int(k),
+            ctypes.c_void_p(out_dist.data_ptr()), ctypes.c_void_p(out_rowids.data_ptr()),
+            ctypes.c_void_p(out_n.data_ptr())))
 
     def search_batch_device(self, d_queries, k: int, out_rowids, out_dist, out_n, out_nan, flags) -> None:
         """Async batched search (<= 256 queries): torch CUDA tensors; ``flags[q] != 0`` marks

@@ -54,6 +54,38 @@ class RecordLayout:
         return (8 + 12 * self.k + 4 + 15) // 16 * 16
 
 
+@dataclass(frozen=True)
+class BatchRecordLayout:
+    """One rank's packed result for nq queries: nan(int64[nq]) | rowids(int64[nq][k]) |
+    dist(float32[nq][k]) | count(int32[nq]) | flags(int32[nq]) | pad to 16."""
+    nq: int
+    k: int
+
+    @property
+    def off_nan(self) -> int:
+        return 0
+
+    @property
+    def off_rowids(self) -> int:
+        return 8 * self.nq
+
+    @property
+    def off_dist(self) -> int:
+        return 8 * self.nq + 8 * self.nq * self.k
+
+    @property
+    def off_count(self) -> int:
+        return 8 * self.nq + 12 * self.nq * self.k
+
+    @property
+    def off_flags(self) -> int:
+        return self.off_count + 4 * self.nq
+
+    @property
+    def nbytes(self) -> int:
+        return (self.off_flags + 4 * self.nq + 15) // 16 * 16
+
+
 class CudaShardBackend:
     """Per-rank work on the GPU: local scan + top-k into a record, merge of gathered records."""
 
@@ -86,6 +118,42 @@ class CudaShardBackend:
     def merge(self, gathered, k: int, lay: RecordLayout, out_dist, out_rowids, out_n) -> None:
         self.index.merge_records_device(gathered, k, lay.off_rowids, lay.off_dist, lay.off_count,
                                         out_dist, out_rowids, out_n)
+
+    def local_search_batch(self, d_queries, k: int, record, lay: BatchRecordLayout) -> None:
+        """nq queries against this rank's shard into a packed batch record.  Uses the tensor-core
+        batched path when the index has its bf16 store (256 queries per pass, flagged queries
+        re-run through the exact scan), else the exact scan per query."""
+        t = self.torch
+        nq, dim = d_queries.shape
+        base = record.data_ptr()
+        qp = d_queries.data_ptr()
+        if not getattr(self.index, "batch_enabled", False) or k > 128:
+            self.index.search_ptrs(qp, nq, k, base + lay.off_rowids, base + lay.off_dist, base + lay.off_count,
+                                   base + lay.off_nan)
+            return
+        for q0 in range(0, nq, 256):
+            m = min(256, nq - q0)
+            self.index.search_batch_ptrs(qp + q0 * dim * 4, m, k, base + lay.off_rowids + q0 * k * 8,
+                                         base + lay.off_dist + q0 * k * 4, base + lay.off_count + q0 * 4,
+                                         base + lay.off_nan + q0 * 8, base + lay.off_flags + q0 * 4)
+        flags = record[lay.off_flags:lay.off_flags + 4 * nq].view(t.int32).cpu()      # syncs the stream
+        for q in t.nonzero(flags).flatten().tolist():
+            self.index.search_ptrs(qp + q * dim * 4, 1, k, base + lay.off_rowids + q * k * 8,
+                                   base + lay.off_dist + q * k * 4, base + lay.off_count + q * 4,
+                                   base + lay.off_nan + q * 8)
+
+    def merge_batch(self, gathered, nq: int, k: int, lay: BatchRecordLayout, out_dist, out_rowids, out_n) -> None:
+        self.index.merge_batch_records_device(gathered, nq, k, lay.off_rowids, lay.off_dist, lay.off_count,
+                                              out_dist, out_rowids, out_n)
+
+    def new_batch_outputs(self, nq: int, k: int):
+        t = self.torch
+        return (t.empty((nq, max(k, 1)), dtype=t.float32, device=self.device),
+                t.empty((nq, max(k, 1)), dtype=t.int64, device=self.device),
+                t.zeros(nq, dtype=t.int32, device=self.device))
+
+    def queries_to_device(self, queries: np.ndarray):
+        return self.torch.from_numpy(np.ascontiguousarray(queries, dtype=np.float32)).to(self.device)
 
     def new_outputs(self, k: int):
         """(dist[k], rowids[k], n[1]) as views into ONE packed device record, so the host
@@ -146,6 +214,26 @@ class ShardedIndex:
             src = self.record.view(1, -1)
         self.backend.merge(src, k, self.layout, self.out_dist, self.out_rowids, self.out_n)
         return self.out_dist, self.out_rowids, self.out_n
+
+    def search_batch(self, queries: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """nq host queries -> (rowids [nq, k], distances [nq, k], counts [nq]); synchronous.
+        Every rank scans its shard for all queries, ONE all-gather moves nq*k candidates per
+        rank, every rank merges per query with the (distance, rowid) order."""
+        queries = np.ascontiguousarray(queries, dtype=np.float32)
+        nq = queries.shape[0]
+        lay = BatchRecordLayout(nq, k)
+        record = self.backend.new_buffer(lay.nbytes)
+        d_q = self.backend.queries_to_device(queries)
+        self.backend.local_search_batch(d_q, k, record, lay)
+        if self.world > 1:
+            gathered = self.backend.new_buffer(lay.nbytes * self.world)
+            self.dist.all_gather_into_tensor(gathered, record, group=self.group)
+            gathered = gathered.view(self.world, lay.nbytes)
+        else:
+            gathered = record.view(1, -1)
+        out_dist, out_rowids, out_n = self.backend.new_batch_outputs(nq, k)
+        self.backend.merge_batch(gathered, nq, k, lay, out_dist, out_rowids, out_n)
+        return (out_rowids.cpu().numpy().copy(), out_dist.cpu().numpy().copy(), out_n.cpu().numpy().copy())
 
     def nan_rows(self) -> int:
         """Admitted rows with NaN distance over all shards for the last search."""

@@ -201,6 +201,14 @@ int clipdb_merge_strided_device(clipdb_ctx *ctx, const void *d_dist, int64_t dis
                                 int32_t lists, int32_t k,
                                 float *d_out_dist, int64_t *d_out_rowids, int32_t *d_out_n);
 
+/* Batched form: nq queries per list; consecutive queries of one list are
+ * *_query_stride bytes apart.  Outputs are nq x k (row-major) and nq counts. */
+int clipdb_merge_batch_device(clipdb_ctx *ctx, const void *d_dist, int64_t dist_stride, int64_t dist_query_stride,
+                              const void *d_rowids, int64_t rowid_stride, int64_t rowid_query_stride,
+                              const void *d_counts, int64_t count_stride, int64_t count_query_stride,
+                              int32_t lists, int32_t nq, int32_t k,
+                              float *d_out_dist, int64_t *d_out_rowids, int32_t *d_out_n);
+
 /* ---- measurement ------------------------------------------------------------
  * With profiling enabled every scan kernel (the dominant, HBM-bound launch) is
  * bracketed by CUDA events on the launching stream; clipdb_profile_read syncs

@@ -37,6 +37,17 @@ out = []
 for q in queries:
     ids, d = sh.search(q, k)
     out.append((ids.tolist(), d.tolist(), sh.nan_rows()))
+n2 = 140_000
+rows2 = synth.unit_rows(n2, 1152, 77)
+lo2, hi2 = shard_bounds(n2, world)[rank]
+idx2 = GpuIndex(rank)
+idx2.load(rows2[lo2:hi2], np.arange(lo2 + 1, hi2 + 1))
+idx2.enable_batch()
+sh2 = ShardedIndex(CudaShardBackend(idx2))
+bq = synth.unit_rows(40, 1152, 5)
+b_ids, b_d, b_n = sh2.search_batch(bq, 50)
+np.savez(os.path.join({out!r}, f"batch{{rank}}.npz"), ids=b_ids, d=b_d, n=b_n)
+idx2.close()
 json.dump(out, open(os.path.join({out!r}, f"rank{{rank}}.json"), "w"))
 idx.close()
 dist.destroy_process_group()
@@ -69,5 +80,17 @@ def test_nccl_sharded_search_equals_unsharded(tmp_path):
             assert nan == 0
             assert_topk_parity(np.array(ids) - 1, np.array(d, dtype=np.float32), oseq, od, ref.distances(rows, q))
         assert got[3][0][:2] == [4, n]          # cross-shard exact tie in rowid order
+    # batched sharded search (tensor-core path per shard) == single-store exact search
+    rows2 = synth.unit_rows(140_000, 1152, 77)
+    bq = synth.unit_rows(40, 1152, 5)
+    from clip_database_b200 import GpuIndex
+    with GpuIndex(0) as whole:
+        whole.load(rows2, np.arange(1, rows2.shape[0] + 1))
+        want = whole.search(bq, 50)
+    for rank in range(world):
+        b = np.load(tmp_path / f"batch{rank}.npz")
+        assert np.array_equal(b["n"], want.counts)
+        assert np.array_equal(b["ids"], want.rowids)
+        assert np.array_equal(b["d"].view(np.uint32), want.distances.view(np.uint32))
     # every rank holds the same merged answer
     assert json.load(open(tmp_path / "rank0.json")) == json.load(open(tmp_path / f"rank{world - 1}.json"))

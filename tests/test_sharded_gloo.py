@@ -42,6 +42,40 @@ class OracleShardBackend:
         buf[lay.off_dist:lay.off_dist + 4 * len(d)].view(np.float32)[:] = d
         buf[lay.off_count:lay.off_count + 4].view(np.int32)[0] = len(ids)
 
+    def queries_to_device(self, queries):
+        return torch.from_numpy(np.ascontiguousarray(queries, dtype=np.float32))
+
+    def new_batch_outputs(self, nq, k):
+        return (torch.empty((nq, max(k, 1)), dtype=torch.float32), torch.empty((nq, max(k, 1)), dtype=torch.int64),
+                torch.zeros(nq, dtype=torch.int32))
+
+    def local_search_batch(self, d_queries, k, record, lay):
+        buf = record.numpy()
+        for q, vec in enumerate(d_queries.numpy()):
+            ids, d, _, n_nan = ref.knn(self.rows, vec, k, rowids=self.rowids)
+            buf[lay.off_nan + 8 * q:lay.off_nan + 8 * q + 8].view(np.int64)[0] = n_nan
+            o = lay.off_rowids + 8 * k * q
+            buf[o:o + 8 * len(ids)].view(np.int64)[:] = ids
+            o = lay.off_dist + 4 * k * q
+            buf[o:o + 4 * len(d)].view(np.float32)[:] = d
+            buf[lay.off_count + 4 * q:lay.off_count + 4 * q + 4].view(np.int32)[0] = len(ids)
+
+    def merge_batch(self, gathered, nq, k, lay, out_dist, out_rowids, out_n):
+        g = gathered.numpy()
+        for q in range(nq):
+            entries = []
+            for l in range(g.shape[0]):
+                cnt = int(g[l, lay.off_count + 4 * q:lay.off_count + 4 * q + 4].view(np.int32)[0])
+                ids = g[l, lay.off_rowids + 8 * k * q:lay.off_rowids + 8 * k * (q + 1)].view(np.int64)
+                d = g[l, lay.off_dist + 4 * k * q:lay.off_dist + 4 * k * (q + 1)].view(np.float32)
+                entries += [(float(d[p]), l, p, int(ids[p])) for p in range(cnt)]
+            entries.sort(key=lambda e: e[:3])
+            entries = entries[:k]
+            out_n[q] = len(entries)
+            for i, e in enumerate(entries):
+                out_dist[q, i] = e[0]
+                out_rowids[q, i] = e[3]
+
     def merge(self, gathered, k, lay, out_dist, out_rowids, out_n):
         g = gathered.numpy()
         entries = []
@@ -77,8 +111,9 @@ def _worker(rank, world, port, n, k, out_dir):
     queries = synth.unit_rows(3, DIM, 99)
     queries[2] = rows[3]
     got = [index.search(q, k) for q in queries]
+    b_ids, b_d, b_n = index.search_batch(queries, k)
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), ids=np.stack([g[0] for g in got]),
-             d=np.stack([g[1] for g in got]))
+             d=np.stack([g[1] for g in got]), b_ids=b_ids, b_d=b_d, b_n=b_n)
     dist.destroy_process_group()
 
 
@@ -96,6 +131,9 @@ def test_sharded_equals_unsharded_over_gloo(tmp_path, world):
             ids, d, _, _ = ref.knn(rows, q, k, rowids=np.arange(1, n + 1))
             assert np.array_equal(got["ids"][qi], ids)
             assert np.array_equal(got["d"][qi], d)
+            assert got["b_n"][qi] == k
+            assert np.array_equal(got["b_ids"][qi], ids)        # batched sharded search == unsharded
+            assert np.array_equal(got["b_d"][qi], d)
     # the planted tie comes back in rowid order across shards
     assert got["ids"][2][:2].tolist() == [4, n]
 
