@@ -55,6 +55,8 @@ def parse_args():
                     help="single: configs[1]; blend: configs[3] (0.7/0.3 blend + negative, then the scan); "
                          "batch: configs[2] (B queries per step through the tcgen05 contraction + fp32 re-rank)")
     ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--sample-stride", type=int, default=0, help="batch: pass A sampling stride (0 = auto)")
+    ap.add_argument("--no-refine", action="store_true", help="batch: skip the second threshold")
     ap.add_argument("--variant", type=int, default=0, help="scan kernel: 0 auto, 1 TMA ring, 2 direct loads")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-rows", type=int, default=100_000)
@@ -264,6 +266,8 @@ def run_batch_workload(args, torch, idx, rows, rows_per_gpu, device, rank, local
     filter-pass kernel's own duration)."""
     B, k = args.batch, args.k
     idx.enable_batch()
+    idx.set_option("batch_sample_stride", args.sample_stride)
+    idx.set_option("batch_refine", 0 if args.no_refine else 1)
     rng = np.random.default_rng(99)
     n_sets = 4
     host_q = rng.standard_normal((n_sets, B, DIM), dtype=np.float32)
@@ -293,6 +297,7 @@ def run_batch_workload(args, torch, idx, rows, rows_per_gpu, device, rank, local
     idx.profile(False)
     launches = idx.launch_count - launches0
     flagged = int((flags != 0).sum())
+    cand, surv = idx.batch_stats()
 
     for i in range(min(args.warmup, 3)):
         idx.search(host_q[i % n_sets], k)
@@ -325,12 +330,15 @@ def run_batch_workload(args, torch, idx, rows, rows_per_gpu, device, rank, local
                                "(BASELINE configs[2]): tcgen05 contraction + fp32 re-rank" % (B, k, rows_per_gpu),
                    "rows_per_gpu": rows_per_gpu, "batch": B, "k": k, "dim": DIM,
                    "store_bytes": {"fp32": rows_per_gpu * ROW_BYTES, "bf16": rows_per_gpu * DIM * 2},
-                   "l2": "inputs_larger_than_L2"},
+                   "l2": "inputs_larger_than_L2", "sample_stride": args.sample_stride,
+                   "refine": not args.no_refine},
         "equivalent_scan_GBps_fp32": B * rows_per_gpu * ROW_BYTES / 1e9 / (ms_step / 1e3),
         "e2e": {"value": B * 1e3 / e2e_ms, "unit": "queries/s", "h2d_bytes_per_step": B * ROW_BYTES,
                 "d2h_bytes_per_step": B * (k * 12 + 12) + B * 4, "ms_per_step": e2e_ms,
                 "api": "GpuIndex.search (clipdb_search, nq=%d)" % B},
         "gpu_launches": int(launches), "flagged_queries_last_step": flagged,
+        "candidates_per_query": {"filter_mean": float(cand[:B].mean()), "filter_max": int(cand[:B].max()),
+                                 "reranked_mean": float(surv[:B].mean()), "reranked_max": int(surv[:B].max())},
         "roofline": {"bound": "tensor", "kernel": "batch_gemm_kernel<filter>", "achieved": flops / 1e12 / (gemm_avg / 1e3),
                      "peak": peak, "unit": "TFLOP/s", "frac": flops / 1e12 / (gemm_avg / 1e3) / peak,
                      "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained", "flops_per_launch": flops,

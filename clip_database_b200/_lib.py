@@ -18,7 +18,7 @@ METRIC_COSINE = 0
 METRIC_L2 = 1
 BLEND_POSITIVE_ZERO_NORM = 1
 BLEND_NEGATIVE_ZERO_NORM = 2
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # every symbol include/clipdb.h declares: (name, restype, argtypes)
 _F = POINTER(c_float)
@@ -56,8 +56,9 @@ SIGNATURES = [
     ("clipdb_blend_search", c_int, [_CTX, _F, _F, c_double, c_double, _F, _D, c_int32, c_int32,
                                     c_int32, c_int32, _I64, _F, _I32, _I64, _F, _I32]),
     ("clipdb_enable_batch", c_int, [_CTX, c_int32]),
-    ("clipdb_search_batch_device", c_int, [_CTX, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+    ("clipdb_search_batch_device", c_int, [_CTX, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_void_p]),
+    ("clipdb_batch_stats", c_int, [_CTX, c_void_p, c_void_p]),
     ("clipdb_merge_device", c_int, [_CTX, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                     c_void_p, c_void_p, c_void_p]),
     ("clipdb_merge_strided_device", c_int, [_CTX, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,

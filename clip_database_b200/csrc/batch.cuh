@@ -50,9 +50,10 @@ constexpr int BQ_B_BYTES = BQ_N * BQ_BLOCK_K * 2;   // 32,768
 constexpr int BQ_STAGE_BYTES = BQ_A_BYTES + BQ_B_BYTES;
 constexpr int BQ_THREADS = 192;  // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 epilogue
 constexpr int BQ_HEADER = 2048;  // barriers, TMEM base, thresholds
-constexpr int BQ_SMEM_BYTES = BQ_HEADER + BQ_STAGES * BQ_STAGE_BYTES + 1024;  // + alignment slack
+constexpr int BQ_QUEUE_SMEM = 4 * 256 * 12;  // = BQ_QUEUE_BYTES (the epilogue warps' hit queues)
+constexpr int BQ_SMEM_BYTES = BQ_HEADER + BQ_STAGES * BQ_STAGE_BYTES + 1024 + BQ_QUEUE_SMEM;  // + alignment slack
 constexpr int BQ_TMEM_COLS = 512;
-constexpr int BQ_SAMPLE_STRIDE = 16;  // pass A visits every 16th tile
+constexpr int BQ_SAMPLE_STRIDE_MAX = 64;  // pass A visits at most every 64th tile (host picks the stride)
 // |cos^ - cos| <= e_d + e_q (1 + e_d) + slack, where e_d = max over rows of ||d^ - d|| / ||d|| and
 // e_q = ||q^ - q|| / ||q|| are the MEASURED bf16 rounding-error norms (Cauchy-Schwarz on
 // q.(d^-d) + (q^-q).d^) and the slack covers the tensor core's fp32 accumulation of 1152 exact
@@ -139,10 +140,12 @@ __device__ __forceinline__ size_t tiled_offset(long long row, int k) {  // eleme
     return ((static_cast<size_t>(tile) * BQ_K_BLOCKS + kb) * BQ_M + r) * BQ_BLOCK_K + kk;
 }
 
-// one warp per row: bf16 copy, 1/||row|| (float32), count of rows whose norm is 0 or not finite
+// one warp per row: bf16 copy of the UNIT-NORMALISED row n = d/||d|| (so the contraction yields
+// u = q^ . n^ directly and the epilogue needs no per-row scale), the count of rows whose norm is 0
+// or not finite (stored as NaN: never pass a >= test), and the largest rounding-error norm
+// ||n^ - n|| over the store (float32 n; its own 2^-23-level error is inside BQ_ACCUM_SLACK).
 __global__ void __launch_bounds__(256) build_bf16_store_kernel(const float *__restrict__ rows, long long n,
                                                                __nv_bfloat16 *__restrict__ out,
-                                                               float *__restrict__ inv_norm,
                                                                unsigned long long *__restrict__ bad_rows,
                                                                unsigned int *__restrict__ max_row_err_bits) {
     const int lane = threadIdx.x & 31;
@@ -152,33 +155,39 @@ __global__ void __launch_bounds__(256) build_bf16_store_kernel(const float *__re
     float worst = 0.f;
     for (long long r = warp; r < n; r += warps) {
         const float4 *src = reinterpret_cast<const float4 *>(rows + r * SCAN_DIM);
-        float ss = 0.f, es = 0.f;
+        float4 v[SCAN_CHUNKS];
+        float ss = 0.f;
 #pragma unroll
         for (int j = 0; j < SCAN_CHUNKS; j++) {
-            const float4 v = ldg_stream(src + lane + 32 * j);
-            ss = fmaf(v.x, v.x, ss);
-            ss = fmaf(v.y, v.y, ss);
-            ss = fmaf(v.z, v.z, ss);
-            ss = fmaf(v.w, v.w, ss);
-            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            v[j] = ldg_stream(src + lane + 32 * j);
+            ss = fmaf(v[j].x, v[j].x, ss);
+            ss = fmaf(v[j].y, v[j].y, ss);
+            ss = fmaf(v[j].z, v[j].z, ss);
+            ss = fmaf(v[j].w, v[j].w, ss);
+        }
+        ss = warp_sum(ss);
+        float inv = 1.0f / sqrtf(ss);
+        const bool ok = ss > 0.f && isfinite(inv) && isfinite(ss);
+        if (!ok) inv = __int_as_float(0x7fc00000);  // NaN row
+        float es = 0.f;
+#pragma unroll
+        for (int j = 0; j < SCAN_CHUNKS; j++) {
+            const float x = v[j].x * inv, y = v[j].y * inv, z = v[j].z * inv, w = v[j].w * inv;
+            __nv_bfloat162 lo = __floats2bfloat162_rn(x, y), hi = __floats2bfloat162_rn(z, w);
             const float2 rl = __bfloat1622float2(lo), rh = __bfloat1622float2(hi);
-            es = fmaf(rl.x - v.x, rl.x - v.x, es);
-            es = fmaf(rl.y - v.y, rl.y - v.y, es);
-            es = fmaf(rh.x - v.z, rh.x - v.z, es);
-            es = fmaf(rh.y - v.w, rh.y - v.w, es);
+            es = fmaf(rl.x - x, rl.x - x, es);
+            es = fmaf(rl.y - y, rl.y - y, es);
+            es = fmaf(rh.x - z, rh.x - z, es);
+            es = fmaf(rh.y - w, rh.y - w, es);
             uint2 packed;
             packed.x = *reinterpret_cast<uint32_t *>(&lo);
             packed.y = *reinterpret_cast<uint32_t *>(&hi);
             *reinterpret_cast<uint2 *>(out + tiled_offset(r, (lane + 32 * j) * 4)) = packed;
         }
-        ss = warp_sum(ss);
         es = warp_sum(es);
-        const float inv = 1.0f / sqrtf(ss);
-        const bool ok = ss > 0.f && isfinite(inv) && isfinite(ss);
         if (lane == 0) {
-            inv_norm[r] = ok ? inv : __int_as_float(0x7fc00000);  // NaN: never passes a >= test
             if (!ok) bad++;
-            else worst = fmaxf(worst, sqrtf(es) * inv * 1.0001f);  // ||d^ - d|| / ||d||, rounded up
+            else worst = fmaxf(worst, sqrtf(es) * 1.0001f);  // ||n^ - n||, ||n|| = 1, rounded up
         }
     }
     if (lane == 0) {
@@ -220,43 +229,89 @@ __global__ void __launch_bounds__(128) prep_queries_kernel(const float *__restri
 // ---- the contraction ---------------------------------------------------------------------------
 
 struct BatchGemmArgs {
-    const float *inv_norm;      // [n]
     const float *thr;           // [256] FILTER: keep iff u >= thr[q]
     float *scores;              // DUMP: [sample_groups][256] group maxima of u
     unsigned int *cand_count;   // FILTER: [256]
     unsigned int *cand_rows;    // FILTER: [256][cand_cap]
+    float *cand_u;              // FILTER: [256][cand_cap] the candidate's u (for the second, tighter threshold)
+    const uint32_t *mask;       // nullable admission bitset (folder pre-filter, idb:1509-1530)
     long long n;
     long long sample_groups;    // DUMP: number of 32-row groups (= 4 per sampled tile)
     int total_tiles;            // ceil(n / 128)
-    int tile_stride;            // 1 (FILTER) or BQ_SAMPLE_STRIDE (DUMP)
+    int tile_stride;            // 1 (FILTER) or the sampling stride (DUMP)
     int cand_cap;
 };
 
-// Filter 32 accumulator columns of one row.  The common case (no column reaches its
-// threshold: ~99 % of chunks) costs one FMUL + one predicate-accumulating FSETP per element
-// with no branches; only chunks with a hit take the slow path with the atomics.  The
-// epilogue must stay well under the ~9,200 cycles the tensor pipe needs per 128-row tile:
-// the first version (a branch per element, ~3,000 instructions per thread per tile) made
-// the whole contraction epilogue-bound (profiles/r01_batch_gemm_ncu.md).
-__device__ __forceinline__ void filter_chunk(const uint32_t (&r)[32], float inv, const float *thr, bool row_ok,
-                                             long long row, int q0, const BatchGemmArgs &a) {
-    bool any0 = false, any1 = false;
-#pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-        any0 |= __uint_as_float(r[j]) * inv >= thr[j];
-        any1 |= __uint_as_float(r[j + 1]) * inv >= thr[j + 1];
+// ---- filter epilogue ---------------------------------------------------------------------------
+// Per 32 accumulator columns of one row: a 32-bit hit mask (one FSETP + one predicated OR per
+// element, no branches).  Hits are rare (a few per warp per tile) but each one needs a slot in
+// its query's candidate list, i.e. a global atomicAdd whose ~700-cycle round trip would sit in
+// the epilogue's critical path: with hits in most warp-chunks (sparse pass-A sampling) that made
+// the whole contraction epilogue-bound (6.0 ms instead of 4.5 ms, profiles/).  So hits go into a
+// per-warp shared-memory queue (warp prefix sum, no global traffic) that is flushed 32 entries
+// at a time — one atomic per lane, all in flight together — when it fills up and at the end.
+// Dense bursts (a threshold of -inf keeps everything) bypass the queue.
+constexpr int BQ_QUEUE_CAP = 256;     // entries per epilogue warp
+constexpr int BQ_QUEUE_BURST = 64;    // a chunk with more hits than this goes straight to global memory
+constexpr int BQ_QUEUE_BYTES = 4 * BQ_QUEUE_CAP * 12;   // 4 epilogue warps x (row, query, u)
+static_assert(BQ_QUEUE_BYTES == BQ_QUEUE_SMEM, "queue size and shared-memory budget disagree");
+
+struct HitQueue {
+    uint32_t *row;   // [BQ_QUEUE_CAP] this warp's slice of shared memory
+    uint32_t *qry;
+    uint32_t *u;
+    int fill;        // warp-uniform
+};
+
+__device__ __forceinline__ void push_candidate(const BatchGemmArgs &a, uint32_t q, uint32_t row, uint32_t u_bits) {
+    const unsigned pos = atomicAdd(a.cand_count + q, 1u);
+    if (pos < static_cast<unsigned>(a.cand_cap)) {
+        a.cand_rows[static_cast<size_t>(q) * a.cand_cap + pos] = row;
+        a.cand_u[static_cast<size_t>(q) * a.cand_cap + pos] = __uint_as_float(u_bits);
     }
-    if ((any0 || any1) && row_ok) {
+}
+
+__device__ __forceinline__ void flush_queue(HitQueue &hq, const BatchGemmArgs &a, int lane) {
+    __syncwarp();
+    for (int i = lane; i < hq.fill; i += 32) push_candidate(a, hq.qry[i], hq.row[i], hq.u[i]);
+    __syncwarp();
+    hq.fill = 0;
+}
+
+__device__ __forceinline__ void filter_chunk(const uint32_t (&r)[32], const float *thr, bool row_ok, uint32_t row,
+                                             int q0, const BatchGemmArgs &a, HitQueue &hq, int lane) {
+    uint32_t hits = 0;
+#pragma unroll
+    for (int j = 0; j < 32; j++)
+        if (__uint_as_float(r[j]) >= thr[j]) hits |= 1u << j;
+    if (!row_ok) hits = 0;
+    if (!__any_sync(FULL_MASK, hits != 0)) return;
+    const int cnt = __popc(hits);
+    int incl = cnt;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(FULL_MASK, incl, off);
+        if (lane >= off) incl += v;
+    }
+    const int total = __shfl_sync(FULL_MASK, incl, 31);
+    if (total > BQ_QUEUE_BURST) {
 #pragma unroll   // static indices: r[] must stay in registers
-        for (int j = 0; j < 32; j++) {
-            if (__uint_as_float(r[j]) * inv >= thr[j]) {
-                const int q = q0 + j;
-                const unsigned pos = atomicAdd(a.cand_count + q, 1u);
-                if (pos < static_cast<unsigned>(a.cand_cap))
-                    a.cand_rows[static_cast<size_t>(q) * a.cand_cap + pos] = static_cast<unsigned>(row);
-            }
+        for (int j = 0; j < 32; j++)
+            if ((hits >> j) & 1u) push_candidate(a, static_cast<uint32_t>(q0 + j), row, r[j]);
+        return;
+    }
+    if (hq.fill + total > BQ_QUEUE_CAP) flush_queue(hq, a, lane);
+    int at = hq.fill + incl - cnt;
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        if ((hits >> j) & 1u) {
+            hq.row[at] = row;
+            hq.qry[at] = static_cast<uint32_t>(q0 + j);
+            hq.u[at] = r[j];
+            at++;
         }
     }
+    hq.fill += total;
 }
 
 template <bool DUMP>
@@ -352,12 +407,16 @@ __global__ void __launch_bounds__(BQ_THREADS, 1) batch_gemm_kernel(const __grid_
     } else {
         // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
         const int lane_base = 32 * (warp & 3);
+        HitQueue hq;
+        hq.row = reinterpret_cast<uint32_t *>(tiles + BQ_STAGES * BQ_STAGE_BYTES) + (warp & 3) * 3 * BQ_QUEUE_CAP;
+        hq.qry = hq.row + BQ_QUEUE_CAP;
+        hq.u = hq.qry + BQ_QUEUE_CAP;
+        hq.fill = 0;
         int it = 0;
         for (int t = first; t < eff_tiles; t += step, it++) {
             const int acc = it & 1;
             const long long row = static_cast<long long>(t) * a.tile_stride * BQ_M + lane_base + lane;
-            const bool row_ok = row < a.n;
-            const float inv = row_ok ? __ldg(a.inv_norm + row) : 0.f;
+            const bool row_ok = row < a.n && row_admitted(a.mask, row);
             mbar_wait(&tmem_full[acc], static_cast<uint32_t>(it >> 1) & 1u);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_base) << 16) +
@@ -372,7 +431,7 @@ __global__ void __launch_bounds__(BQ_THREADS, 1) batch_gemm_kernel(const __grid_
                     float m[32];
 #pragma unroll
                     for (int j = 0; j < 32; j++)
-                        m[j] = row_ok ? __uint_as_float(r[j]) * inv : __int_as_float(0xff800000);
+                        m[j] = row_ok ? __uint_as_float(r[j]) : __int_as_float(0xff800000);
 #pragma unroll
                     for (int half = 16; half >= 1; half >>= 1) {
                         const bool upper = (lane & half) != 0;
@@ -386,13 +445,14 @@ __global__ void __launch_bounds__(BQ_THREADS, 1) batch_gemm_kernel(const __grid_
                     const long long group = static_cast<long long>(t) * 4 + (warp & 3);
                     if (group < a.sample_groups) a.scores[group * BQ_N + c * 32 + lane] = m[0];
                 } else {
-                    filter_chunk(r, inv, thr_s + c * 32, row_ok, row, c * 32, a);
+                    filter_chunk(r, thr_s + c * 32, row_ok, static_cast<uint32_t>(row), c * 32, a, hq, lane);
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
+        if (!DUMP) flush_queue(hq, a, lane);
     }
 
     tc_fence_before();
@@ -411,7 +471,7 @@ constexpr int BP_STAGES = 6;
 constexpr int BP_A_BYTES = BQ_M * BQ_BLOCK_K * 2;          // 16,384: this CTA's 128 rows
 constexpr int BP_B_BYTES = (BQ_N / 2) * BQ_BLOCK_K * 2;    // 16,384: this CTA's 128 queries
 constexpr int BP_STAGE_BYTES = BP_A_BYTES + BP_B_BYTES;
-constexpr int BP_SMEM_BYTES = BQ_HEADER + BP_STAGES * BP_STAGE_BYTES + 1024;
+constexpr int BP_SMEM_BYTES = BQ_HEADER + BP_STAGES * BP_STAGE_BYTES + 1024 + BQ_QUEUE_SMEM;
 constexpr uint32_t BP_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((BQ_N >> 3) << 17) | ((256u >> 4) << 24);
 constexpr uint32_t BP_PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> CTA 0
 
@@ -572,13 +632,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
     } else {
         // ===== epilogue (both CTAs): warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
         const int lane_base = 32 * (warp & 3);
+        HitQueue hq;
+        hq.row = reinterpret_cast<uint32_t *>(tiles + BP_STAGES * BP_STAGE_BYTES) + (warp & 3) * 3 * BQ_QUEUE_CAP;
+        hq.qry = hq.row + BQ_QUEUE_CAP;
+        hq.u = hq.qry + BQ_QUEUE_CAP;
+        hq.fill = 0;
         int it = 0;
         for (int t = pair; t < eff_tiles; t += pairs, it++) {
             const int acc = it & 1;
             const long long t128 = static_cast<long long>(t) * a.tile_stride * 2 + rank;   // 128-row tile index
             const long long row = t128 * BQ_M + lane_base + lane;
-            const bool row_ok = row < a.n;
-            const float inv = row_ok ? __ldg(a.inv_norm + row) : 0.f;
+            const bool row_ok = row < a.n && row_admitted(a.mask, row);
             mbar_wait(&tmem_full[acc], static_cast<uint32_t>(it >> 1) & 1u);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_base) << 16) +
@@ -592,7 +656,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
                     float m[32];
 #pragma unroll
                     for (int j = 0; j < 32; j++)
-                        m[j] = row_ok ? __uint_as_float(r[j]) * inv : __int_as_float(0xff800000);
+                        m[j] = row_ok ? __uint_as_float(r[j]) : __int_as_float(0xff800000);
 #pragma unroll
                     for (int half = 16; half >= 1; half >>= 1) {
                         const bool upper = (lane & half) != 0;
@@ -606,13 +670,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
                     const long long group = (static_cast<long long>(t) * 2 + rank) * 4 + (warp & 3);
                     if (group < a.sample_groups) a.scores[group * BQ_N + c * 32 + lane] = m[0];
                 } else {
-                    filter_chunk(r, inv, thr_s + c * 32, row_ok, row, c * 32, a);
+                    filter_chunk(r, thr_s + c * 32, row_ok, static_cast<uint32_t>(row), c * 32, a, hq, lane);
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_on_cta(&tmem_empty[acc], 0);   // the leader's barrier
         }
+        if (!DUMP) flush_queue(hq, a, lane);
     }
 
     tc_fence_before();
@@ -641,86 +706,188 @@ __device__ __forceinline__ void write_part_list(WarpTopK<KPL> &top, uint64_t *sc
     for (int i = tid; i < 32 * KPL; i += BQ_SEL_THREADS) dst[i] = scratch[i];
 }
 
-// level 1 over the sampled group maxima scores[group][256]: best = largest u, keys order by -u
-template <int KPL>
-__global__ void __launch_bounds__(BQ_SEL_THREADS) batch_sample_topk_kernel(const float *__restrict__ scores,
-                                                                           long long groups, int k,
-                                                                           uint64_t *__restrict__ part_keys) {
-    __shared__ uint64_t scratch[BQ_SEL_WARPS * 32 * KPL];
-    const int q = blockIdx.x, part = blockIdx.y, parts = gridDim.y;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const long long lo = groups * part / parts, hi = groups * (part + 1) / parts;
-    WarpTopK<KPL> top;
-    top.init(k, lane);
-    constexpr int U = 8;  // independent loads in flight per lane
-    for (long long base = lo + static_cast<long long>(warp) * (32 * U); base < hi; base += BQ_SEL_WARPS * 32 * U) {
-        float u[U];
-#pragma unroll
-        for (int j = 0; j < U; j++) {
-            const long long i = base + j * 32 + lane;
-            u[j] = i < hi ? __ldg(scores + i * BQ_N + q) : __int_as_float(0xff800000);
-        }
-#pragma unroll
-        for (int j = 0; j < U; j++) {
-            const long long i = base + j * 32 + lane;
-            const bool valid = u[j] == u[j] && u[j] > __int_as_float(0xff800000);
-            const uint64_t key = valid ? make_key(-u[j], static_cast<uint32_t>(i)) : KEY_EMPTY;
-            unsigned pending = __ballot_sync(FULL_MASK, key < top.thr);
-            while (pending) {  // warp-uniform inserts, one offered key at a time (rare after warm-up)
-                const int src_lane = __ffs(pending) - 1;
-                const uint64_t kk = __shfl_sync(FULL_MASK, key, src_lane);
-                if (kk < top.thr) top.insert(kk, lane);
-                pending &= pending - 1;
-            }
-        }
-    }
-    write_part_list<KPL>(top, scratch, part_keys + (static_cast<size_t>(q) * parts + part) * (32 * KPL), tid, warp, lane);
+// ---- k-th largest of a query's values: radix select -------------------------------------------------
+// Thresholds need one order statistic per query (the k-th largest of ~10^4 floats), not a sorted
+// list.  Four passes over the values, most significant byte first: a shared-memory histogram of
+// the byte among the values that match the digits found so far, then one warp walks the 256 bins
+// from the top to find the bin holding the k-th largest.  Exact (all 32 bits of the orderable
+// encoding), ~10 us for 256 queries; the register top-k lists used by the scan took 0.2-0.3 ms
+// here because with k = 100 most of a warp's few hundred items are admissions.
+// A CTA serves QPC queries: thread t works for query q0 + t % QPC, so that values laid out
+// query-minor (scores[group][256]) are still read a sector at a time.
+constexpr int BQ_SELECT_PASSES = 3;   // 24 of 32 bits: the bucket's lower edge is <= the k-th largest by < 2^-15 relative
+
+template <int QPC>
+struct SelectSmem {
+    unsigned hist[QPC][256];
+    unsigned prefix[QPC];      // digits found so far (high bits of the answer)
+    unsigned remaining[QPC];   // rank still to be located inside the current prefix
+    unsigned short_of_k[QPC];  // fewer than k valid values
+};
+
+// valid floats -> uint32 ascending; invalid (NaN, -inf) values are skipped
+__device__ __forceinline__ bool select_key(float v, uint32_t &key) {
+    key = f32_orderable(v);
+    return v == v && v > __int_as_float(0xff800000);
 }
 
-// level 2 for thresholds: tau = k-th best sampled u; thr = tau - 2E||q||
-__global__ void __launch_bounds__(256) batch_threshold_finish_kernel(const uint64_t *__restrict__ part_keys,
-                                                                     int parts, int stride,
-                                                                     const float *__restrict__ q_norm,
-                                                                     const float *__restrict__ q_err,
-                                                                     const unsigned int *__restrict__ max_row_err_bits,
-                                                                     int nq, int k, float *__restrict__ thr,
-                                                                     int *__restrict__ flags) {
-    __shared__ uint64_t s[BQ_THR_PARTS * 128];
-    const int q = blockIdx.x, tid = threadIdx.x;
-    if (q >= nq) {  // padding slots never produce candidates
-        if (tid == 0) thr[q] = __int_as_float(0x7f800000);
-        return;
+// `load(ql, i)` returns the i-th value of local query ql; `count(ql)` its number of values.
+// Returns (to every thread) a value t <= the k-th largest valid value of query ql such that at
+// least k values are >= t, or -inf when there are fewer than k valid values.  The callers only
+// need such a lower bound, so the last byte is not resolved.
+template <int QPC, int THREADS, typename Load, typename Count>
+__device__ __forceinline__ float radix_select_kth_largest(SelectSmem<QPC> &sm, int k, int ql_out, Load load, Count count) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ql = tid % QPC, slot = tid / QPC;
+    constexpr int SLOTS = THREADS / QPC;
+    constexpr int U = 8;   // independent loads in flight per thread
+    if (tid < QPC) {
+        sm.prefix[tid] = 0;
+        sm.remaining[tid] = static_cast<unsigned>(k);
+        sm.short_of_k[tid] = 0;
     }
-    const int total = parts * stride, padded = next_pow2(total);
-    for (int i = tid; i < padded; i += 256)
-        s[i] = i < total ? part_keys[static_cast<size_t>(q) * total + i] : KEY_EMPTY;
-    block_bitonic_sort(s, padded, tid, 256);
-    if (tid == 0) {
-        const float qn = q_norm[q];
-        const uint64_t kth = s[k - 1];
-        int f = 0;
-        float t = __int_as_float(0x7f800000);
-        if (!(qn > 0.f) || !isfinite(qn)) {
-            f = BQ_FLAG_BAD_QUERY;
-        } else if (kth == KEY_EMPTY) {
-            t = __int_as_float(0xff800000);  // fewer than k finite samples: keep everything
-        } else {
-            const float tau = -orderable_f32(static_cast<uint32_t>(kth >> 32));
-            const float ed = __uint_as_float(*max_row_err_bits), eq = q_err[q];
-            const float bound = ed + eq * (1.0f + ed) + BQ_ACCUM_SLACK;   // E
-            t = tau - 2.0f * bound * qn;
+    const unsigned n_items = count(ql);
+#pragma unroll 1
+    for (int pass = 0; pass < BQ_SELECT_PASSES; pass++) {
+        const int shift = 24 - 8 * pass;
+        for (int i = tid; i < QPC * 256; i += THREADS) (&sm.hist[0][0])[i] = 0;
+        __syncthreads();
+        const unsigned want = sm.prefix[ql];
+        for (unsigned base = slot; base < n_items; base += SLOTS * U) {
+            float v[U];
+#pragma unroll
+            for (int j = 0; j < U; j++) {
+                const unsigned i = base + j * SLOTS;
+                v[j] = i < n_items ? load(ql, i) : __int_as_float(0xff800000);
+            }
+#pragma unroll
+            for (int j = 0; j < U; j++) {
+                uint32_t key;
+                if (select_key(v[j], key) && (pass == 0 || (key >> ((shift + 8) & 31)) == want))
+                    atomicAdd(&sm.hist[ql][(key >> shift) & 255u], 1u);
+            }
+        }
+        __syncthreads();
+        if (warp < QPC) {
+            // lane L owns bins 255-8L .. 248-8L (descending value order across lanes)
+            unsigned c[8], mine = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                c[j] = sm.hist[warp][255 - 8 * lane - j];
+                mine += c[j];
+            }
+            unsigned incl = mine;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned v = __shfl_up_sync(FULL_MASK, incl, off);
+                if (lane >= off) incl += v;
+            }
+            const unsigned rem = sm.remaining[warp];
+            const unsigned owners = __ballot_sync(FULL_MASK, incl >= rem);
+            if (owners == 0) {
+                if (lane == 0) sm.short_of_k[warp] = 1;   // only possible in pass 0
+            } else if (lane == __ffs(owners) - 1) {
+                unsigned above = incl - mine;   // values in higher bins
+                int j = 0;
+#pragma unroll
+                for (int t = 0; t < 8; t++)
+                    if (t == j && above + c[t] < rem) {
+                        above += c[t];
+                        j++;
+                    }
+                sm.prefix[warp] = (sm.prefix[warp] << 8) | static_cast<unsigned>(255 - 8 * lane - j);
+                sm.remaining[warp] = rem - above;
+            }
+        }
+        __syncthreads();
+    }
+    if (sm.short_of_k[ql_out]) return __int_as_float(0xff800000);
+    return orderable_f32(sm.prefix[ql_out] << (32 - 8 * BQ_SELECT_PASSES));
+}
+
+// pass A -> thresholds: tau = k-th largest sampled group maximum of u; thr = tau - 2E||q||
+constexpr int BQ_THR_QPC = 4;
+constexpr int BQ_THR_THREADS = 1024;
+__global__ void __launch_bounds__(BQ_THR_THREADS) batch_threshold_kernel(const float *__restrict__ scores,
+                                                                         long long groups,
+                                                                         const float *__restrict__ q_norm,
+                                                                         const float *__restrict__ q_err,
+                                                                         const unsigned int *__restrict__ max_row_err_bits,
+                                                                         int nq, int k, float *__restrict__ thr,
+                                                                         float *__restrict__ margin,
+                                                                         int *__restrict__ flags) {
+    __shared__ SelectSmem<BQ_THR_QPC> sm;
+    const int q0 = blockIdx.x * BQ_THR_QPC;
+    const int mine = threadIdx.x < BQ_THR_QPC ? threadIdx.x : 0;
+    const float tau = radix_select_kth_largest<BQ_THR_QPC, BQ_THR_THREADS>(
+        sm, k, mine, [&](int ql, unsigned i) { return __ldg(scores + static_cast<long long>(i) * BQ_N + q0 + ql); },
+        [&](int) { return static_cast<unsigned>(groups); });
+    if (threadIdx.x < BQ_THR_QPC) {
+        const int q = q0 + threadIdx.x;
+        float t = __int_as_float(0x7f800000), mg = 0.f;   // padding slots (q >= nq) never produce candidates
+        if (q < nq) {
+            const float qn = q_norm[q];
+            int f = 0;
+            if (!(qn > 0.f) || !isfinite(qn)) {
+                f = BQ_FLAG_BAD_QUERY;
+            } else {
+                const float ed = __uint_as_float(*max_row_err_bits), eq = q_err[q];
+                const float bound = ed + eq * (1.0f + ed) + BQ_ACCUM_SLACK;   // E
+                mg = 2.0f * bound * qn;
+                t = tau - mg;   // tau = -inf (fewer than k samples): keep everything
+            }
+            flags[q] = f;
         }
         thr[q] = t;
-        flags[q] = f;
+        margin[q] = mg;
     }
+}
+
+// ---- second threshold: exact k-th best u over the WHOLE store -------------------------------------
+// Pass B kept every row with u >= tau - 2E||q||, tau being the k-th best u of a SAMPLE.  tau2 = the
+// k-th largest u among those candidates is at least as large, k distinct rows have u >= tau2, and
+// the same argument as for tau (so cos_k >= tau2/||q|| - E, so every true top-k row has
+// u >= tau2 - 2E||q||) lets the re-rank skip every candidate below tau2 - 2E||q||.  That cuts the
+// rows whose float32 originals are gathered from ~n*k/n_sample per query to a few times k, which
+// is what allows pass A to sample sparsely.  The survivors are compacted into a dense list.
+constexpr int BQ_SELECT_THREADS = 256;
+__global__ void __launch_bounds__(BQ_SELECT_THREADS) batch_refine_kernel(const float *__restrict__ cand_u,
+                                                                         const unsigned int *__restrict__ cand_rows,
+                                                                         const unsigned int *__restrict__ cand_count,
+                                                                         int cand_cap, int k, int refine,
+                                                                         const float *__restrict__ margin,
+                                                                         unsigned int *__restrict__ surv_rows,
+                                                                         unsigned int *__restrict__ surv_count) {
+    __shared__ SelectSmem<1> sm;
+    __shared__ unsigned n_surv;
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const unsigned total = cand_count[q];
+    const unsigned count = total > static_cast<unsigned>(cand_cap) ? static_cast<unsigned>(cand_cap) : total;
+    const float *u = cand_u + static_cast<size_t>(q) * cand_cap;
+    if (tid == 0) n_surv = 0;
+    float thr2 = __int_as_float(0xff800000);
+    if (refine) {   // tau2 = -inf (fewer than k candidates): re-rank them all
+        thr2 = radix_select_kth_largest<1, BQ_SELECT_THREADS>(
+                   sm, k, 0, [&](int, unsigned i) { return __ldg(u + i); }, [&](int) { return count; }) -
+               margin[q];
+    } else {
+        __syncthreads();
+    }
+    const unsigned int *rows = cand_rows + static_cast<size_t>(q) * cand_cap;
+    unsigned int *dst = surv_rows + static_cast<size_t>(q) * cand_cap;
+    for (unsigned i = tid; i < count; i += BQ_SELECT_THREADS)
+        if (__ldg(u + i) >= thr2) dst[atomicAdd(&n_surv, 1u)] = rows[i];
+    __syncthreads();
+    if (tid == 0) surv_count[q] = n_surv;
 }
 
 // ---- exact re-rank: K1's arithmetic over each query's candidate rows ------------------------------
 struct RerankArgs {
     const float *rows;            // fp32 store
     const float *queries;         // [nq][1152] fp32
-    const unsigned int *cand_count;
-    const unsigned int *cand_rows;
+    const unsigned int *cand_count;   // pass B's count (overflow check)
+    const unsigned int *surv_rows;    // [nq][cand_cap] candidates that passed the second threshold
+    const unsigned int *surv_count;   // [nq]
     uint64_t *part_keys;          // [nq][BQ_RERANK_PARTS][32*KPL]
     int cand_cap;
     int k;
@@ -734,8 +901,7 @@ __global__ void __launch_bounds__(BQ_SEL_THREADS) batch_rerank_kernel(const Rera
     __shared__ uint64_t scratch[BQ_SEL_WARPS * 32 * KPL];
     const int q = blockIdx.x, part = blockIdx.y, parts = gridDim.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const unsigned total = a.cand_count[q];
-    const unsigned count = total > static_cast<unsigned>(a.cand_cap) ? static_cast<unsigned>(a.cand_cap) : total;
+    const unsigned count = a.surv_count[q];
 
     float4 qv[SCAN_CHUNKS];
     const float4 *q4 = reinterpret_cast<const float4 *>(a.queries + static_cast<size_t>(q) * SCAN_DIM);
@@ -754,17 +920,15 @@ __global__ void __launch_bounds__(BQ_SEL_THREADS) batch_rerank_kernel(const Rera
     WarpTopK<KPL> top;
     top.init(a.k, lane);
     unsigned nan_rows = 0;
-    const unsigned int *list = a.cand_rows + static_cast<size_t>(q) * a.cand_cap;
-    // a warp takes 32 candidates at a time (one coalesced index load) and keeps two rows'
-    // loads in flight: the gather is latency-bound, not bandwidth-bound
-    const unsigned chunk_stride = static_cast<unsigned>(parts * BQ_SEL_WARPS) * 32u;
-    for (unsigned c0 = (part * BQ_SEL_WARPS + warp) * 32u; c0 < count; c0 += chunk_stride) {
-        const unsigned mine = c0 + lane < count ? list[c0 + lane] : 0u;
-        const int m = count - c0 < 32u ? static_cast<int>(count - c0) : 32;
-        for (int e = 0; e < m; e += 2) {
-            const long long pos0 = __shfl_sync(FULL_MASK, mine, e);
-            const bool two = e + 1 < m;
-            const long long pos1 = __shfl_sync(FULL_MASK, mine, two ? e + 1 : e);
+    const unsigned int *list = a.surv_rows + static_cast<size_t>(q) * a.cand_cap;
+    // survivors are few (a few times k): deal them out two at a time over all of the query's warps,
+    // each warp keeping two rows' loads in flight (the gather is latency-bound, not bandwidth-bound)
+    const unsigned pair_stride = static_cast<unsigned>(parts * BQ_SEL_WARPS) * 2u;
+    {
+        for (unsigned j0 = (part * BQ_SEL_WARPS + warp) * 2u; j0 < count; j0 += pair_stride) {
+            const bool two = j0 + 1 < count;
+            const long long pos0 = list[j0];
+            const long long pos1 = list[two ? j0 + 1 : j0];
             const float4 *src0 = reinterpret_cast<const float4 *>(a.rows + pos0 * SCAN_DIM);
             const float4 *src1 = reinterpret_cast<const float4 *>(a.rows + pos1 * SCAN_DIM);
             float4 v0[SCAN_CHUNKS], v1[SCAN_CHUNKS];

@@ -27,7 +27,7 @@ using namespace clipdb;
 
 namespace {
 
-constexpr int ABI_VERSION = 1;
+constexpr int ABI_VERSION = 2;
 constexpr int FUSED_K_MAX = 128;        // largest k served by the register-resident lists
 constexpr int MERGE_SHARD_MAX_KEYS = 16384;
 
@@ -66,14 +66,18 @@ struct clipdb_ctx {
 
     // batched path (K4): bf16 copy of the store + workspaces
     bool batch_enabled = false;
-    Buffer bf16_rows, inv_norm, bad_rows, bq_queries, bq_qnorm, bq_scores, bq_thr, bq_flags, bq_count, bq_cand, bq_parts, bq_qerr, row_err;
+    bool batch_dirty = false;            // rows changed since the bf16 copy was built (rebuilt on next use)
+    unsigned long long batch_bad_rows = 0;  // zero-norm / non-finite rows found when the copy was built
+    Buffer bf16_rows, bad_rows, bq_queries, bq_qnorm, bq_scores, bq_thr, bq_flags, bq_count, bq_cand, bq_parts, bq_qerr, row_err;
+    Buffer bq_cand_u, bq_margin, bq_surv, bq_surv_count;
     CUtensorMap map_rows, map_q, map_qhalf;
-    int64_t bq_sample_groups = 0;       // capacity of bq_scores in groups
     int64_t bq_sample_groups_used = 0;  // groups the last pass A wrote
     int64_t batch_min_nq = 2;       // clipdb_search switches to the batched path from this nq (one batch
                                     // costs about one single-query scan, whatever its size)
     int64_t batch_cand_cap = 32768; // candidate rows kept per query
     int64_t batch_cta_pair = 1;     // 1: cta_group::2 contraction (CTA pairs), 0: single-CTA kernel
+    int64_t batch_sample_stride = 0; // pass A visits every s-th 128-row tile; 0 = auto (tiles/1024 clamped to 1..64)
+    int64_t batch_refine = 1;       // 1: second threshold from the candidates' own scores before the re-rank
 
     // scan-kernel event timing (clipdb_profile)
     bool profiling = false;
@@ -192,7 +196,6 @@ void release_store(clipdb_ctx *c) {
     c->mask_words = 0;
     c->batch_enabled = false;   // the bf16 copy described the old rows
     free_buffer(c->bf16_rows);
-    free_buffer(c->inv_norm);
 }
 
 // copy `m` rows of `dim` floats (host or device) into the store at row `at`
@@ -577,39 +580,47 @@ int encode_bf16_map(clipdb_ctx *c, CUtensorMap *map, void *base, uint64_t rows, 
 
 constexpr int64_t BATCH_MIN_ROWS = 65536;
 
+// Pass A's sampling stride in 128-row tiles.  Auto: about 1000 sampled tiles (4000 group maxima
+// per query) however large the store, never sparser than every 64th tile; a power of two so the
+// CTA-pair kernel (256-row pair tiles) samples the same fraction.
+int batch_sample_stride(const clipdb_ctx *c, int64_t tiles) {
+    int64_t s = c->batch_sample_stride > 0 ? c->batch_sample_stride : tiles / 1024;
+    if (s > BQ_SAMPLE_STRIDE_MAX) s = BQ_SAMPLE_STRIDE_MAX;
+    int p = 1;
+    while (p * 2 <= s) p *= 2;
+    return p;
+}
+
 int batch_build_locked(clipdb_ctx *c) {
     if (!c->rows || c->dim != SCAN_DIM || c->ld != SCAN_DIM)
         return fail(c, CLIPDB_ERR_UNSUPPORTED, "batched path needs a loaded store with dim == %d", SCAN_DIM);
     if (c->n < BATCH_MIN_ROWS)
         return fail(c, CLIPDB_ERR_UNSUPPORTED, "batched path needs at least %lld rows", (long long)BATCH_MIN_ROWS);
     const int64_t tiles = (c->n + BQ_M - 1) / BQ_M;
-    const int64_t eff = (tiles + BQ_SAMPLE_STRIDE - 1) / BQ_SAMPLE_STRIDE;
-    // one maximum per (sampled 128-row tile, epilogue warp); the CTA-pair kernel samples whole
-    // 256-row pair tiles (every 8th), so size for whichever visits more tiles
-    const int64_t eff_pair = ((tiles + 1) / 2 + BQ_SAMPLE_STRIDE / 2 - 1) / (BQ_SAMPLE_STRIDE / 2);
-    c->bq_sample_groups = (eff * 4 > eff_pair * 8 ? eff * 4 : eff_pair * 8);
     // pre-tiled bf16 copy: whole 128-row tiles (the last one zero padded)
     const size_t bf16_bytes = static_cast<size_t>(tiles) * BQ_M * SCAN_DIM * 2;
     RC_TRY(ensure_device(c, c->bf16_rows, bf16_bytes));
     if (c->n % BQ_M)
         CU_TRY(c, cudaMemsetAsync(static_cast<uint8_t *>(c->bf16_rows.p) + static_cast<size_t>(tiles - 1) * BQ_M * SCAN_DIM * 2,
                                   0, static_cast<size_t>(BQ_M) * SCAN_DIM * 2, c->stream));
-    RC_TRY(ensure_device(c, c->inv_norm, static_cast<size_t>(c->n) * sizeof(float)));
     RC_TRY(ensure_device(c, c->bad_rows, sizeof(unsigned long long)));
     RC_TRY(ensure_device(c, c->bq_queries, static_cast<size_t>(BQ_N) * SCAN_DIM * 2));
     RC_TRY(ensure_device(c, c->bq_qnorm, BQ_N * sizeof(float)));
     RC_TRY(ensure_device(c, c->bq_qerr, BQ_N * sizeof(float)));
     RC_TRY(ensure_device(c, c->row_err, sizeof(unsigned int)));
     CU_TRY(c, cudaMemsetAsync(c->row_err.p, 0, sizeof(unsigned int), c->stream));
-    RC_TRY(ensure_device(c, c->bq_scores, static_cast<size_t>(BQ_N) * c->bq_sample_groups * sizeof(float)));
     RC_TRY(ensure_device(c, c->bq_thr, BQ_N * sizeof(float)));
     RC_TRY(ensure_device(c, c->bq_flags, BQ_N * sizeof(int32_t)));
     RC_TRY(ensure_device(c, c->bq_count, BQ_N * sizeof(unsigned int)));
     RC_TRY(ensure_device(c, c->bq_cand, static_cast<size_t>(BQ_N) * c->batch_cand_cap * sizeof(unsigned int)));
+    RC_TRY(ensure_device(c, c->bq_cand_u, static_cast<size_t>(BQ_N) * c->batch_cand_cap * sizeof(float)));
+    RC_TRY(ensure_device(c, c->bq_margin, BQ_N * sizeof(float)));
+    RC_TRY(ensure_device(c, c->bq_surv, static_cast<size_t>(BQ_N) * c->batch_cand_cap * sizeof(unsigned int)));
+    RC_TRY(ensure_device(c, c->bq_surv_count, BQ_N * sizeof(unsigned int)));
     RC_TRY(ensure_device(c, c->bq_parts, static_cast<size_t>(BQ_N) * 8 * 128 * sizeof(uint64_t)));
     CU_TRY(c, cudaMemsetAsync(c->bad_rows.p, 0, sizeof(unsigned long long), c->stream));
     build_bf16_store_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(
-        c->rows, c->n, static_cast<__nv_bfloat16 *>(c->bf16_rows.p), static_cast<float *>(c->inv_norm.p),
+        c->rows, c->n, static_cast<__nv_bfloat16 *>(c->bf16_rows.p),
         static_cast<unsigned long long *>(c->bad_rows.p), static_cast<unsigned int *>(c->row_err.p));
     CU_TRY(c, cudaGetLastError());
     c->launches++;
@@ -621,14 +632,20 @@ int batch_build_locked(clipdb_ctx *c) {
     CU_TRY(c, cudaFuncSetAttribute(batch_gemm_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_BYTES));
     CU_TRY(c, cudaFuncSetAttribute(batch_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BQ_SMEM_BYTES));
     CU_TRY(c, cudaFuncSetAttribute(batch_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BQ_SMEM_BYTES));
+    CU_TRY(c, cudaMemcpyAsync(&c->batch_bad_rows, c->bad_rows.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                              c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     c->batch_enabled = true;
+    c->batch_dirty = false;
     return CLIPDB_OK;
 }
 
+// A mask is honoured by both passes' epilogues; the NaN count reported by the batched path is
+// the store-wide one taken when the bf16 copy was built, so a masked search over a store that
+// holds zero-norm rows goes through the exact scan (which counts admitted NaN rows only).
 bool batch_eligible(const clipdb_ctx *c, int32_t nq, int32_t k, int32_t metric, int32_t use_mask) {
-    return c->batch_enabled && metric == CLIPDB_METRIC_COSINE && !use_mask && k >= 1 && k <= FUSED_K_MAX &&
-           k <= c->n && nq >= 1 && nq <= BQ_N;
+    return c->batch_enabled && metric == CLIPDB_METRIC_COSINE && (!use_mask || (c->mask && c->batch_bad_rows == 0)) &&
+           k >= 1 && k <= FUSED_K_MAX && k <= c->n && nq >= 1 && nq <= BQ_N;
 }
 
 template <int KPL>
@@ -636,20 +653,25 @@ int batch_launch_tail(clipdb_ctx *c, const float *d_queries, int32_t nq, int32_t
                       float *d_out_dist, int32_t *d_out_n, int64_t *d_out_nan, int32_t *d_flags, bool threshold) {
     uint64_t *parts = static_cast<uint64_t *>(c->bq_parts.p);
     if (threshold) {
-        batch_sample_topk_kernel<KPL><<<dim3(nq, BQ_THR_PARTS), BQ_SEL_THREADS, 0, c->stream>>>(
-            static_cast<const float *>(c->bq_scores.p), c->bq_sample_groups_used, k, parts);
+        batch_threshold_kernel<<<BQ_N / BQ_THR_QPC, BQ_THR_THREADS, 0, c->stream>>>(
+            static_cast<const float *>(c->bq_scores.p), c->bq_sample_groups_used,
+            static_cast<const float *>(c->bq_qnorm.p), static_cast<const float *>(c->bq_qerr.p),
+            static_cast<const unsigned int *>(c->row_err.p), nq, k, static_cast<float *>(c->bq_thr.p),
+            static_cast<float *>(c->bq_margin.p), d_flags);
+    } else {
+        batch_refine_kernel<<<nq, BQ_SELECT_THREADS, 0, c->stream>>>(
+            static_cast<const float *>(c->bq_cand_u.p), static_cast<const unsigned int *>(c->bq_cand.p),
+            static_cast<const unsigned int *>(c->bq_count.p), static_cast<int>(c->batch_cand_cap), k,
+            static_cast<int>(c->batch_refine), static_cast<const float *>(c->bq_margin.p),
+            static_cast<unsigned int *>(c->bq_surv.p), static_cast<unsigned int *>(c->bq_surv_count.p));
         CU_TRY(c, cudaGetLastError());
         c->launches++;
-        batch_threshold_finish_kernel<<<BQ_N, 256, 0, c->stream>>>(
-            parts, BQ_THR_PARTS, 32 * KPL, static_cast<const float *>(c->bq_qnorm.p),
-            static_cast<const float *>(c->bq_qerr.p), static_cast<const unsigned int *>(c->row_err.p), nq, k,
-            static_cast<float *>(c->bq_thr.p), d_flags);
-    } else {
         RerankArgs r{};
         r.rows = c->rows;
         r.queries = d_queries;
         r.cand_count = static_cast<const unsigned int *>(c->bq_count.p);
-        r.cand_rows = static_cast<const unsigned int *>(c->bq_cand.p);
+        r.surv_rows = static_cast<const unsigned int *>(c->bq_surv.p);
+        r.surv_count = static_cast<const unsigned int *>(c->bq_surv_count.p);
         r.part_keys = parts;
         r.cand_cap = static_cast<int>(c->batch_cand_cap);
         r.k = k;
@@ -672,14 +694,16 @@ int batch_launch_tail(clipdb_ctx *c, const float *d_queries, int32_t nq, int32_t
     return CLIPDB_OK;
 }
 
-int batch_search_device_locked(clipdb_ctx *c, const float *d_queries, int32_t nq, int32_t k,
+int batch_search_device_locked(clipdb_ctx *c, const float *d_queries, int32_t nq, int32_t k, int32_t use_mask,
                                int64_t *d_out_rowids, float *d_out_dist, int32_t *d_out_n, int64_t *d_out_nan,
                                int32_t *d_flags) {
     if (!d_queries || !d_out_rowids || !d_out_dist || !d_out_n || !d_flags)
         return fail(c, CLIPDB_ERR_INVALID, "search_batch: null pointer");
-    if (!batch_eligible(c, nq, k, CLIPDB_METRIC_COSINE, 0))
+    if (c->batch_enabled && c->batch_dirty) RC_TRY(batch_build_locked(c));   // rows were appended / updated
+    if (!batch_eligible(c, nq, k, CLIPDB_METRIC_COSINE, use_mask))
         return fail(c, CLIPDB_ERR_STATE, "search_batch: batch store not enabled or arguments out of range "
-                                         "(1 <= nq <= 256, 1 <= k <= 128)");
+                                         "(1 <= nq <= 256, 1 <= k <= 128 and <= rows; a mask needs a store without "
+                                         "zero-norm rows)");
     const int kpl = k <= 32 ? 1 : (k <= 64 ? 2 : 4);
     const int tiles = static_cast<int>((c->n + BQ_M - 1) / BQ_M);
     prep_queries_kernel<<<BQ_N, 128, 0, c->stream>>>(d_queries, nq, static_cast<__nv_bfloat16 *>(c->bq_queries.p),
@@ -688,29 +712,29 @@ int batch_search_device_locked(clipdb_ctx *c, const float *d_queries, int32_t nq
     c->launches++;
 
     BatchGemmArgs g{};
-    g.inv_norm = static_cast<const float *>(c->inv_norm.p);
     g.thr = static_cast<const float *>(c->bq_thr.p);
-    g.scores = static_cast<float *>(c->bq_scores.p);
     g.cand_count = static_cast<unsigned int *>(c->bq_count.p);
     g.cand_rows = static_cast<unsigned int *>(c->bq_cand.p);
+    g.cand_u = static_cast<float *>(c->bq_cand_u.p);
+    g.mask = use_mask ? c->mask : nullptr;
     g.n = c->n;
-    g.sample_groups = c->bq_sample_groups;
     g.total_tiles = tiles;
     g.cand_cap = static_cast<int>(c->batch_cand_cap);
 
     // pass A: group maxima over a tile sample -> per-query thresholds
     const bool pair = c->batch_cta_pair != 0 && (c->sm_count % 2 == 0);
     const int pair_grid = c->sm_count & ~1;
+    const int sstride = batch_sample_stride(c, tiles);
+    // one maximum per (sampled 128-row tile, epilogue warp)
+    g.tile_stride = pair ? (sstride >= 2 ? sstride / 2 : 1) : sstride;   // pair kernel: in 256-row pair tiles
+    const int eff = ((pair ? (tiles + 1) / 2 : tiles) + g.tile_stride - 1) / g.tile_stride;
+    g.sample_groups = static_cast<long long>(eff) * (pair ? 8 : 4);
+    RC_TRY(ensure_device(c, c->bq_scores, static_cast<size_t>(BQ_N) * g.sample_groups * sizeof(float)));
+    g.scores = static_cast<float *>(c->bq_scores.p);
     if (pair) {
-        g.tile_stride = BQ_SAMPLE_STRIDE / 2;          // in 256-row pair tiles
-        const int eff = ((tiles + 1) / 2 + g.tile_stride - 1) / g.tile_stride;
-        g.sample_groups = static_cast<long long>(eff) * 8;
         const int grid = 2 * eff < pair_grid ? 2 * eff : pair_grid;
         batch_gemm_pair_kernel<true><<<grid, BQ_THREADS, BP_SMEM_BYTES, c->stream>>>(c->map_rows, c->map_qhalf, g);
     } else {
-        g.tile_stride = BQ_SAMPLE_STRIDE;
-        const int eff = (tiles + BQ_SAMPLE_STRIDE - 1) / BQ_SAMPLE_STRIDE;
-        g.sample_groups = static_cast<long long>(eff) * 4;
         batch_gemm_kernel<true><<<eff < c->sm_count ? eff : c->sm_count, BQ_THREADS, BQ_SMEM_BYTES, c->stream>>>(
             c->map_rows, c->map_q, g);
     }
@@ -792,9 +816,10 @@ void clipdb_destroy(clipdb_ctx *c) {
         release_store(c);
         Buffer *bufs[] = {&c->cand_a, &c->cand_b, &c->nan_ctr, &c->tile_ctr, &c->all_keys_a, &c->all_keys_b,
                           &c->cub_tmp, &c->d_query, &c->d_out_rowids, &c->d_out_dist, &c->d_out_n,
-                          &c->d_out_nan, &c->d_blend_in, &c->d_blend_flags, &c->bf16_rows, &c->inv_norm,
+                          &c->d_out_nan, &c->d_blend_in, &c->d_blend_flags, &c->bf16_rows,
                           &c->bad_rows, &c->bq_queries, &c->bq_qnorm, &c->bq_scores, &c->bq_thr, &c->bq_flags,
-                          &c->bq_count, &c->bq_cand, &c->bq_parts, &c->bq_qerr, &c->row_err};
+                          &c->bq_count, &c->bq_cand, &c->bq_parts, &c->bq_qerr, &c->row_err, &c->bq_cand_u, &c->bq_margin,
+                          &c->bq_surv, &c->bq_surv_count};
         for (Buffer *b : bufs) free_buffer(*b);
         if (c->pinned.p) cudaFreeHost(c->pinned.p);
         if (c->pinned_aux.p) cudaFreeHost(c->pinned_aux.p);
@@ -847,6 +872,8 @@ static int64_t *option_slot(clipdb_ctx *c, const char *name) {
     if (!strcmp(name, "batch_min_nq")) return &c->batch_min_nq;
     if (!strcmp(name, "batch_cand_cap")) return &c->batch_cand_cap;
     if (!strcmp(name, "batch_cta_pair")) return &c->batch_cta_pair;
+    if (!strcmp(name, "batch_sample_stride")) return &c->batch_sample_stride;
+    if (!strcmp(name, "batch_refine")) return &c->batch_refine;
     return nullptr;
 }
 
@@ -918,6 +945,7 @@ int clipdb_append_rows(clipdb_ctx *c, const float *rows, const int64_t *rowids, 
     }
     RC_TRY(copy_rows_in(c, rows, rowids, c->n, m));
     c->n += m;
+    if (m > 0) c->batch_dirty = true;   // the bf16 copy is rebuilt before the next batched search
     if (c->mask) {  // a mask sized for the old row count no longer applies
         cudaFree(c->mask);
         c->mask = nullptr;
@@ -935,6 +963,7 @@ int clipdb_update_row(clipdb_ctx *c, int64_t position, const float *row) {
     CU_TRY(c, cudaMemcpyAsync(c->rows + position * c->ld, row, c->dim * sizeof(float), cudaMemcpyDefault,
                               c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
+    c->batch_dirty = true;
     return CLIPDB_OK;
 }
 
@@ -1099,6 +1128,7 @@ int clipdb_search(clipdb_ctx *c, const float *queries, int32_t nq, int32_t k, in
     float *o_dist = static_cast<float *>(c->d_out_dist.p);
     int32_t *o_n = static_cast<int32_t *>(c->d_out_n.p);
     int64_t *o_nan = static_cast<int64_t *>(c->d_out_nan.p);
+    if (nq >= c->batch_min_nq && c->batch_enabled && c->batch_dirty) RC_TRY(batch_build_locked(c));
     if (nq >= c->batch_min_nq && batch_eligible(c, nq < BQ_N ? nq : BQ_N, k, metric, use_mask)) {
         // batched path: tensor-core pre-selection + exact re-rank, 256 queries per pass; queries
         // it flags (candidate overflow, zero norm) are re-run through the exact scan
@@ -1106,7 +1136,7 @@ int clipdb_search(clipdb_ctx *c, const float *queries, int32_t nq, int32_t k, in
         int32_t *d_flags = static_cast<int32_t *>(c->bq_flags.p);
         for (int32_t q0 = 0; q0 < nq; q0 += BQ_N) {
             const int32_t m = nq - q0 < BQ_N ? nq - q0 : BQ_N;
-            RC_TRY(batch_search_device_locked(c, dq + static_cast<size_t>(q0) * c->dim, m, k, o_ids + q0 * kcols,
+            RC_TRY(batch_search_device_locked(c, dq + static_cast<size_t>(q0) * c->dim, m, k, use_mask, o_ids + q0 * kcols,
                                               o_dist + q0 * kcols, o_n + q0, o_nan + q0, d_flags + q0));
         }
         std::vector<int32_t> flags(static_cast<size_t>(nq));
@@ -1177,20 +1207,37 @@ int clipdb_enable_batch(clipdb_ctx *c, int32_t enable) {
     if (!enable) {
         CU_TRY(c, cudaStreamSynchronize(c->stream));
         c->batch_enabled = false;
-        Buffer *bufs[] = {&c->bf16_rows, &c->inv_norm, &c->bq_scores, &c->bq_cand};
+        Buffer *bufs[] = {&c->bf16_rows, &c->bq_scores, &c->bq_cand, &c->bq_cand_u, &c->bq_surv};
         for (Buffer *b : bufs) free_buffer(*b);
         return CLIPDB_OK;
     }
     return batch_build_locked(c);
 }
 
-int clipdb_search_batch_device(clipdb_ctx *c, const float *d_queries, int32_t nq, int32_t k,
+int clipdb_search_batch_device(clipdb_ctx *c, const float *d_queries, int32_t nq, int32_t k, int32_t use_mask,
                                int64_t *d_out_rowids, float *d_out_dist, int32_t *d_out_n,
                                int64_t *d_out_nan, int32_t *d_flags) {
     if (!c) return CLIPDB_ERR_INVALID;
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
-    return batch_search_device_locked(c, d_queries, nq, k, d_out_rowids, d_out_dist, d_out_n, d_out_nan, d_flags);
+    if (use_mask && !c->mask) return fail(c, CLIPDB_ERR_STATE, "search_batch: use_mask set but no mask installed");
+    return batch_search_device_locked(c, d_queries, nq, k, use_mask, d_out_rowids, d_out_dist, d_out_n, d_out_nan,
+                                      d_flags);
+}
+
+int clipdb_batch_stats(clipdb_ctx *c, uint32_t *cand_counts, uint32_t *surv_counts) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->batch_enabled || !c->bq_count.p || !c->bq_surv_count.p)
+        return fail(c, CLIPDB_ERR_STATE, "batch_stats: batch store not enabled");
+    DeviceGuard g(c->device);
+    if (cand_counts)
+        CU_TRY(c, cudaMemcpyAsync(cand_counts, c->bq_count.p, BQ_N * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (surv_counts)
+        CU_TRY(c, cudaMemcpyAsync(surv_counts, c->bq_surv_count.p, BQ_N * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                  c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return CLIPDB_OK;
 }
 
 int clipdb_merge_batch_device(clipdb_ctx *c, const void *d_dist, int64_t dist_stride, int64_t dist_qstride,

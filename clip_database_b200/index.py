@@ -297,6 +297,15 @@ class GpuIndex:
         self._check(self._L.clipdb_enable_batch(self._ctx, int(bool(enable))))
         self.batch_enabled = bool(enable)
 
+    def batch_stats(self) -> Tuple[np.ndarray, np.ndarray]:
+        """(candidates kept by the tensor-core filter, candidates re-ranked in float32) per query
+        slot of the last batched pass (uint32 [256] each)."""
+        cand = np.zeros(256, dtype=np.uint32)
+        surv = np.zeros(256, dtype=np.uint32)
+        self._check(self._L.clipdb_batch_stats(self._ctx, ctypes.c_void_p(cand.ctypes.data),
+                                               ctypes.c_void_p(surv.ctypes.data)))
+        return cand, surv
+
     def search_ptrs(self, q_ptr: int, nq: int, k: int, p_rowids: int, p_dist: int, p_n: int, p_nan: int,
                     metric="cosine", use_mask: bool = False) -> None:
         """Async exact search on raw device addresses (outputs nq x k row-major)."""
@@ -305,10 +314,11 @@ class GpuIndex:
             ctypes.c_void_p(p_rowids), ctypes.c_void_p(p_dist), ctypes.c_void_p(p_n), ctypes.c_void_p(p_nan)))
 
     def search_batch_ptrs(self, q_ptr: int, nq: int, k: int, p_rowids: int, p_dist: int, p_n: int, p_nan: int,
-                          p_flags: int) -> None:
+                          p_flags: int, use_mask: bool = False) -> None:
         """Async batched (tensor-core) search on raw device addresses, nq <= 256."""
         self._check(self._L.clipdb_search_batch_device(
-            self._ctx, ctypes.c_void_p(q_ptr), nq, int(k), ctypes.c_void_p(p_rowids), ctypes.c_void_p(p_dist),
+            self._ctx, ctypes.c_void_p(q_ptr), nq, int(k), int(bool(use_mask)), ctypes.c_void_p(p_rowids),
+            ctypes.c_void_p(p_dist),
             ctypes.c_void_p(p_n), ctypes.c_void_p(p_nan), ctypes.c_void_p(p_flags)))
 
     def merge_batch_records_device(self, records, nq: int, k: int, off_rowids: int, off_dist: int, off_count: int,
@@ -323,12 +333,14 @@ class GpuIndex:
             ctypes.c_void_p(out_dist.data_ptr()), ctypes.c_void_p(out_rowids.data_ptr()),
             ctypes.c_void_p(out_n.data_ptr())))
 
-    def search_batch_device(self, d_queries, k: int, out_rowids, out_dist, out_n, out_nan, flags) -> None:
+    def search_batch_device(self, d_queries, k: int, out_rowids, out_dist, out_n, out_nan, flags,
+                            use_mask: bool = False) -> None:
         """Async batched search (<= 256 queries): torch CUDA tensors; ``flags[q] != 0`` marks
         queries that must be re-run with ``search_device`` (see clipdb.h)."""
         nq = d_queries.shape[0]
         self._check(self._L.clipdb_search_batch_device(
-            self._ctx, ctypes.c_void_p(d_queries.data_ptr()), nq, int(k), ctypes.c_void_p(out_rowids.data_ptr()),
+            self._ctx, ctypes.c_void_p(d_queries.data_ptr()), nq, int(k), int(bool(use_mask)),
+            ctypes.c_void_p(out_rowids.data_ptr()),
             ctypes.c_void_p(out_dist.data_ptr()), ctypes.c_void_p(out_n.data_ptr()),
             ctypes.c_void_p(out_nan.data_ptr() if out_nan is not None else 0), ctypes.c_void_p(flags.data_ptr())))
 

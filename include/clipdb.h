@@ -168,7 +168,9 @@ int clipdb_blend_search(clipdb_ctx *ctx, const float *e1, const float *e2, doubl
  * store (2 bytes per element next to the 4-byte one) so that batches of queries
  * can be pre-selected by one tcgen05 tensor-core contraction and re-ranked with
  * the exact single-query arithmetic; results are identical to clipdb_search.
- * Requirements: dim == 1152, cosine, no mask, 1 <= k <= 128, >= 65536 rows.
+ * Requirements: dim == 1152, cosine, 1 <= k <= 128, >= 65536 rows; with a mask
+ * (clipdb_set_mask) additionally a store without zero-norm rows.  Rows appended or updated
+ * after clipdb_enable_batch are picked up: the bf16 copy is rebuilt before the next batched search.
  * With the batch store enabled, clipdb_search uses this path by itself for
  * nq >= 2 (option "batch_min_nq") and transparently re-runs flagged queries
  * through the exact scan.
@@ -180,9 +182,14 @@ int clipdb_blend_search(clipdb_ctx *ctx, const float *e1, const float *e2, doubl
 #define CLIPDB_BATCH_OVERFLOW   1
 #define CLIPDB_BATCH_BAD_QUERY  2
 int clipdb_enable_batch(clipdb_ctx *ctx, int32_t enable);
-int clipdb_search_batch_device(clipdb_ctx *ctx, const float *d_queries, int32_t nq, int32_t k,
+int clipdb_search_batch_device(clipdb_ctx *ctx, const float *d_queries, int32_t nq, int32_t k, int32_t use_mask,
                                int64_t *d_out_rowids, float *d_out_dist, int32_t *d_out_n,
                                int64_t *d_out_nan, int32_t *d_flags);
+
+/* Measurement: per query slot (256 entries each, host pointers, nullable) of the LAST batched
+ * pass — rows the tensor-core filter kept, and rows that also passed the second threshold and
+ * were re-ranked in float32.  Synchronises the stream. */
+int clipdb_batch_stats(clipdb_ctx *ctx, uint32_t *cand_counts, uint32_t *surv_counts);
 
 /* ---- shard merge (multi-GPU) --------------------------------
  * Merges `lists` per-shard result lists (each k entries, already sorted, shard

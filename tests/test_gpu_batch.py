@@ -68,6 +68,79 @@ def test_batched_clustered_queries(store):
     assert np.array_equal(got.rowids[:, 0], picks + 1)
 
 
+@pytest.mark.parametrize("stride,refine", [(1, 1), (4, 0), (16, 1), (64, 1), (64, 0)])
+def test_sampling_stride_and_refinement_do_not_change_results(store, stride, refine):
+    """Pass A's sampling density and the second (candidate-derived) threshold only change how
+    many rows are re-ranked, never the answer."""
+    rows, exact, batched = store
+    queries = synth.unit_rows(96, DIM, 77)
+    batched.set_option("batch_sample_stride", stride)
+    batched.set_option("batch_refine", refine)
+    try:
+        same(batched.search(queries, 100), exact.search(queries, 100))
+        same(batched.search(queries[:40], 7), exact.search(queries[:40], 7))
+    finally:
+        batched.set_option("batch_sample_stride", 0)
+        batched.set_option("batch_refine", 1)
+
+
+def test_batched_with_folder_mask():
+    """The folder pre-filter bitset (idb:1509-1530) is honoured by the tensor-core path."""
+    from clip_database_b200 import GpuIndex
+    rows = synth.unit_rows(80_000, DIM, 21)
+    rng = np.random.default_rng(5)
+    admitted = rng.random(rows.shape[0]) < 0.3
+    admitted[:100] = False
+    queries = synth.unit_rows(64, DIM, 22)
+    queries[3] = rows[50]            # best match is masked out
+    queries[4] = rows[np.flatnonzero(admitted)[10]]
+    with GpuIndex(0) as exact, GpuIndex(0) as batched:
+        exact.load(rows)
+        batched.load(rows)
+        exact.set_mask(admitted)
+        batched.set_mask(admitted)
+        batched.enable_batch()
+        before = batched.launch_count
+        got = batched.search(queries, 50, use_mask=True)
+        assert batched.launch_count - before <= 16, "batched path was not taken"
+        same(got, exact.search(queries, 50, use_mask=True))
+        assert admitted[got.rowids].all()
+        # a mask admitting fewer rows than k: every admitted row comes back
+        few = np.zeros(rows.shape[0], dtype=bool)
+        few[[7, 70_000, 123]] = True
+        exact.set_mask(few)
+        batched.set_mask(few)
+        got = batched.search(queries[:8], 20, use_mask=True)
+        same(got, exact.search(queries[:8], 20, use_mask=True))
+        assert np.all(got.counts == 3)
+
+
+def test_batched_sees_appended_and_updated_rows():
+    """append_rows / update_row after enable_batch: the bf16 copy is rebuilt before the next
+    batched search (the scanner INSERTs and UPDATEs in place, idb:1165-1175)."""
+    from clip_database_b200 import GpuIndex
+    rows = synth.unit_rows(70_000, DIM, 31)
+    extra = synth.unit_rows(300, DIM, 32)
+    queries = synth.unit_rows(16, DIM, 33)
+    queries[0] = extra[17]
+    queries[1] = extra[200]
+    with GpuIndex(0) as exact, GpuIndex(0) as batched:
+        exact.load(rows)
+        batched.load(rows)
+        batched.enable_batch()
+        same(batched.search(queries, 10), exact.search(queries, 10))
+        exact.append(extra)
+        batched.append(extra)
+        got = batched.search(queries, 10)
+        same(got, exact.search(queries, 10))
+        assert got.rowids[0, 0] == 70_000 + 17
+        exact.update_row(123, extra[200])
+        batched.update_row(123, extra[200])
+        got = batched.search(queries, 10)
+        same(got, exact.search(queries, 10))
+        assert got.rowids[1, 0] == 123 and got.rowids[1, 1] == 70_000 + 200
+
+
 def test_batched_zero_query_falls_back(store):
     rows, exact, batched = store
     queries = synth.unit_rows(32, DIM, 5)
