@@ -205,6 +205,20 @@ class GpuIndex:
         words.view(np.uint8)[: packed.shape[0]] = packed
         self._check(self._L.clipdb_set_mask(self._ctx, ctypes.c_void_p(words.ctypes.data), words.shape[0]))
 
+    def set_mask_words(self, words) -> None:
+        """The bitset itself: ``ceil(num_rows / 32)`` 32-bit words (bit ``r & 31`` of word ``r >> 5``
+        = row r admitted) as a numpy array or a torch tensor on any device; copied."""
+        need = (self.num_rows + 31) // 32
+        if _is_torch(words):
+            if words.element_size() != 4 or not words.is_contiguous() or words.numel() < need:
+                raise ValueError("mask words must be a contiguous 32-bit tensor with one bit per row")
+            self._check(self._L.clipdb_set_mask(self._ctx, ctypes.c_void_p(words.data_ptr()), words.numel()))
+            return
+        w = np.ascontiguousarray(words, dtype=np.uint32)
+        if w.shape[0] < need:
+            raise ValueError("mask words must hold one bit per row")
+        self._check(self._L.clipdb_set_mask(self._ctx, ctypes.c_void_p(w.ctypes.data), w.shape[0]))
+
     def clear_mask(self) -> None:
         self._check(self._L.clipdb_clear_mask(self._ctx))
 
