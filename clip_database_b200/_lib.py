@@ -16,6 +16,8 @@ OK = 0
 ERR_NAMES = {1: "INVALID", 2: "CUDA", 3: "NOMEM", 4: "STATE", 5: "UNSUPPORTED"}
 METRIC_COSINE = 0
 METRIC_L2 = 1
+SCORE_REFERENCE_UINT8 = 0   # popcount(q AND row) modulo 256, as numpy's uint8 dot product gives
+SCORE_POPCOUNT = 1
 BLEND_POSITIVE_ZERO_NORM = 1
 BLEND_NEGATIVE_ZERO_NORM = 2
 ABI_VERSION = 2
@@ -59,6 +61,13 @@ SIGNATURES = [
     ("clipdb_search_batch_device", c_int, [_CTX, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_void_p]),
     ("clipdb_batch_stats", c_int, [_CTX, c_void_p, c_void_p]),
+    ("clipdb_load_codes", c_int, [_CTX, c_void_p, c_void_p, c_int64, c_int32]),
+    ("clipdb_num_codes", c_int64, [_CTX]),
+    ("clipdb_set_code_mask", c_int, [_CTX, c_void_p, c_int64, c_void_p]),
+    ("clipdb_clear_code_mask", c_int, [_CTX]),
+    ("clipdb_binary_search", c_int, [_CTX, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    ("clipdb_binary_search_device", c_int, [_CTX, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                            c_void_p]),
     ("clipdb_merge_device", c_int, [_CTX, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                     c_void_p, c_void_p, c_void_p]),
     ("clipdb_merge_strided_device", c_int, [_CTX, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,

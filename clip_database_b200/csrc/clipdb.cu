@@ -19,6 +19,7 @@
 
 #include "../../include/clipdb.h"
 #include "batch.cuh"
+#include "binary.cuh"
 #include "blend.cuh"
 #include "merge.cuh"
 #include "scan_topk.cuh"
@@ -56,6 +57,16 @@ struct clipdb_ctx {
     int64_t rowid_base = 0;
     uint32_t *mask = nullptr;
     int64_t mask_words = 0;
+
+    // sign-code store (binary fallback search, image_database.py:1591-1629)
+    uint32_t *codes = nullptr;       // [n_codes][36] bit-packed
+    int64_t *code_ids = nullptr;     // nullable: id returned for a row (else its scan position)
+    int64_t n_codes = 0;
+    uint32_t *code_mask = nullptr;
+    int64_t code_mask_words = 0;
+    uint32_t *code_seq = nullptr;        // tie-break sequence installed with the mask (nullable)
+    int64_t *code_ids_by_seq = nullptr;  // ids indexed by that sequence
+    Buffer d_code_query, code_stage, code_bad;
 
     // workspaces (grown on demand)
     Buffer cand_a, cand_b, nan_ctr, tile_ctr, all_keys_a, all_keys_b, cub_tmp;
@@ -196,6 +207,21 @@ void release_store(clipdb_ctx *c) {
     c->mask_words = 0;
     c->batch_enabled = false;   // the bf16 copy described the old rows
     free_buffer(c->bf16_rows);
+}
+
+void release_codes(clipdb_ctx *c) {
+    if (c->codes) cudaFree(c->codes);
+    if (c->code_ids) cudaFree(c->code_ids);
+    if (c->code_mask) cudaFree(c->code_mask);
+    if (c->code_seq) cudaFree(c->code_seq);
+    if (c->code_ids_by_seq) cudaFree(c->code_ids_by_seq);
+    c->codes = nullptr;
+    c->code_ids = nullptr;
+    c->code_mask = nullptr;
+    c->code_seq = nullptr;
+    c->code_ids_by_seq = nullptr;
+    c->n_codes = 0;
+    c->code_mask_words = 0;
 }
 
 // copy `m` rows of `dim` floats (host or device) into the store at row `at`
@@ -349,6 +375,50 @@ int scan_grid(const clipdb_ctx *c, bool tma) {
     return tma ? c->sm_count : c->sm_count * static_cast<int>(c->ldg_ctas_per_sm);
 }
 
+// merge tree over the per-CTA candidate lists in cand_a: lists -> ceil(lists / per_cta) -> ... -> 1 (decoded)
+int merge_cta_lists(clipdb_ctx *c, int grid, int stride, const DecodeArgs &dec) {
+    const int per_cta = MERGE_KEYS / stride;
+    int lists = grid;
+    const uint64_t *in = static_cast<const uint64_t *>(c->cand_a.p);
+    RC_TRY(ensure_device(c, c->cand_b,
+                         static_cast<size_t>((grid + per_cta - 1) / per_cta) * stride * sizeof(uint64_t) * 2));
+    uint64_t *ping = static_cast<uint64_t *>(c->cand_b.p);
+    uint64_t *pong = ping + static_cast<size_t>((grid + per_cta - 1) / per_cta) * stride;
+    for (;;) {
+        const int ctas = (lists + per_cta - 1) / per_cta;
+        const int last = ctas == 1;
+        reduce_lists_kernel<<<ctas, MERGE_THREADS, 0, c->stream>>>(in, lists, stride, per_cta, ping, dec, last);
+        CU_TRY(c, cudaGetLastError());
+        c->launches++;
+        if (last) break;
+        in = ping;
+        lists = ctas;
+        uint64_t *t = ping;
+        ping = pong;
+        pong = t;
+    }
+    return CLIPDB_OK;
+}
+
+// general k: all_keys_a holds one key per row; radix sort, decode the first kk
+int sort_all_keys_and_decode(clipdb_ctx *c, int64_t n, int64_t kk, const DecodeArgs &dec) {
+    uint64_t *keys = static_cast<uint64_t *>(c->all_keys_a.p);
+    size_t tmp_bytes = 0;
+    CU_TRY(c, cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys, static_cast<uint64_t *>(c->all_keys_b.p), n, 0,
+                                             64, c->stream));
+    RC_TRY(ensure_device(c, c->cub_tmp, tmp_bytes));
+    CU_TRY(c, cub::DeviceRadixSort::SortKeys(c->cub_tmp.p, tmp_bytes, keys, static_cast<uint64_t *>(c->all_keys_b.p), n,
+                                             0, 64, c->stream));
+    c->launches++;  // counted once; CUB's passes are library kernels, not ours
+    CU_TRY(c, cudaMemsetAsync(dec.out_n, 0, sizeof(int32_t), c->stream));
+    const int threads = 256;
+    const int blocks = static_cast<int>((kk + threads - 1) / threads);
+    decode_sorted_kernel<<<blocks, threads, 0, c->stream>>>(static_cast<const uint64_t *>(c->all_keys_b.p), n, dec);
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    return CLIPDB_OK;
+}
+
 // one query: scan + merge tree (k <= FUSED_K_MAX) or scan + radix sort (any k)
 int search_one(clipdb_ctx *c, const float *d_query, int k, int metric, bool use_mask,
                int64_t *d_out_rowids, float *d_out_dist, int32_t *d_out_n, int64_t *d_out_nan,
@@ -402,30 +472,7 @@ int search_one(clipdb_ctx *c, const float *d_query, int k, int metric, bool use_
             case 2: RC_TRY((launch_scan_metric<2, false>(c, a, metric, tma, grid))); break;
             default: RC_TRY((launch_scan_metric<4, false>(c, a, metric, tma, grid))); break;
         }
-        // merge tree: lists -> ceil(lists / per_cta) -> ... -> 1 (decoded)
-        const int per_cta = MERGE_KEYS / stride;
-        int lists = grid;
-        const uint64_t *in = static_cast<const uint64_t *>(c->cand_a.p);
-        RC_TRY(ensure_device(c, c->cand_b,
-                             static_cast<size_t>((grid + per_cta - 1) / per_cta) * stride *
-                                 sizeof(uint64_t) * 2));
-        uint64_t *ping = static_cast<uint64_t *>(c->cand_b.p);
-        uint64_t *pong = ping + static_cast<size_t>((grid + per_cta - 1) / per_cta) * stride;
-        for (;;) {
-            const int ctas = (lists + per_cta - 1) / per_cta;
-            const int last = ctas == 1;
-            reduce_lists_kernel<<<ctas, MERGE_THREADS, 0, c->stream>>>(in, lists, stride, per_cta,
-                                                                       ping, dec, last);
-            CU_TRY(c, cudaGetLastError());
-            c->launches++;
-            if (last) break;
-            in = ping;
-            lists = ctas;
-            uint64_t *t = ping;
-            ping = pong;
-            pong = t;
-        }
-        return CLIPDB_OK;
+        return merge_cta_lists(c, grid, stride, dec);
     }
 
     // general k: every key to HBM (8 B/row next to the 4*dim B/row just read), radix sort, decode
@@ -436,23 +483,7 @@ int search_one(clipdb_ctx *c, const float *d_query, int k, int metric, bool use_
     a.cand_stride = 32;
     a.k = 0;
     RC_TRY((launch_scan_metric<1, true>(c, a, metric, tma, grid)));
-    size_t tmp_bytes = 0;
-    CU_TRY(c, cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, a.all_keys,
-                                             static_cast<uint64_t *>(c->all_keys_b.p), c->n, 0, 64,
-                                             c->stream));
-    RC_TRY(ensure_device(c, c->cub_tmp, tmp_bytes));
-    CU_TRY(c, cub::DeviceRadixSort::SortKeys(c->cub_tmp.p, tmp_bytes, a.all_keys,
-                                             static_cast<uint64_t *>(c->all_keys_b.p), c->n, 0, 64,
-                                             c->stream));
-    c->launches++;  // counted once; CUB's passes are library kernels, not ours
-    CU_TRY(c, cudaMemsetAsync(d_out_n, 0, sizeof(int32_t), c->stream));
-    const int threads = 256;
-    const int blocks = static_cast<int>((kk + threads - 1) / threads);
-    decode_sorted_kernel<<<blocks, threads, 0, c->stream>>>(
-        static_cast<const uint64_t *>(c->all_keys_b.p), c->n, dec);
-    CU_TRY(c, cudaGetLastError());
-    c->launches++;
-    return CLIPDB_OK;
+    return sort_all_keys_and_decode(c, c->n, kk, dec);
 }
 
 int search_device_locked(clipdb_ctx *c, const float *d_queries, int32_t nq, int32_t k,
@@ -769,6 +800,84 @@ int batch_search_device_locked(clipdb_ctx *c, const float *d_queries, int32_t nq
     }
 }
 
+// ---- sign-code search (binary.cuh) -----------------------------------------------------
+
+template <int KPL, bool ALL>
+int launch_binary_scan(clipdb_ctx *c, const BinaryArgs &a, int grid) {
+    auto kern = binary_scan_kernel<KPL, ALL>;
+    static thread_local int configured_device = -1;
+    if (configured_device != c->device) {
+        CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_SMEM_BYTES));
+        configured_device = c->device;
+    }
+    RC_TRY(profile_mark(c, true));
+    kern<<<grid, BIN_THREADS, BIN_SMEM_BYTES, c->stream>>>(a);
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    return profile_mark(c, false);
+}
+
+int binary_search_device_locked(clipdb_ctx *c, const uint32_t *d_query_words, int32_t k, int32_t score_mode,
+                                int32_t use_mask, int64_t *d_out_ids, int32_t *d_out_scores, int32_t *d_out_n) {
+    if (!c->codes || c->n_codes == 0) return fail(c, CLIPDB_ERR_STATE, "binary_search: no codes loaded");
+    if (!d_query_words || !d_out_n || (k > 0 && (!d_out_ids || !d_out_scores)))
+        return fail(c, CLIPDB_ERR_INVALID, "binary_search: null pointer");
+    if (score_mode != CLIPDB_SCORE_REFERENCE_UINT8 && score_mode != CLIPDB_SCORE_POPCOUNT)
+        return fail(c, CLIPDB_ERR_INVALID, "binary_search: unknown score mode %d", score_mode);
+    if (use_mask && !c->code_mask) return fail(c, CLIPDB_ERR_STATE, "binary_search: use_mask set but no code mask installed");
+    if (c->n_codes >= (1ll << 32)) return fail(c, CLIPDB_ERR_UNSUPPORTED, "more than 2^32-1 codes per context");
+    const int64_t kk = k < c->n_codes ? k : c->n_codes;
+    if (kk <= 0) {
+        CU_TRY(c, cudaMemsetAsync(d_out_n, 0, sizeof(int32_t), c->stream));
+        return CLIPDB_OK;
+    }
+    const int grid = c->scan_ctas > 0 ? static_cast<int>(c->scan_ctas) : c->sm_count;
+    RC_TRY(ensure_device(c, c->tile_ctr, sizeof(unsigned int)));
+    CU_TRY(c, cudaMemsetAsync(c->tile_ctr.p, 0, sizeof(unsigned int), c->stream));
+
+    BinaryArgs a{};
+    a.codes = c->codes;
+    a.query = d_query_words;
+    a.mask = use_mask ? c->code_mask : nullptr;
+    a.seq = use_mask ? c->code_seq : nullptr;
+    a.tile_counter = static_cast<unsigned int *>(c->tile_ctr.p);
+    a.n = c->n_codes;
+    a.k = static_cast<int>(kk);
+    a.chunk_tiles = static_cast<int>(c->scan_chunk);
+    a.score_mask = score_mode == CLIPDB_SCORE_REFERENCE_UINT8 ? 0xFFu : 0xFFFFu;
+    a.score_max = score_mode == CLIPDB_SCORE_REFERENCE_UINT8 ? 255u : static_cast<uint32_t>(SCAN_DIM);
+
+    DecodeArgs dec{};
+    dec.rowids = a.seq ? c->code_ids_by_seq : c->code_ids;
+    dec.rowid_base = 0;
+    dec.out_rowids = d_out_ids;
+    dec.out_dist = reinterpret_cast<float *>(d_out_scores);   // int32 scores (score_max > 0)
+    dec.out_n = d_out_n;
+    dec.k = static_cast<int>(kk);
+    dec.score_max = static_cast<int>(a.score_max);
+
+    if (kk <= FUSED_K_MAX) {
+        const int kpl = kk <= 32 ? 1 : (kk <= 64 ? 2 : 4);
+        a.cand_stride = 32 * kpl;
+        RC_TRY(ensure_device(c, c->cand_a, static_cast<size_t>(grid) * a.cand_stride * sizeof(uint64_t)));
+        a.cand = static_cast<uint64_t *>(c->cand_a.p);
+        switch (kpl) {
+            case 1: RC_TRY((launch_binary_scan<1, false>(c, a, grid))); break;
+            case 2: RC_TRY((launch_binary_scan<2, false>(c, a, grid))); break;
+            default: RC_TRY((launch_binary_scan<4, false>(c, a, grid))); break;
+        }
+        return merge_cta_lists(c, grid, a.cand_stride, dec);
+    }
+    const size_t key_bytes = static_cast<size_t>(c->n_codes) * sizeof(uint64_t);
+    RC_TRY(ensure_device(c, c->all_keys_a, key_bytes));
+    RC_TRY(ensure_device(c, c->all_keys_b, key_bytes));
+    a.all_keys = static_cast<uint64_t *>(c->all_keys_a.p);
+    a.cand_stride = 32;
+    a.k = 0;
+    RC_TRY((launch_binary_scan<1, true>(c, a, grid)));
+    return sort_all_keys_and_decode(c, c->n_codes, kk, dec);
+}
+
 }  // namespace
 
 // ================================ C ABI ==========================================
@@ -814,7 +923,8 @@ void clipdb_destroy(clipdb_ctx *c) {
         DeviceGuard g(c->device);
         cudaStreamSynchronize(c->stream);
         release_store(c);
-        Buffer *bufs[] = {&c->cand_a, &c->cand_b, &c->nan_ctr, &c->tile_ctr, &c->all_keys_a, &c->all_keys_b,
+        release_codes(c);
+        Buffer *bufs[] = {&c->d_code_query, &c->code_stage, &c->code_bad, &c->cand_a, &c->cand_b, &c->nan_ctr, &c->tile_ctr, &c->all_keys_a, &c->all_keys_b,
                           &c->cub_tmp, &c->d_query, &c->d_out_rowids, &c->d_out_dist, &c->d_out_n,
                           &c->d_out_nan, &c->d_blend_in, &c->d_blend_flags, &c->bf16_rows,
                           &c->bad_rows, &c->bq_queries, &c->bq_qnorm, &c->bq_scores, &c->bq_thr, &c->bq_flags,
@@ -1238,6 +1348,149 @@ int clipdb_batch_stats(clipdb_ctx *c, uint32_t *cand_counts, uint32_t *surv_coun
                                   c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     return CLIPDB_OK;
+}
+
+int clipdb_load_codes(clipdb_ctx *c, const uint8_t *codes, const int64_t *ids, int64_t n, int32_t dim) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (n < 0 || (n > 0 && !codes)) return fail(c, CLIPDB_ERR_INVALID, "load_codes: bad argument");
+    if (dim != SCAN_DIM) return fail(c, CLIPDB_ERR_UNSUPPORTED, "load_codes: sign codes are %d elements wide", SCAN_DIM);
+    DeviceGuard g(c->device);
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    release_codes(c);
+    if (n == 0) return CLIPDB_OK;
+    CU_TRY(c, cudaMalloc(reinterpret_cast<void **>(&c->codes), static_cast<size_t>(n) * BIN_ROW_BYTES));
+    if (ids) {
+        CU_TRY(c, cudaMalloc(reinterpret_cast<void **>(&c->code_ids), static_cast<size_t>(n) * sizeof(int64_t)));
+        CU_TRY(c, cudaMemcpyAsync(c->code_ids, ids, static_cast<size_t>(n) * sizeof(int64_t), cudaMemcpyDefault, c->stream));
+    }
+    // bytes -> bits on the device, through a bounded staging buffer
+    const int64_t chunk_rows = 32768;   // 37.7 MB of bytes per chunk
+    RC_TRY(ensure_device(c, c->code_stage, static_cast<size_t>(chunk_rows < n ? chunk_rows : n) * SCAN_DIM));
+    RC_TRY(ensure_device(c, c->code_bad, sizeof(unsigned int)));
+    CU_TRY(c, cudaMemsetAsync(c->code_bad.p, 0, sizeof(unsigned int), c->stream));
+    for (int64_t lo = 0; lo < n; lo += chunk_rows) {
+        const int64_t m = n - lo < chunk_rows ? n - lo : chunk_rows;
+        CU_TRY(c, cudaMemcpyAsync(c->code_stage.p, codes + lo * SCAN_DIM, static_cast<size_t>(m) * SCAN_DIM,
+                                  cudaMemcpyDefault, c->stream));
+        const long long words = m * BIN_WORDS;
+        pack_codes_kernel<<<static_cast<unsigned>((words + 255) / 256), 256, 0, c->stream>>>(
+            static_cast<const uint8_t *>(c->code_stage.p), words, c->codes + lo * BIN_WORDS,
+            static_cast<unsigned int *>(c->code_bad.p));
+        CU_TRY(c, cudaGetLastError());
+        c->launches++;
+        CU_TRY(c, cudaStreamSynchronize(c->stream));   // the staging buffer (and a pageable source) is reused
+    }
+    unsigned int bad = 0;
+    CU_TRY(c, cudaMemcpy(&bad, c->code_bad.p, sizeof bad, cudaMemcpyDeviceToHost));
+    if (bad) {
+        release_codes(c);
+        return fail(c, CLIPDB_ERR_INVALID, "load_codes: %u words hold bytes other than 0/1 (not sign codes)", bad);
+    }
+    c->n_codes = n;
+    return CLIPDB_OK;
+}
+
+int64_t clipdb_num_codes(const clipdb_ctx *c) { return c ? c->n_codes : 0; }
+
+int clipdb_set_code_mask(clipdb_ctx *c, const uint32_t *words, int64_t n_words, const uint32_t *order) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->codes) return fail(c, CLIPDB_ERR_STATE, "set_code_mask: no codes loaded");
+    const int64_t need = (c->n_codes + 31) / 32;
+    if (!words || n_words < need) return fail(c, CLIPDB_ERR_INVALID, "set_code_mask: need %lld words", (long long)need);
+    DeviceGuard g(c->device);
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->code_mask_words < need) {
+        if (c->code_mask) cudaFree(c->code_mask);
+        c->code_mask = nullptr;
+        c->code_mask_words = 0;
+        CU_TRY(c, cudaMalloc(reinterpret_cast<void **>(&c->code_mask), static_cast<size_t>(need) * 4));
+        c->code_mask_words = need;
+    }
+    CU_TRY(c, cudaMemcpyAsync(c->code_mask, words, static_cast<size_t>(need) * 4, cudaMemcpyDefault, c->stream));
+    if (c->code_seq) cudaFree(c->code_seq);
+    if (c->code_ids_by_seq) cudaFree(c->code_ids_by_seq);
+    c->code_seq = nullptr;
+    c->code_ids_by_seq = nullptr;
+    if (order) {
+        const size_t n = static_cast<size_t>(c->n_codes);
+        CU_TRY(c, cudaMalloc(reinterpret_cast<void **>(&c->code_seq), n * sizeof(uint32_t)));
+        CU_TRY(c, cudaMalloc(reinterpret_cast<void **>(&c->code_ids_by_seq), n * sizeof(int64_t)));
+        CU_TRY(c, cudaMemcpyAsync(c->code_seq, order, n * sizeof(uint32_t), cudaMemcpyDefault, c->stream));
+        CU_TRY(c, cudaMemsetAsync(c->code_ids_by_seq, 0xFF, n * sizeof(int64_t), c->stream));
+        RC_TRY(ensure_device(c, c->code_bad, sizeof(unsigned int)));
+        CU_TRY(c, cudaMemsetAsync(c->code_bad.p, 0, sizeof(unsigned int), c->stream));
+        ids_by_sequence_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->stream>>>(
+            c->code_seq, c->code_ids, c->n_codes, c->code_ids_by_seq, static_cast<unsigned int *>(c->code_bad.p));
+        CU_TRY(c, cudaGetLastError());
+        c->launches++;
+        unsigned int bad = 0;
+        CU_TRY(c, cudaMemcpyAsync(&bad, c->code_bad.p, sizeof bad, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        if (bad) {
+            cudaFree(c->code_seq);
+            cudaFree(c->code_ids_by_seq);
+            c->code_seq = nullptr;
+            c->code_ids_by_seq = nullptr;
+            return fail(c, CLIPDB_ERR_INVALID, "set_code_mask: order holds %u values >= the number of codes", bad);
+        }
+    }
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return CLIPDB_OK;
+}
+
+int clipdb_clear_code_mask(clipdb_ctx *c) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->code_mask) cudaFree(c->code_mask);
+    if (c->code_seq) cudaFree(c->code_seq);
+    if (c->code_ids_by_seq) cudaFree(c->code_ids_by_seq);
+    c->code_mask = nullptr;
+    c->code_seq = nullptr;
+    c->code_ids_by_seq = nullptr;
+    c->code_mask_words = 0;
+    return CLIPDB_OK;
+}
+
+int clipdb_binary_search_device(clipdb_ctx *c, const uint32_t *d_query_words, int32_t k, int32_t score_mode,
+                                int32_t use_mask, int64_t *d_out_ids, int32_t *d_out_scores, int32_t *d_out_n) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    return binary_search_device_locked(c, d_query_words, k, score_mode, use_mask, d_out_ids, d_out_scores, d_out_n);
+}
+
+int clipdb_binary_search(clipdb_ctx *c, const uint8_t *query_code, int32_t k, int32_t score_mode, int32_t use_mask,
+                         int64_t *out_ids, int32_t *out_scores, int32_t *out_n) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!query_code || !out_n || (k > 0 && (!out_ids || !out_scores)))
+        return fail(c, CLIPDB_ERR_INVALID, "binary_search: null pointer");
+    DeviceGuard g(c->device);
+    const int64_t kcols = k > 0 ? k : 0;
+    RC_TRY(ensure_pinned(c, BIN_ROW_BYTES));
+    RC_TRY(ensure_device(c, c->d_code_query, BIN_ROW_BYTES));
+    RC_TRY(ensure_result_buffers(c, 1, kcols));
+    uint32_t *hq = static_cast<uint32_t *>(c->pinned.p);
+    for (int w = 0; w < BIN_WORDS; w++) {
+        uint32_t bits = 0;
+        for (int b = 0; b < 32; b++) {
+            const uint8_t v = query_code[w * 32 + b];
+            if (v > 1) return fail(c, CLIPDB_ERR_INVALID, "binary_search: query code bytes must be 0 or 1");
+            bits |= static_cast<uint32_t>(v) << b;
+        }
+        hq[w] = bits;
+    }
+    CU_TRY(c, cudaMemcpyAsync(c->d_code_query.p, hq, BIN_ROW_BYTES, cudaMemcpyHostToDevice, c->stream));
+    RC_TRY(binary_search_device_locked(c, static_cast<const uint32_t *>(c->d_code_query.p), k, score_mode, use_mask,
+                                       static_cast<int64_t *>(c->d_out_rowids.p),
+                                       reinterpret_cast<int32_t *>(c->d_out_dist.p),
+                                       static_cast<int32_t *>(c->d_out_n.p)));
+    CU_TRY(c, cudaMemsetAsync(c->d_out_nan.p, 0, sizeof(int64_t), c->stream));
+    return fetch_results(c, 1, kcols, out_ids, reinterpret_cast<float *>(out_scores), out_n, nullptr);
 }
 
 int clipdb_merge_batch_device(clipdb_ctx *c, const void *d_dist, int64_t dist_stride, int64_t dist_qstride,

@@ -21,11 +21,16 @@ struct DecodeArgs {
     int64_t *out_nan;                    // nullable [1]
     const unsigned long long *nan_rows;  // counter the scan accumulated
     int k;
+    int score_max;                       // > 0: keys carry (score_max - integer score) instead of a float32
+                                         // distance (binary.cuh); out_dist then receives int32 scores
 };
 
 __device__ __forceinline__ void decode_one(const DecodeArgs &d, int i, uint64_t key) {
     const uint32_t pos = static_cast<uint32_t>(key & 0xFFFFFFFFull);
-    d.out_dist[i] = orderable_f32(static_cast<uint32_t>(key >> 32));
+    if (d.score_max > 0)
+        reinterpret_cast<int32_t *>(d.out_dist)[i] = d.score_max - static_cast<int32_t>(key >> 32);
+    else
+        d.out_dist[i] = orderable_f32(static_cast<uint32_t>(key >> 32));
     d.out_rowids[i] = d.rowids ? d.rowids[pos] : d.rowid_base + static_cast<int64_t>(pos);
 }
 
@@ -60,7 +65,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) reduce_lists_kernel(
     }
     if (tid == 0) {
         *dec.out_n = found;
-        if (dec.out_nan) *dec.out_nan = static_cast<int64_t>(*dec.nan_rows);
+        if (dec.out_nan) *dec.out_nan = dec.nan_rows ? static_cast<int64_t>(*dec.nan_rows) : 0;
     }
 }
 
@@ -72,7 +77,7 @@ __global__ void decode_sorted_kernel(const uint64_t *__restrict__ keys, long lon
     if (valid) decode_one(dec, static_cast<int>(i), keys[i]);
     const unsigned votes = __ballot_sync(FULL_MASK, valid);
     if ((threadIdx.x & 31) == 0 && votes) atomicAdd(dec.out_n, __popc(votes));
-    if (i == 0 && dec.out_nan) *dec.out_nan = static_cast<int64_t>(*dec.nan_rows);
+    if (i == 0 && dec.out_nan) *dec.out_nan = dec.nan_rows ? static_cast<int64_t>(*dec.nan_rows) : 0;
 }
 
 // Shard merge (multi-GPU): `lists` sorted result lists of k (distance, rowid)

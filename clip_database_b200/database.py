@@ -97,9 +97,16 @@ class ImageDatabase:
     embedding_dim = schema.EMBEDDING_DIM
 
     def __init__(self, db_path: str, device: int = 0, embedder: Optional[Embedder] = None,
-                 nan_policy: str = "reference", verbose: bool = False):
+                 nan_policy: str = "reference", verbose: bool = False,
+                 binary_score_mode: str = "reference"):
         if nan_policy not in ("reference", "exclude"):
             raise ValueError("nan_policy must be 'reference' or 'exclude'")
+        if binary_score_mode not in ("reference", "popcount"):
+            raise ValueError("binary_score_mode must be 'reference' (uint8 wrap-around, as the reference "
+                             "computes it) or 'popcount'")
+        self.binary_score_mode = binary_score_mode
+        self._codes = None                 # loader.HostCodes once the sign-code fallback is needed
+        self._code_mask_key: Optional[Tuple[str, ...]] = None
         self.db_path = db_path
         self.embedder = embedder
         self.nan_policy = nan_policy
@@ -130,6 +137,8 @@ class ImageDatabase:
         self._rowids = host.rowids
         self._rowid_to_pos = {int(r): i for i, r in enumerate(host.rowids)}
         self._mask_key = None
+        self._codes = None
+        self._code_mask_key = None
         if host.rows.shape[0]:
             self.index.load(host.rows, host.rowids)
         self._log(f"loaded {host.rows.shape[0]} rows ({host.source}); {host.dropped} vec0 rows without "
@@ -243,14 +252,15 @@ class ImageDatabase:
         similarity conversion, duplicate filter (image_database.py:1378-1658)."""
         import time
         timings = {}
-        # guards (:1488-1500, :1532-1555).  The binary (sign-code) fallback used when
-        # vec0 is empty is a different, approximate path and is not provided here.
+        # guards (:1488-1500, :1532-1555)
         if self._binary_count <= 0:
             print("Error: Database has no embeddings. Please run scan first.")
             return []
         if self._vec0_count <= 0:
-            raise NotImplementedError("vec0 is empty: the reference would fall back to its binary "
-                                      "sign-code search (image_database.py:1591-1629), which is out of scope")
+            # vec0 is empty: the sign-code fallback (:1591-1629)
+            results = self._binary_fallback(embedding1, k, embedding2, weights, negative_embeddings,
+                                            negative_weights, filter_folders, timings)
+            return self._finish(results, show_duplicates, profile, timings)
         try:
             k = int(k)
             t0 = time.time()
@@ -272,11 +282,69 @@ class ImageDatabase:
             top = [(self._paths[self._rowid_to_pos[int(r)]], 1.0 - float(d)) for r, d in zip(rowids, dist)]
             timings["db_query"] = time.time() - t0
             results = [(p, float(s)) for p, s in top]
-        except NotImplementedError:
-            raise
         except Exception as e:                       # error envelope, :1637-1640
             print(f"Error during search: {e}")
             return []
+        return self._finish(results, show_duplicates, profile, timings)
+
+    # ---- sign-code fallback (vec0 empty, image_database.py:1591-1629) -------------------------
+    def _filtered_statement_walks_the_path_index(self) -> bool:
+        """Ask THIS SQLite how it would run the fallback's statement with a folder WHERE clause.
+        3.45 walks the UNIQUE index on images.file_path (rows arrive in file_path order) instead
+        of scanning binary_embeddings (rowid order); the arrival order is the tie-break of the
+        reference's stable sort, so it has to be mirrored."""
+        conn = loader.connect(self.db_path)
+        try:
+            plan = conn.execute("EXPLAIN QUERY PLAN " + loader.BINARY_SQL +
+                                " WHERE (i.file_path LIKE ? ESCAPE '\\')", ("x%",)).fetchall()
+        finally:
+            conn.close()
+        return bool(plan) and str(plan[0][-1]).startswith("SCAN i")
+
+    def _binary_fallback(self, embedding1, k, embedding2, weights, negative_embeddings, negative_weights,
+                         filter_folders, timings) -> Result:
+        import time
+        try:
+            t0 = time.time()
+            if self._codes is None:
+                self._codes = loader.read_codes(self.db_path, expect_dim=self.embedding_dim)
+                self.index.load_codes(self._codes.codes)
+                self._code_mask_key = None
+            paths = self._codes.file_paths
+            n = len(paths)
+            use_mask = False
+            admitted_n = n
+            if filter_folders:
+                key = tuple(filter_folders)
+                if key != self._code_mask_key:
+                    admitted = like_prefix_mask(paths, filter_folders)
+                    order = None
+                    if self._filtered_statement_walks_the_path_index():
+                        by_path = sorted(range(n), key=lambda i: paths[i].encode("utf-8"))   # BINARY collation
+                        order = np.empty(n, dtype=np.uint32)
+                        order[by_path] = np.arange(n, dtype=np.uint32)
+                    self.index.set_code_mask(admitted, order)
+                    self._code_mask_key = key
+                    self._code_admitted = int(admitted.sum())
+                use_mask = True
+                admitted_n = self._code_admitted
+            timings["build_query"] = time.time() - t0
+            t0 = time.time()
+            # blend / negatives exactly as for the float path (:1378-1472), then the sign code (:1593)
+            query, _flags = self.index.blend(embedding1, embedding2, weights, negative_embeddings, negative_weights)
+            code = (query >= 0).astype(np.uint8)
+            k = int(k)
+            kk = k if k >= 0 else max(admitted_n + k, 0)      # `candidate_scores[:k]` is a Python slice (:1628)
+            pos, scores = self.index.binary_search(code, kk, score_mode=self.binary_score_mode, use_mask=use_mask)
+            results = [(paths[int(p)], float(int(s)) / self.embedding_dim) for p, s in zip(pos, scores)]
+            timings["db_query"] = time.time() - t0
+            return results
+        except Exception as e:                       # error envelope, :1637-1640
+            print(f"Error during search: {e}")
+            return []
+
+    def _finish(self, results: Result, show_duplicates: bool, profile: bool, timings) -> Result:
+        import time
         if not show_duplicates and len(results) > 0:
             t0 = time.time()
             results = self._filter_duplicates(results, tolerance_bits=2)

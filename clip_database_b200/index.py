@@ -222,6 +222,76 @@ class GpuIndex:
     def clear_mask(self) -> None:
         self._check(self._L.clipdb_clear_mask(self._ctx))
 
+    # ---- sign codes (the reference's binary fallback search) -------------------------------------
+    @property
+    def num_codes(self) -> int:
+        return int(self._L.clipdb_num_codes(self._ctx))
+
+    def load_codes(self, codes, ids=None) -> None:
+        """``codes``: uint8 ``[n, 1152]`` of 0/1 (numpy, or a torch tensor on any device), as stored
+        in ``binary_embeddings`` (image_database.py:1189-1190); bit-packed on the GPU.  ``ids``
+        (int64 ``[n]``) are what ``binary_search`` returns instead of scan positions."""
+        if _is_torch(codes):
+            t = codes.detach().contiguous()
+            if t.element_size() != 1 or t.dim() != 2:
+                raise ValueError("codes must be [n, dim] uint8")
+            n, dim = t.shape
+            ptr = t.data_ptr()
+        else:
+            t = np.ascontiguousarray(codes, dtype=np.uint8)
+            if t.ndim != 2:
+                raise ValueError("codes must be [n, dim] uint8")
+            n, dim = t.shape
+            ptr = t.ctypes.data
+        ids_a = None
+        if ids is not None:
+            ids_a = np.ascontiguousarray(ids, dtype=np.int64)
+            if ids_a.shape != (n,):
+                raise ValueError("ids must be [n]")
+        self._check(self._L.clipdb_load_codes(self._ctx, ctypes.c_void_p(ptr),
+                                              ctypes.c_void_p(ids_a.ctypes.data if ids_a is not None else 0), n, dim))
+
+    def set_code_mask(self, admitted, order=None) -> None:
+        """Admission bitset of the code store (bool per code) and, optionally, the tie-break
+        sequence of every code while the mask is in use (see clipdb_set_code_mask)."""
+        n = self.num_codes
+        bits = np.asarray(admitted).astype(bool)
+        if bits.shape != (n,):
+            raise ValueError("mask must have one entry per code")
+        packed = np.packbits(bits, bitorder="little")
+        words = np.zeros((n + 31) // 32, dtype=np.uint32)
+        words.view(np.uint8)[: packed.shape[0]] = packed
+        order_a = None
+        if order is not None:
+            order_a = np.ascontiguousarray(order, dtype=np.uint32)
+            if order_a.shape != (n,):
+                raise ValueError("order must have one entry per code")
+        self._check(self._L.clipdb_set_code_mask(self._ctx, ctypes.c_void_p(words.ctypes.data), words.shape[0],
+                                                 ctypes.c_void_p(order_a.ctypes.data if order_a is not None else 0)))
+
+    def clear_code_mask(self) -> None:
+        self._check(self._L.clipdb_clear_code_mask(self._ctx))
+
+    def binary_search(self, query_code, k: int, score_mode: str = "reference", use_mask: bool = False
+                      ) -> Tuple[np.ndarray, np.ndarray]:
+        """Top-k codes by AND-popcount with ``query_code`` (uint8 ``[1152]`` of 0/1).  Returns
+        (ids int64, scores int32), score descending, ties in scan order.  ``score_mode``:
+        "reference" = modulo 256 like the reference's uint8 ``np.dot``; "popcount" = plain."""
+        modes = {"reference": _lib.SCORE_REFERENCE_UINT8, "popcount": _lib.SCORE_POPCOUNT}
+        if score_mode not in modes:
+            raise ValueError(f"score_mode must be one of {sorted(modes)}")
+        q = np.ascontiguousarray(query_code, dtype=np.uint8).ravel()
+        if q.shape[0] != 1152:
+            raise ValueError("query code must be uint8[1152]")
+        kc = max(int(k), 0)
+        ids = np.full(max(kc, 1), -1, dtype=np.int64)
+        scores = np.zeros(max(kc, 1), dtype=np.int32)
+        n = ctypes.c_int32(0)
+        self._check(self._L.clipdb_binary_search(self._ctx, ctypes.c_void_p(q.ctypes.data), kc, modes[score_mode],
+                                                 int(bool(use_mask)), ctypes.c_void_p(ids.ctypes.data),
+                                                 ctypes.c_void_p(scores.ctypes.data), ctypes.byref(n)))
+        return ids[:n.value].copy(), scores[:n.value].copy()
+
     # ---- query arithmetic -----------------------------------------------------------------
     @staticmethod
     def _pack_negatives(negatives, negative_weights, dim):

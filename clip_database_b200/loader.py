@@ -37,6 +37,45 @@ class HostStore:
         return int(self.rows.shape[1]) if self.rows.ndim == 2 else 0
 
 
+@dataclass
+class HostCodes:
+    """The row set of the reference's binary-fallback statement (image_database.py:1597-1605)."""
+    image_ids: np.ndarray     # int64 [n], in the order the UNFILTERED statement returns rows
+    codes: np.ndarray         # uint8 [n, dim] of 0/1
+    file_paths: List[str]     # [n]
+
+
+# The fallback's statement without its {where_clause} (image_database.py:1597-1605).
+BINARY_SQL = """
+    SELECT
+        be.image_id,
+        be.embedding,
+        i.file_path
+    FROM binary_embeddings be
+    JOIN images i ON be.image_id = i.id
+"""
+
+
+def read_codes(db_path: str, expect_dim: Optional[int] = None) -> HostCodes:
+    """Run the fallback's own statement (no WHERE) and keep the rows in the order SQLite
+    returns them: that order is the tie-break of the reference's stable sort (:1627)."""
+    conn = connect(db_path)
+    try:
+        rows = conn.execute(BINARY_SQL).fetchall()
+    finally:
+        conn.close()
+    dim = expect_dim
+    for image_id, blob, _ in rows:
+        if dim is None:
+            dim = len(blob)
+        if len(blob) != dim:
+            raise ValueError(f"binary_embeddings image_id {image_id}: {len(blob)} bytes, expected {dim}")
+    n = len(rows)
+    codes = np.frombuffer(b"".join(r[1] for r in rows), dtype=np.uint8).reshape(n, dim or 0)
+    return HostCodes(np.asarray([r[0] for r in rows], dtype=np.int64), np.ascontiguousarray(codes),
+                     [r[2] for r in rows])
+
+
 def connect(db_path: str, readonly: bool = True) -> sqlite3.Connection:
     if readonly:
         return sqlite3.connect(f"file:{db_path}?mode=ro", uri=True, timeout=30.0)

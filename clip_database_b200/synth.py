@@ -41,13 +41,15 @@ def default_paths(n: int, folders: Sequence[str] = ("/data/photos/a", "/data/pho
 def write_reference_db(path: str, rows: np.ndarray, file_paths: Optional[Sequence[str]] = None,
                        vec0_layout: str = "standin", rowid_start: int = 1,
                        drop_mapping_for: Iterable[int] = (), drop_image_for: Iterable[int] = (),
-                       binary_codes: bool = True, chunk_size: int = 1024) -> None:
+                       binary_codes: bool = True, chunk_size: int = 1024, vectors: bool = True) -> None:
     """Create ``path`` with ``rows[i]`` stored as vec0 rowid ``rowid_start + i``.
 
     ``drop_mapping_for`` / ``drop_image_for`` are positions whose ``image_embeddings``
     / ``images`` row is removed afterwards: orphaned vec0 rows that the reference's
     INNER JOINs silently exclude (image_database.py:1569-1570).
     ``vec0_layout``: "standin" (plain table) or "shadow" (sqlite-vec shadow tables).
+    ``vectors=False`` leaves ``vec0`` and ``image_embeddings`` empty: a binary-only database,
+    which makes the reference's search() take its sign-code fallback (image_database.py:1591-1629).
     """
     rows = np.ascontiguousarray(rows, dtype=np.float32)
     n, dim = rows.shape
@@ -65,7 +67,9 @@ def write_reference_db(path: str, rows: np.ndarray, file_paths: Optional[Sequenc
     cur.executemany("INSERT INTO images (id, file_path, last_modified, file_hash) VALUES (?, ?, ?, ?)",
                     ((i + 1, file_paths[i], 1.7e9 + i, f"{i:032x}") for i in range(n)))
     rowids = np.arange(rowid_start, rowid_start + n, dtype=np.int64)
-    if vec0_layout == "standin":
+    if not vectors:
+        cur.execute(schema.VEC0_STANDIN)
+    elif vec0_layout == "standin":
         cur.execute(schema.VEC0_STANDIN)
         cur.executemany("INSERT INTO vec0 (rowid, embedding) VALUES (?, ?)",
                         ((int(rowids[i]), rows[i].tobytes()) for i in range(n)))
@@ -90,8 +94,9 @@ def write_reference_db(path: str, rows: np.ndarray, file_paths: Optional[Sequenc
                             ((int(rowids[lo + j]), c + 1, j) for j in range(m)))
     else:
         raise ValueError("vec0_layout must be 'standin' or 'shadow'")
-    cur.executemany("INSERT INTO image_embeddings (rowid, image_id) VALUES (?, ?)",
-                    ((int(rowids[i]), i + 1) for i in range(n)))
+    if vectors:
+        cur.executemany("INSERT INTO image_embeddings (rowid, image_id) VALUES (?, ?)",
+                        ((int(rowids[i]), i + 1) for i in range(n)))
     if binary_codes:
         codes = (rows >= 0).astype(np.uint8)  # image_database.py:1189-1190
         cur.executemany("INSERT INTO binary_embeddings (image_id, embedding) VALUES (?, ?)",

@@ -191,6 +191,43 @@ int clipdb_search_batch_device(clipdb_ctx *ctx, const float *d_queries, int32_t 
  * were re-ranked in float32.  Synchronises the stream. */
 int clipdb_batch_stats(clipdb_ctx *ctx, uint32_t *cand_counts, uint32_t *surv_counts);
 
+/* ---- sign-code search (the reference's binary fallback) ----------------------------
+ * Replaces idb:1591-1629, the path search() takes when `vec0` is empty but
+ * `binary_embeddings` is not: every stored code is dim bytes of 0/1
+ * (`(embedding >= 0).astype(np.uint8)`, idb:1189-1190), the query is quantised the same
+ * way (idb:1593), score(row) = np.dot(query_code, row_code) (idb:1621) and the k rows
+ * with the largest score come back, ties in scan order (Python's stable sort, idb:1627-1628).
+ *   CLIPDB_SCORE_REFERENCE_UINT8  numpy evaluates that dot product in uint8, so the
+ *                                 reference's score is popcount(q AND row) MODULO 256;
+ *                                 this mode reproduces it.
+ *   CLIPDB_SCORE_POPCOUNT         the plain AND-popcount (what the reference meant).
+ * clipdb_load_codes copies n x dim bytes (host or device pointer; dim must be 1152; any
+ * byte other than 0/1 is refused) and bit-packs them on the device: 144 B per row
+ * resident.  `ids` (nullable) are returned instead of scan positions.  The code store is
+ * independent of the float32 row store and has its own admission bitset
+ * (clipdb_set_code_mask: the WHERE clause applies to this statement too, idb:1597-1611).
+ * `order` (nullable, n uint32, a permutation of 0..n-1): the tie-break sequence of each row
+ * while this mask is in use.  SQLite 3.45 answers the FILTERED statement by walking the
+ * UNIQUE index on images.file_path (rows arrive in file_path order) and the unfiltered one by
+ * scanning binary_embeddings (rowid order) [PROBED, EXPLAIN QUERY PLAN]; Python's stable sort
+ * keeps that arrival order among equal scores, so the caller passes each row's file_path
+ * rank here to get the reference's tie order.
+ * clipdb_binary_search: host query code (dim bytes of 0/1) in, out_ids / out_scores
+ * (k entries each, score descending, scan position ascending) and out_n out; synchronous.
+ * similarity = score / dim is left to the caller (idb:1624). */
+#define CLIPDB_SCORE_REFERENCE_UINT8  0
+#define CLIPDB_SCORE_POPCOUNT         1
+int clipdb_load_codes(clipdb_ctx *ctx, const uint8_t *codes, const int64_t *ids, int64_t n, int32_t dim);
+int64_t clipdb_num_codes(const clipdb_ctx *ctx);
+int clipdb_set_code_mask(clipdb_ctx *ctx, const uint32_t *words, int64_t n_words, const uint32_t *order);
+int clipdb_clear_code_mask(clipdb_ctx *ctx);
+int clipdb_binary_search(clipdb_ctx *ctx, const uint8_t *query_code, int32_t k, int32_t score_mode,
+                         int32_t use_mask, int64_t *out_ids, int32_t *out_scores, int32_t *out_n);
+/* device form: the query already bit-packed (36 words, bit (i & 31) of word (i >> 5) =
+ * element i); enqueued on the ctx stream, no sync. */
+int clipdb_binary_search_device(clipdb_ctx *ctx, const uint32_t *d_query_words, int32_t k, int32_t score_mode,
+                                int32_t use_mask, int64_t *d_out_ids, int32_t *d_out_scores, int32_t *d_out_n);
+
 /* ---- shard merge (multi-GPU) --------------------------------
  * Merges `lists` per-shard result lists (each k entries, already sorted, shard
  * order = rowid order; counts[l] valid entries in list l) into the global

@@ -119,6 +119,37 @@ def reference_search(db_path: str, embedding: np.ndarray, k: int,
     return results
 
 
+# The fallback's statement (image_database.py:1597-1605) with its {where_clause} slot.
+BINARY_SQL = """
+    SELECT
+        be.image_id,
+        be.embedding,
+        i.file_path
+    FROM binary_embeddings be
+    JOIN images i ON be.image_id = i.id
+    {where_clause}
+"""
+
+
+def reference_binary_search(db_path: str, embedding: np.ndarray, k: int,
+                            filter_folders: Optional[Sequence[str]] = None) -> List[Tuple[str, float]]:
+    """The sign-code fallback of ``search()`` written the literal way (image_database.py:1591-1629):
+    the statement executed by the real SQLite (so the arrival order, which breaks ties in the
+    stable sort, is SQLite's own), then the reference's per-row numpy arithmetic."""
+    conn = sqlite3.connect(db_path, timeout=30.0)
+    where, fparams = where_clause_and_params(filter_folders)
+    query_binary = (np.asarray(embedding) >= 0).astype(np.uint8)
+    rows = conn.execute(BINARY_SQL.format(where_clause=where), tuple(fparams)).fetchall()
+    conn.close()
+    candidate_scores = []
+    for _image_id, binary_blob, file_path in rows:
+        candidate_binary = np.frombuffer(binary_blob, dtype=np.uint8)
+        binary_score = np.dot(query_binary, candidate_binary)      # uint8 arithmetic: modulo 256
+        candidate_scores.append((file_path, float(binary_score) / query_binary.shape[0]))
+    candidate_scores.sort(key=lambda x: x[1], reverse=True)
+    return candidate_scores[:k]
+
+
 def reference_filter_duplicates(db_path: str, results: List[Tuple[str, float]],
                                 tolerance_bits: int = 2) -> List[Tuple[str, float]]:
     """Behavioural restatement of ``_filter_duplicates`` (image_database.py:1207-1306),
