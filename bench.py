@@ -51,9 +51,10 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--k", type=int, default=20)
     ap.add_argument("--rows", type=int, default=0, help="rows per GPU (default 10M at N=1, 12.5M at N>1)")
-    ap.add_argument("--workload", default="single", choices=["single", "blend", "batch"],
+    ap.add_argument("--workload", default="single", choices=["single", "blend", "batch", "binary"],
                     help="single: configs[1]; blend: configs[3] (0.7/0.3 blend + negative, then the scan); "
-                         "batch: configs[2] (B queries per step through the tcgen05 contraction + fp32 re-rank)")
+                         "batch: configs[2] (B queries per step through the tcgen05 contraction + fp32 re-rank); "
+                         "binary: the sign-code fallback search (SURVEY §8 f-4) over bit-packed codes")
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--sample-stride", type=int, default=0, help="batch: pass A sampling stride (0 = auto)")
     ap.add_argument("--no-refine", action="store_true", help="batch: skip the second threshold")
@@ -351,6 +352,116 @@ def run_batch_workload(args, torch, idx, rows, rows_per_gpu, device, rank, local
     return 0
 
 
+def run_binary_workload(args, torch, device, local_rank):
+    """one query's AND-popcount scan + top-k over N bit-packed sign codes (144 B per
+    row resident).  metric = scanned GB/s of the packed store; HBM roofline."""
+    from clip_database_b200 import GpuIndex
+    k = args.k
+    n = args.rows or 10_000_000
+    idx = GpuIndex(local_rank)
+    idx.use_torch_stream()
+    gen = torch.Generator(device=device)
+    gen.manual_seed(1234)
+    # codes are generated and packed chunk by chunk (n x 1152 bytes would be 11.5 GB at 10M rows)
+    chunk = 1_000_000
+    parts = []
+    for lo in range(0, n, chunk):
+        m = min(chunk, n - lo)
+        parts.append((torch.randn((m, DIM), generator=gen, device=device) >= 0).to(torch.uint8))
+    codes = torch.cat(parts)
+    del parts
+    idx.load_codes(codes)
+    del codes
+    torch.cuda.empty_cache()
+    rng = np.random.default_rng(99)
+    n_q = 64
+    host_codes = (rng.standard_normal((n_q, DIM), dtype=np.float32) >= 0).astype(np.uint8)
+    words = np.zeros((n_q, DIM // 32), dtype=np.uint32)
+    words.view(np.uint8)[:] = np.packbits(host_codes, axis=1, bitorder="little")
+    d_words = torch.from_numpy(words.view(np.int32)).to(device)
+    o_ids = torch.empty(k, dtype=torch.int64, device=device)
+    o_sc = torch.empty(k, dtype=torch.int32, device=device)
+    o_n = torch.zeros(1, dtype=torch.int32, device=device)
+    sampler = ClockSampler(local_rank)
+    for i in range(args.warmup):
+        idx.binary_search_device(d_words[i % n_q], k, o_ids, o_sc, o_n)
+    torch.cuda.synchronize()
+    sampler.start()
+    launches0 = idx.launch_count
+    idx.profile(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        idx.binary_search_device(d_words[i % n_q], k, o_ids, o_sc, o_n)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms_step = ev0.elapsed_time(ev1) / args.steps
+    scan_ms, scans = idx.profile_read()
+    idx.profile(False)
+    launches = idx.launch_count - launches0
+    for i in range(3):
+        idx.binary_search(host_codes[i], k)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        last = idx.binary_search(host_codes[i % n_q], k)
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    sampler.stop()
+    assert len(last[0]) == k and np.all(np.diff(last[1]) <= 0)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    gb = n * (DIM // 8) / 1e9
+    scan_avg = scan_ms / max(scans, 1)
+    line = {
+        "metric": "binary_scan_throughput", "value": gb / (ms_step / 1e3), "unit": "GB/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32 (AND + popcount)", "data": "synthetic",
+        "config": {"workload": "sign-code fallback search (image_database.py:1591-1629), k=%d, %d x 1152-bit codes "
+                               "(144 B per row resident), score = popcount(q AND row) mod 256" % (k, n),
+                   "rows_per_gpu": n, "k": k, "dim": DIM, "l2": "inputs_larger_than_L2"},
+        "queries_per_s": 1e3 / ms_step, "rows_per_s": n / (ms_step / 1e3),
+        "e2e": {"value": gb / (e2e_ms / 1e3), "unit": "GB/s", "h2d_bytes_per_step": DIM // 8,
+                "d2h_bytes_per_step": k * 12 + 12, "ms_per_step": e2e_ms, "queries_per_s": 1e3 / e2e_ms,
+                "api": "GpuIndex.binary_search (clipdb_binary_search)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "binary_scan_kernel", "achieved": gb / (scan_avg / 1e3), "peak": peak,
+                     "unit": "GB/s", "frac": gb / (scan_avg / 1e3) / peak,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)",
+                     "algorithmic_bytes_per_launch": n * (DIM // 8), "avg_launch_ms": scan_avg,
+                     "launches_timed": int(scans), "traffic": None},
+        "clocks": sampler.summary(),
+    }
+    if not args.no_cpu_baseline:
+        # the reference's own fallback on the host: fetch every row, np.frombuffer + np.dot per row
+        from clip_database_b200 import synth
+        from oracle import ref, sql_harness
+        m = min(args.cpu_sample_rows, 50_000)
+        rows = ref.fill_unit_rows(m, DIM, 1234)
+        tmp = tempfile.mkdtemp(prefix="clipdb_bin_")
+        db_path = os.path.join(tmp, "b.db")
+        synth.write_reference_db(db_path, rows, vectors=False)
+        q = ref.fill_unit_rows(4, DIM, 99)
+        sql_harness.reference_binary_search(db_path, q[0], k)
+        t0 = time.perf_counter()
+        for j in range(1, 4):
+            sql_harness.reference_binary_search(db_path, q[j], k)
+        sec = (time.perf_counter() - t0) / 3
+        os.remove(db_path)
+        os.rmdir(tmp)
+        line["cpu_baseline"] = {"value": m * (DIM // 8) / 1e9 / sec, "unit": "GB/s", "cores": 1, "kind": "port",
+                                "rows_per_s": m / sec,
+                                "sample": "literal restatement of image_database.py:1591-1629 (real SQLite fetchall + "
+                                          "np.frombuffer + np.dot per row, 1 thread), %d-row sample, 3 queries; GB/s in "
+                                          "the same packed-store bytes (the reference itself reads 1152 B per row)" % m,
+                                "cpu": cpu_model()}
+    emit(line)
+    idx.close()
+    return 0
+
+
 _REAL_STDOUT = None
 
 
@@ -397,6 +508,8 @@ def main():
         dist.init_process_group("nccl", device_id=device)
 
     k = args.k
+    if args.workload == "binary":
+        return run_binary_workload(args, torch, device, local_rank)
     rows_per_gpu = args.rows or (10_000_000 if world == 1 else 12_500_000)
     rows = generate_rows(torch, device, rows_per_gpu, 1234 + rank)
     idx = GpuIndex(local_rank)

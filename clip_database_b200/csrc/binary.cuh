@@ -44,13 +44,15 @@ struct BinaryArgs {
                                    // file_path index order, see clipdb_set_code_mask)
     uint64_t *cand;                // [gridDim.x][cand_stride]
     uint64_t *all_keys;            // WRITE_ALL: [n]
-    unsigned int *tile_counter;    // zeroed before the launch
+    ScanSync *sync;                // tile / done counters, zero between launches (merge.cuh)
     long long n;
     int k;
     int cand_stride;
     int chunk_tiles;
     uint32_t score_mask;           // 0xFF: the reference's uint8 wrap-around; 0xFFFF: plain popcount
     uint32_t score_max;            // 255 or 1152: key = (score_max - score) << 32 | position
+    int fuse_tail;                 // the last CTA to finish merges all lists and decodes the result
+    DecodeArgs dec;
 };
 
 // bytes (0/1) -> bits.  One thread per output word; `bad` counts bytes other than 0/1 (the
@@ -136,10 +138,10 @@ __global__ void __launch_bounds__(BIN_THREADS, 1) binary_scan_kernel(const Binar
                 }
             };
             const unsigned chunk = static_cast<unsigned>(a.chunk_tiles > 0 ? a.chunk_tiles : 1);
-            unsigned next = atomicAdd(a.tile_counter, chunk);
+            unsigned next = atomicAdd(&a.sync->tile_counter, chunk);
             while (next < static_cast<unsigned>(total_tiles)) {
                 const unsigned base = next;
-                next = atomicAdd(a.tile_counter, chunk);
+                next = atomicAdd(&a.sync->tile_counter, chunk);
                 for (unsigned j = 0; j < chunk && base + j < static_cast<unsigned>(total_tiles); j++)
                     push(static_cast<int>(base + j));
             }
@@ -208,6 +210,9 @@ __global__ void __launch_bounds__(BIN_THREADS, 1) binary_scan_kernel(const Binar
     __syncthreads();
     emit_cta_list<KPL>(scratch, BIN_CONSUMER_WARPS, a.cand + static_cast<size_t>(blockIdx.x) * a.cand_stride, tid,
                        BIN_THREADS);
+    if (!a.fuse_tail) return;
+    if (!last_cta_done(&a.sync->done_counter, tid)) return;
+    merge_decode_reset<32 * KPL>(a.cand, static_cast<int>(gridDim.x), scratch, a.dec, a.sync, tid, BIN_THREADS);
 }
 
 }  // namespace clipdb

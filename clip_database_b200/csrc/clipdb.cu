@@ -69,7 +69,8 @@ struct clipdb_ctx {
     Buffer d_code_query, code_stage, code_bad;
 
     // workspaces (grown on demand)
-    Buffer cand_a, cand_b, nan_ctr, tile_ctr, all_keys_a, all_keys_b, cub_tmp;
+    Buffer cand_a, cand_b, sync_buf, all_keys_a, all_keys_b, cub_tmp;
+    bool sync_dirty = true;   // the scan kernels' counters may be non-zero
     Buffer d_query, d_out_rowids, d_out_dist, d_out_n, d_out_nan;
     Buffer d_blend_in, d_blend_flags;
     Buffer pinned;      // host staging (inputs, then results)
@@ -105,6 +106,7 @@ struct clipdb_ctx {
     int64_t scan_cfg = 0;      // ring shape (ScanCfg0..4); shapes other than 0 exist for k <= 32 cosine only
     int64_t scan_assign = 2;   // SCAN_ASSIGN_* (dynamic: +5 % over static interleaving, profiles/r01_sweep2.json)
     int64_t scan_chunk = 4;    // tiles per atomicAdd (dynamic assignment)
+    int64_t fuse_tail = 1;     // 1: the scan's last CTA merges and decodes (one launch per query); 0: merge-tree kernels
 };
 
 namespace {
@@ -419,11 +421,21 @@ int sort_all_keys_and_decode(clipdb_ctx *c, int64_t n, int64_t kk, const DecodeA
     return CLIPDB_OK;
 }
 
-// one query: scan + merge tree (k <= FUSED_K_MAX) or scan + radix sort (any k)
+// The scan kernels' shared counters (merge.cuh ScanSync).  A fused launch leaves them zero (its
+// last CTA resets them); any other use marks them dirty and the next user zeroes them first.
+int prepare_sync(clipdb_ctx *c, ScanSync **out) {
+    const bool fresh = c->sync_buf.p == nullptr;
+    RC_TRY(ensure_device(c, c->sync_buf, sizeof(ScanSync)));
+    if (fresh || c->sync_dirty) CU_TRY(c, cudaMemsetAsync(c->sync_buf.p, 0, sizeof(ScanSync), c->stream));
+    c->sync_dirty = true;   // until a fused launch has been enqueued successfully
+    *out = static_cast<ScanSync *>(c->sync_buf.p);
+    return CLIPDB_OK;
+}
+
+// one query: ONE launch (TMA scan with the fused merge/decode tail, k <= FUSED_K_MAX), or
+// scan + merge tree (direct-load kernel), or scan + radix sort (any k)
 int search_one(clipdb_ctx *c, const float *d_query, int k, int metric, bool use_mask,
-               int64_t *d_out_rowids, float *d_out_dist, int32_t *d_out_n, int64_t *d_out_nan,
-               unsigned long long *d_nan_ctr) {
-    CU_TRY(c, cudaMemsetAsync(d_nan_ctr, 0, sizeof(unsigned long long), c->stream));
+               int64_t *d_out_rowids, float *d_out_dist, int32_t *d_out_n, int64_t *d_out_nan) {
     const int64_t kk = k < c->n ? k : c->n;
     if (kk <= 0) {
         CU_TRY(c, cudaMemsetAsync(d_out_n, 0, sizeof(int32_t), c->stream));
@@ -437,7 +449,7 @@ int search_one(clipdb_ctx *c, const float *d_query, int k, int metric, bool use_
     a.rows = c->rows;
     a.query = d_query;
     a.mask = use_mask ? c->mask : nullptr;
-    a.nan_rows = d_nan_ctr;
+    RC_TRY(prepare_sync(c, &a.sync));
     a.n = c->n;
     a.dim = c->dim;
     a.ld = c->ld;
@@ -445,11 +457,6 @@ int search_one(clipdb_ctx *c, const float *d_query, int k, int metric, bool use_
     a.evict_first = static_cast<int>(c->evict_first);
     a.assign = static_cast<int>(c->scan_assign);
     a.chunk_tiles = static_cast<int>(c->scan_chunk);
-    if (tma && a.assign == SCAN_ASSIGN_DYNAMIC) {
-        RC_TRY(ensure_device(c, c->tile_ctr, sizeof(unsigned int)));
-        a.tile_counter = static_cast<unsigned int *>(c->tile_ctr.p);
-        CU_TRY(c, cudaMemsetAsync(a.tile_counter, 0, sizeof(unsigned int), c->stream));
-    }
 
     DecodeArgs dec{};
     dec.rowids = c->rowids;
@@ -458,7 +465,7 @@ int search_one(clipdb_ctx *c, const float *d_query, int k, int metric, bool use_
     dec.out_dist = d_out_dist;
     dec.out_n = d_out_n;
     dec.out_nan = d_out_nan;
-    dec.nan_rows = d_nan_ctr;
+    dec.nan_rows = &a.sync->nan_rows;
     dec.k = static_cast<int>(kk);
 
     if (kk <= FUSED_K_MAX) {
@@ -467,10 +474,19 @@ int search_one(clipdb_ctx *c, const float *d_query, int k, int metric, bool use_
         a.cand_stride = stride;
         RC_TRY(ensure_device(c, c->cand_a, static_cast<size_t>(grid) * stride * sizeof(uint64_t)));
         a.cand = static_cast<uint64_t *>(c->cand_a.p);
+        // every CTA's list must fit the last CTA's shared memory (the smallest ring among the shapes)
+        const size_t ring_bytes = c->scan_cfg == 0 ? ScanCfg0::STAGES * ScanCfg0::STAGE_BYTES
+                                                   : ScanCfg3::STAGES * ScanCfg3::STAGE_BYTES;
+        a.fuse_tail = tma && c->fuse_tail && static_cast<size_t>(grid) * stride * sizeof(uint64_t) <= ring_bytes;
+        a.dec = dec;
         switch (kpl) {
             case 1: RC_TRY((launch_scan_metric<1, false>(c, a, metric, tma, grid))); break;
             case 2: RC_TRY((launch_scan_metric<2, false>(c, a, metric, tma, grid))); break;
             default: RC_TRY((launch_scan_metric<4, false>(c, a, metric, tma, grid))); break;
+        }
+        if (a.fuse_tail) {
+            c->sync_dirty = false;
+            return CLIPDB_OK;
         }
         return merge_cta_lists(c, grid, stride, dec);
     }
@@ -496,13 +512,11 @@ int search_device_locked(clipdb_ctx *c, const float *d_queries, int32_t nq, int3
         return fail(c, CLIPDB_ERR_INVALID, "search: unknown metric %d", metric);
     if (use_mask && !c->mask) return fail(c, CLIPDB_ERR_STATE, "search: use_mask set but no mask installed");
     if (c->n >= (1ll << 32)) return fail(c, CLIPDB_ERR_UNSUPPORTED, "more than 2^32-1 rows per context");
-    RC_TRY(ensure_device(c, c->nan_ctr, static_cast<size_t>(nq > 0 ? nq : 1) * sizeof(unsigned long long)));
     const int64_t kcols = k > 0 ? k : 0;
     for (int32_t q = 0; q < nq; q++) {
         RC_TRY(search_one(c, d_queries + static_cast<size_t>(q) * c->dim, k, metric, use_mask != 0,
                           d_out_rowids + q * kcols, d_out_dist + q * kcols, d_out_n + q,
-                          d_out_nan ? d_out_nan + q : nullptr,
-                          static_cast<unsigned long long *>(c->nan_ctr.p) + q));
+                          d_out_nan ? d_out_nan + q : nullptr));
     }
     return CLIPDB_OK;
 }
@@ -832,15 +846,13 @@ int binary_search_device_locked(clipdb_ctx *c, const uint32_t *d_query_words, in
         return CLIPDB_OK;
     }
     const int grid = c->scan_ctas > 0 ? static_cast<int>(c->scan_ctas) : c->sm_count;
-    RC_TRY(ensure_device(c, c->tile_ctr, sizeof(unsigned int)));
-    CU_TRY(c, cudaMemsetAsync(c->tile_ctr.p, 0, sizeof(unsigned int), c->stream));
 
     BinaryArgs a{};
     a.codes = c->codes;
     a.query = d_query_words;
     a.mask = use_mask ? c->code_mask : nullptr;
     a.seq = use_mask ? c->code_seq : nullptr;
-    a.tile_counter = static_cast<unsigned int *>(c->tile_ctr.p);
+    RC_TRY(prepare_sync(c, &a.sync));
     a.n = c->n_codes;
     a.k = static_cast<int>(kk);
     a.chunk_tiles = static_cast<int>(c->scan_chunk);
@@ -861,10 +873,17 @@ int binary_search_device_locked(clipdb_ctx *c, const uint32_t *d_query_words, in
         a.cand_stride = 32 * kpl;
         RC_TRY(ensure_device(c, c->cand_a, static_cast<size_t>(grid) * a.cand_stride * sizeof(uint64_t)));
         a.cand = static_cast<uint64_t *>(c->cand_a.p);
+        a.fuse_tail = c->fuse_tail &&
+                      static_cast<size_t>(grid) * a.cand_stride * sizeof(uint64_t) <= BIN_STAGES * BIN_STAGE_BYTES;
+        a.dec = dec;
         switch (kpl) {
             case 1: RC_TRY((launch_binary_scan<1, false>(c, a, grid))); break;
             case 2: RC_TRY((launch_binary_scan<2, false>(c, a, grid))); break;
             default: RC_TRY((launch_binary_scan<4, false>(c, a, grid))); break;
+        }
+        if (a.fuse_tail) {
+            c->sync_dirty = false;
+            return CLIPDB_OK;
         }
         return merge_cta_lists(c, grid, a.cand_stride, dec);
     }
@@ -924,7 +943,7 @@ void clipdb_destroy(clipdb_ctx *c) {
         cudaStreamSynchronize(c->stream);
         release_store(c);
         release_codes(c);
-        Buffer *bufs[] = {&c->d_code_query, &c->code_stage, &c->code_bad, &c->cand_a, &c->cand_b, &c->nan_ctr, &c->tile_ctr, &c->all_keys_a, &c->all_keys_b,
+        Buffer *bufs[] = {&c->d_code_query, &c->code_stage, &c->code_bad, &c->cand_a, &c->cand_b, &c->sync_buf, &c->all_keys_a, &c->all_keys_b,
                           &c->cub_tmp, &c->d_query, &c->d_out_rowids, &c->d_out_dist, &c->d_out_n,
                           &c->d_out_nan, &c->d_blend_in, &c->d_blend_flags, &c->bf16_rows,
                           &c->bad_rows, &c->bq_queries, &c->bq_qnorm, &c->bq_scores, &c->bq_thr, &c->bq_flags,
@@ -979,6 +998,7 @@ static int64_t *option_slot(clipdb_ctx *c, const char *name) {
     if (!strcmp(name, "scan_cfg")) return &c->scan_cfg;
     if (!strcmp(name, "scan_assign")) return &c->scan_assign;
     if (!strcmp(name, "scan_chunk")) return &c->scan_chunk;
+    if (!strcmp(name, "fuse_tail")) return &c->fuse_tail;
     if (!strcmp(name, "batch_min_nq")) return &c->batch_min_nq;
     if (!strcmp(name, "batch_cand_cap")) return &c->batch_cand_cap;
     if (!strcmp(name, "batch_cta_pair")) return &c->batch_cta_pair;

@@ -34,6 +34,81 @@ __device__ __forceinline__ void decode_one(const DecodeArgs &d, int i, uint64_t 
     d.out_rowids[i] = d.rowids ? d.rowids[pos] : d.rowid_base + static_cast<int64_t>(pos);
 }
 
+// ---- fused tail: the CTA that finishes last merges every CTA's list and decodes the answer ----
+// Each CTA has written one ascending list of L keys.  The last one to finish (a ticket from a
+// global counter, after a __threadfence so the lists are visible) pulls all lists into shared
+// memory and runs a tournament: per round, lists p and p+half are combined with the bitonic
+// half-cleaner C[i] = min(A[i], B[L-1-i]) — the L smallest of the union, as a bitonic sequence —
+// followed by log2(L) compare-exchange steps.  ceil(log2(lists)) rounds of 1 + log2(L) steps:
+// ~50 block-wide steps for 148 lists of 32 keys (a few microseconds) instead of two more kernel
+// launches that each sort 2048 keys from scratch, so one query is ONE launch.
+__device__ __forceinline__ bool last_cta_done(unsigned int *done_counter, int tid) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(done_counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    return s_last != 0;
+}
+
+template <int L>
+__device__ __forceinline__ void merge_sorted_lists_tournament(uint64_t *m, int cnt, int tid, int nthreads) {
+    while (cnt > 1) {
+        const int half = (cnt + 1) >> 1, pairs = cnt >> 1;
+        for (int w = tid; w < pairs * L; w += nthreads) {
+            const int p = w / L, i = w - p * L;
+            const uint64_t b = m[(p + half) * L + (L - 1 - i)];
+            if (b < m[p * L + i]) m[p * L + i] = b;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int s = L / 2; s >= 1; s >>= 1) {
+            for (int w = tid; w < pairs * (L / 2); w += nthreads) {
+                const int p = w / (L / 2), j = w - p * (L / 2);
+                const int lo = p * L + 2 * j - (j & (s - 1)), hi = lo + s;
+                const uint64_t a = m[lo], b = m[hi];
+                if (a > b) {
+                    m[lo] = b;
+                    m[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+        cnt = half;
+    }
+}
+
+// Counters shared by the CTAs of one scan launch.  All zero between launches: the last CTA
+// resets them, so a query needs no memset nodes.
+struct ScanSync {
+    unsigned int tile_counter;        // dynamic tile scheduler
+    unsigned int done_counter;        // CTAs finished
+    unsigned long long nan_rows;      // admitted rows whose distance was NaN
+};
+
+// lists: [n_lists][L] in global memory (written by other CTAs: read through L2), scratch: shared
+template <int L>
+__device__ __forceinline__ void merge_decode_reset(const uint64_t *lists, int n_lists, uint64_t *scratch,
+                                                   const DecodeArgs &dec, ScanSync *sync, int tid, int nthreads) {
+    for (int i = tid; i < n_lists * L; i += nthreads) scratch[i] = __ldcg(lists + i);
+    __syncthreads();
+    merge_sorted_lists_tournament<L>(scratch, n_lists, tid, nthreads);
+    int found = 0;
+    for (int base = 0; base < dec.k; base += nthreads) {
+        const int i = base + tid;
+        const bool valid = i < dec.k && i < L && scratch[i] != KEY_EMPTY;
+        if (valid) decode_one(dec, i, scratch[i]);
+        found += __syncthreads_count(valid);
+    }
+    if (tid == 0) {
+        *dec.out_n = found;
+        const unsigned long long nan = atomicExch(&sync->nan_rows, 0ull);
+        if (dec.out_nan) *dec.out_nan = static_cast<int64_t>(nan);
+        sync->tile_counter = 0;
+        sync->done_counter = 0;
+    }
+}
+
 // One level of the reduction tree: CTA b merges lists [b*lists_per_cta, ...) of
 // `stride` ascending keys each into one ascending list of `stride` keys.  When
 // do_decode != 0 (single CTA, last level) the first k keys are decoded into the

@@ -22,6 +22,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "merge.cuh"
 
 namespace clipdb {
 
@@ -69,7 +70,7 @@ struct ScanArgs {
     const float *query;            // [dim]
     const uint32_t *mask;          // nullable admission bitset
     uint64_t *cand;                // [gridDim.x][cand_stride], each ascending
-    unsigned long long *nan_rows;  // += admitted rows whose distance is NaN
+    ScanSync *sync;                // tile / done / NaN counters, zero between launches (merge.cuh)
     uint64_t *all_keys;            // WRITE_ALL: [n] keys (KEY_EMPTY = not admitted / NaN)
     long long n;
     int dim;
@@ -79,7 +80,8 @@ struct ScanArgs {
     int evict_first;  // stream rows with an L2 evict-first policy
     int assign;       // SCAN_ASSIGN_*
     int chunk_tiles;  // tiles claimed per atomicAdd (dynamic assignment)
-    unsigned int *tile_counter;  // zeroed before the launch (dynamic assignment)
+    int fuse_tail;    // the last CTA to finish merges all lists and decodes the result (TMA kernel)
+    DecodeArgs dec;   // used when fuse_tail != 0
 };
 
 // The exact finish (double sqrt, multiply, divide) is ~70 instructions.  A float32
@@ -265,10 +267,10 @@ __global__ void __launch_bounds__(CFG::THREADS, 1) scan_tma_kernel(const ScanArg
             const int grid = static_cast<int>(gridDim.x), b = static_cast<int>(blockIdx.x);
             if (a.assign == SCAN_ASSIGN_DYNAMIC) {
                 const unsigned chunk = static_cast<unsigned>(a.chunk_tiles > 0 ? a.chunk_tiles : 1);
-                unsigned next = atomicAdd(a.tile_counter, chunk);
+                unsigned next = atomicAdd(&a.sync->tile_counter, chunk);
                 while (next < static_cast<unsigned>(total_tiles)) {
                     const unsigned base = next;
-                    next = atomicAdd(a.tile_counter, chunk);  // claimed ahead: latency hidden by the pushes
+                    next = atomicAdd(&a.sync->tile_counter, chunk);  // claimed ahead: latency hidden by the pushes
                     for (unsigned j = 0; j < chunk && base + j < static_cast<unsigned>(total_tiles); j++)
                         push(static_cast<int>(base + j));
                 }
@@ -334,7 +336,7 @@ __global__ void __launch_bounds__(CFG::THREADS, 1) scan_tma_kernel(const ScanArg
         }
     }
 
-    if (nan_rows && lane == 0) atomicAdd(a.nan_rows, static_cast<unsigned long long>(nan_rows));
+    if (nan_rows && lane == 0) atomicAdd(&a.sync->nan_rows, static_cast<unsigned long long>(nan_rows));
     if (WRITE_ALL) return;
 
     // every issued copy has been consumed (each full barrier was waited on), so
@@ -345,6 +347,9 @@ __global__ void __launch_bounds__(CFG::THREADS, 1) scan_tma_kernel(const ScanArg
     __syncthreads();
     emit_cta_list<KPL>(scratch, CFG::CONSUMER_WARPS,
                        a.cand + static_cast<size_t>(blockIdx.x) * a.cand_stride, tid, CFG::THREADS);
+    if (!a.fuse_tail) return;
+    if (!last_cta_done(&a.sync->done_counter, tid)) return;
+    merge_decode_reset<32 * KPL>(a.cand, static_cast<int>(gridDim.x), scratch, a.dec, a.sync, tid, CFG::THREADS);
 }
 
 // ---- direct-load variant, any dim -----------------------------------------------
@@ -423,7 +428,7 @@ __global__ void __launch_bounds__(LDG_THREADS) scan_ldg_kernel(const ScanArgs a)
         offer_row<KPL, METRIC, WRITE_ALL>(t0, t1, sqrt_b, rsqrt_b, pos, top, nan_rows, a.all_keys, lane);
     }
 
-    if (nan_rows && lane == 0) atomicAdd(a.nan_rows, static_cast<unsigned long long>(nan_rows));
+    if (nan_rows && lane == 0) atomicAdd(&a.sync->nan_rows, static_cast<unsigned long long>(nan_rows));
     if (WRITE_ALL) return;
 
     top.dump(scratch + warp * 32 * KPL, lane);

@@ -292,6 +292,16 @@ class GpuIndex:
                                                  ctypes.c_void_p(scores.ctypes.data), ctypes.byref(n)))
         return ids[:n.value].copy(), scores[:n.value].copy()
 
+    def binary_search_device(self, d_query_words, k: int, out_ids, out_scores, out_n,
+                             score_mode: str = "reference", use_mask: bool = False) -> None:
+        """Async: torch CUDA tensors (query: 36 packed 32-bit words; outputs int64 ``[k]``, int32 ``[k]``,
+        int32 ``[1]``), enqueued on the context's stream."""
+        modes = {"reference": _lib.SCORE_REFERENCE_UINT8, "popcount": _lib.SCORE_POPCOUNT}
+        self._check(self._L.clipdb_binary_search_device(
+            self._ctx, ctypes.c_void_p(d_query_words.data_ptr()), int(k), modes[score_mode], int(bool(use_mask)),
+            ctypes.c_void_p(out_ids.data_ptr()), ctypes.c_void_p(out_scores.data_ptr()),
+            ctypes.c_void_p(out_n.data_ptr())))
+
     # ---- query arithmetic -----------------------------------------------------------------
     @staticmethod
     def _pack_negatives(negatives, negative_weights, dim):
