@@ -58,6 +58,9 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--sample-stride", type=int, default=0, help="batch: pass A sampling stride (0 = auto)")
     ap.add_argument("--no-refine", action="store_true", help="batch: skip the second threshold")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: fused = the scan kernel's last CTA exchanges candidates over NVLink peer memory "
+                         "and merges (one launch per rank); nccl = all-gather + merge kernel")
     ap.add_argument("--variant", type=int, default=0, help="scan kernel: 0 auto, 1 TMA ring, 2 direct loads")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-rows", type=int, default=100_000)
@@ -80,6 +83,8 @@ def workload_config(args, rows_per_gpu, n_gpus):
         "l2": "inputs_larger_than_L2",
         "parallelism": "row-shard x%d" % n_gpus if n_gpus > 1 else "single GPU",
     }
+    if getattr(args, "exchange_used", None):
+        cfg["exchange"] = args.exchange_used
     if n_gpus in (2, 4):
         cfg["note"] = "100M fp32 rows do not fit %d GPUs (%.1f GB/GPU); weak-scaled shard of 12.5M rows/GPU" % (
             n_gpus, 100e6 * ROW_BYTES / n_gpus / 1e9)
@@ -516,7 +521,9 @@ def main():
     idx.attach(rows, rowid_base=1 + rank * rows_per_gpu)
     idx.set_option("scan_variant", args.variant)
     backend = CudaShardBackend(idx)          # puts the context on torch's current stream
-    sharded = ShardedIndex(backend)
+    sharded = ShardedIndex(backend, fused=(args.exchange == "fused")) if world > 1 else ShardedIndex(backend)
+    args.exchange_used = ("fused peer-memory exchange in the scan kernel" if sharded.fused else
+                          "NCCL all-gather + merge kernel") if world > 1 else "none (single GPU)"
 
     if args.workload == "batch":
         return run_batch_workload(args, torch, idx, rows, rows_per_gpu, device, rank, local_rank)

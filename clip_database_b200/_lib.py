@@ -18,6 +18,7 @@ METRIC_COSINE = 0
 METRIC_L2 = 1
 SCORE_REFERENCE_UINT8 = 0   # popcount(q AND row) modulo 256, as numpy's uint8 dot product gives
 SCORE_POPCOUNT = 1
+IPC_HANDLE_BYTES = 64
 BLEND_POSITIVE_ZERO_NORM = 1
 BLEND_NEGATIVE_ZERO_NORM = 2
 ABI_VERSION = 2
@@ -68,6 +69,11 @@ SIGNATURES = [
     ("clipdb_binary_search", c_int, [_CTX, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     ("clipdb_binary_search_device", c_int, [_CTX, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                             c_void_p]),
+    ("clipdb_exchange_init", c_int, [_CTX, c_int32, c_int32, c_void_p, c_void_p]),
+    ("clipdb_exchange_connect", c_int, [_CTX, c_void_p]),
+    ("clipdb_exchange_connect_pointers", c_int, [_CTX, c_void_p, c_void_p]),
+    ("clipdb_search_sharded_device", c_int, [_CTX, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                             c_void_p]),
     ("clipdb_merge_device", c_int, [_CTX, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                     c_void_p, c_void_p, c_void_p]),
     ("clipdb_merge_strided_device", c_int, [_CTX, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,

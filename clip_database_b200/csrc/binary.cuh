@@ -212,7 +212,8 @@ __global__ void __launch_bounds__(BIN_THREADS, 1) binary_scan_kernel(const Binar
                        BIN_THREADS);
     if (!a.fuse_tail) return;
     if (!last_cta_done(&a.sync->done_counter, tid)) return;
-    merge_decode_reset<32 * KPL>(a.cand, static_cast<int>(gridDim.x), scratch, a.dec, a.sync, tid, BIN_THREADS);
+    ExchangeArgs none{};
+    merge_decode_reset<32 * KPL>(a.cand, static_cast<int>(gridDim.x), scratch, a.dec, none, a.sync, tid, BIN_THREADS);
 }
 
 }  // namespace clipdb

@@ -68,6 +68,15 @@ struct clipdb_ctx {
     int64_t *code_ids_by_seq = nullptr;  // ids indexed by that sequence
     Buffer d_code_query, code_stage, code_bad;
 
+    // fused shard exchange (merge.cuh): own inbox + every rank's inbox as mapped in this process
+    ExchangeSlot *xchg_inbox = nullptr;
+    ExchangeSlot *xchg_peer[XCHG_MAX_WORLD] = {};
+    bool xchg_ipc[XCHG_MAX_WORLD] = {};       // peer pointer came from cudaIpcOpenMemHandle
+    int xchg_world = 0, xchg_rank = 0;
+    bool xchg_connected = false;
+    uint32_t xchg_epoch = 0;
+    int64_t xchg_timeout_ms = 10000;
+
     // workspaces (grown on demand)
     Buffer cand_a, cand_b, sync_buf, all_keys_a, all_keys_b, cub_tmp;
     bool sync_dirty = true;   // the scan kernels' counters may be non-zero
@@ -209,6 +218,19 @@ void release_store(clipdb_ctx *c) {
     c->mask_words = 0;
     c->batch_enabled = false;   // the bf16 copy described the old rows
     free_buffer(c->bf16_rows);
+}
+
+void release_exchange(clipdb_ctx *c) {
+    for (int r = 0; r < XCHG_MAX_WORLD; r++) {
+        if (c->xchg_ipc[r] && c->xchg_peer[r]) cudaIpcCloseMemHandle(c->xchg_peer[r]);
+        c->xchg_peer[r] = nullptr;
+        c->xchg_ipc[r] = false;
+    }
+    if (c->xchg_inbox) cudaFree(c->xchg_inbox);
+    c->xchg_inbox = nullptr;
+    c->xchg_world = 0;
+    c->xchg_connected = false;
+    cudaGetLastError();
 }
 
 void release_codes(clipdb_ctx *c) {
@@ -435,8 +457,11 @@ int prepare_sync(clipdb_ctx *c, ScanSync **out) {
 // one query: ONE launch (TMA scan with the fused merge/decode tail, k <= FUSED_K_MAX), or
 // scan + merge tree (direct-load kernel), or scan + radix sort (any k)
 int search_one(clipdb_ctx *c, const float *d_query, int k, int metric, bool use_mask,
-               int64_t *d_out_rowids, float *d_out_dist, int32_t *d_out_n, int64_t *d_out_nan) {
+               int64_t *d_out_rowids, float *d_out_dist, int32_t *d_out_n, int64_t *d_out_nan,
+               const ExchangeArgs *xa = nullptr) {
     const int64_t kk = k < c->n ? k : c->n;
+    if (xa && (kk <= 0 || k > FUSED_K_MAX))
+        return fail(c, CLIPDB_ERR_UNSUPPORTED, "sharded search: needs 1 <= k <= %d and a non-empty shard", FUSED_K_MAX);
     if (kk <= 0) {
         CU_TRY(c, cudaMemsetAsync(d_out_n, 0, sizeof(int32_t), c->stream));
         if (d_out_nan) CU_TRY(c, cudaMemsetAsync(d_out_nan, 0, sizeof(int64_t), c->stream));
@@ -479,6 +504,12 @@ int search_one(clipdb_ctx *c, const float *d_query, int k, int metric, bool use_
                                                    : ScanCfg3::STAGES * ScanCfg3::STAGE_BYTES;
         a.fuse_tail = tma && c->fuse_tail && static_cast<size_t>(grid) * stride * sizeof(uint64_t) <= ring_bytes;
         a.dec = dec;
+        if (xa) {
+            if (!a.fuse_tail)
+                return fail(c, CLIPDB_ERR_UNSUPPORTED, "sharded search: needs the TMA scan kernel with its fused tail "
+                                                       "(dim 1152, option fuse_tail = 1)");
+            a.xchg = *xa;
+        }
         switch (kpl) {
             case 1: RC_TRY((launch_scan_metric<1, false>(c, a, metric, tma, grid))); break;
             case 2: RC_TRY((launch_scan_metric<2, false>(c, a, metric, tma, grid))); break;
@@ -943,6 +974,7 @@ void clipdb_destroy(clipdb_ctx *c) {
         cudaStreamSynchronize(c->stream);
         release_store(c);
         release_codes(c);
+        release_exchange(c);
         Buffer *bufs[] = {&c->d_code_query, &c->code_stage, &c->code_bad, &c->cand_a, &c->cand_b, &c->sync_buf, &c->all_keys_a, &c->all_keys_b,
                           &c->cub_tmp, &c->d_query, &c->d_out_rowids, &c->d_out_dist, &c->d_out_n,
                           &c->d_out_nan, &c->d_blend_in, &c->d_blend_flags, &c->bf16_rows,
@@ -999,6 +1031,7 @@ static int64_t *option_slot(clipdb_ctx *c, const char *name) {
     if (!strcmp(name, "scan_assign")) return &c->scan_assign;
     if (!strcmp(name, "scan_chunk")) return &c->scan_chunk;
     if (!strcmp(name, "fuse_tail")) return &c->fuse_tail;
+    if (!strcmp(name, "xchg_timeout_ms")) return &c->xchg_timeout_ms;
     if (!strcmp(name, "batch_min_nq")) return &c->batch_min_nq;
     if (!strcmp(name, "batch_cand_cap")) return &c->batch_cand_cap;
     if (!strcmp(name, "batch_cta_pair")) return &c->batch_cta_pair;
@@ -1511,6 +1544,99 @@ int clipdb_binary_search(clipdb_ctx *c, const uint8_t *query_code, int32_t k, in
                                        static_cast<int32_t *>(c->d_out_n.p)));
     CU_TRY(c, cudaMemsetAsync(c->d_out_nan.p, 0, sizeof(int64_t), c->stream));
     return fetch_results(c, 1, kcols, out_ids, reinterpret_cast<float *>(out_scores), out_n, nullptr);
+}
+
+// ---- fused shard exchange -----------------------------------------------------------------
+
+int clipdb_exchange_init(clipdb_ctx *c, int32_t world, int32_t rank, void *out_ipc_handle, void **out_inbox) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (world < 1 || world > XCHG_MAX_WORLD || rank < 0 || rank >= world)
+        return fail(c, CLIPDB_ERR_INVALID, "exchange_init: world must be 1..%d and 0 <= rank < world", XCHG_MAX_WORLD);
+    DeviceGuard g(c->device);
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    release_exchange(c);
+    const size_t bytes = static_cast<size_t>(2) * world * sizeof(ExchangeSlot);
+    CU_TRY(c, cudaMalloc(reinterpret_cast<void **>(&c->xchg_inbox), bytes));
+    CU_TRY(c, cudaMemset(c->xchg_inbox, 0, bytes));
+    c->xchg_world = world;
+    c->xchg_rank = rank;
+    c->xchg_epoch = 0;
+    c->xchg_peer[rank] = c->xchg_inbox;
+    c->xchg_connected = world == 1;
+    if (out_ipc_handle) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == CLIPDB_IPC_HANDLE_BYTES, "IPC handle size");
+        cudaIpcMemHandle_t h;
+        CU_TRY(c, cudaIpcGetMemHandle(&h, c->xchg_inbox));
+        memcpy(out_ipc_handle, &h, sizeof h);
+    }
+    if (out_inbox) *out_inbox = c->xchg_inbox;
+    return CLIPDB_OK;
+}
+
+int clipdb_exchange_connect(clipdb_ctx *c, const void *ipc_handles) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->xchg_inbox) return fail(c, CLIPDB_ERR_STATE, "exchange_connect: call exchange_init first");
+    if (!ipc_handles) return fail(c, CLIPDB_ERR_INVALID, "exchange_connect: null handles");
+    DeviceGuard g(c->device);
+    for (int r = 0; r < c->xchg_world; r++) {
+        if (r == c->xchg_rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const uint8_t *>(ipc_handles) + static_cast<size_t>(r) * sizeof h, sizeof h);
+        void *p = nullptr;
+        CU_TRY(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        c->xchg_peer[r] = static_cast<ExchangeSlot *>(p);
+        c->xchg_ipc[r] = true;
+    }
+    c->xchg_connected = true;
+    return CLIPDB_OK;
+}
+
+int clipdb_exchange_connect_pointers(clipdb_ctx *c, void *const *inboxes, const int32_t *devices) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->xchg_inbox) return fail(c, CLIPDB_ERR_STATE, "exchange_connect: call exchange_init first");
+    if (!inboxes) return fail(c, CLIPDB_ERR_INVALID, "exchange_connect: null pointers");
+    DeviceGuard g(c->device);
+    for (int r = 0; r < c->xchg_world; r++) {
+        if (r == c->xchg_rank) continue;
+        if (!inboxes[r]) return fail(c, CLIPDB_ERR_INVALID, "exchange_connect: inbox %d is null", r);
+        if (devices && devices[r] != c->device) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(devices[r], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return fail(c, CLIPDB_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d) failed: %s", devices[r],
+                            cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+        c->xchg_peer[r] = static_cast<ExchangeSlot *>(inboxes[r]);
+        c->xchg_ipc[r] = false;
+    }
+    c->xchg_connected = true;
+    return CLIPDB_OK;
+}
+
+int clipdb_search_sharded_device(clipdb_ctx *c, const float *d_query, int32_t k, int32_t metric, int32_t use_mask,
+                                 int64_t *d_out_rowids, float *d_out_dist, int32_t *d_out_n, int64_t *d_out_nan) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->xchg_connected) return fail(c, CLIPDB_ERR_STATE, "sharded search: exchange not connected");
+    if (!c->rows || c->dim == 0) return fail(c, CLIPDB_ERR_STATE, "no rows loaded");
+    if (!d_query || !d_out_rowids || !d_out_dist || !d_out_n) return fail(c, CLIPDB_ERR_INVALID, "sharded search: null pointer");
+    if (metric != CLIPDB_METRIC_COSINE && metric != CLIPDB_METRIC_L2)
+        return fail(c, CLIPDB_ERR_INVALID, "search: unknown metric %d", metric);
+    if (use_mask && !c->mask) return fail(c, CLIPDB_ERR_STATE, "search: use_mask set but no mask installed");
+    DeviceGuard g(c->device);
+    ExchangeArgs xa{};
+    for (int r = 0; r < c->xchg_world; r++) xa.inbox[r] = c->xchg_peer[r];
+    xa.world = c->xchg_world;
+    xa.rank = c->xchg_rank;
+    xa.k = k;
+    if (++c->xchg_epoch == 0) c->xchg_epoch = 1;   // 0 means "never written"
+    xa.epoch = c->xchg_epoch;
+    xa.timeout_ns = static_cast<unsigned long long>(c->xchg_timeout_ms) * 1000000ull;
+    if (xa.world == 1) return search_one(c, d_query, k, metric, use_mask != 0, d_out_rowids, d_out_dist, d_out_n, d_out_nan);
+    return search_one(c, d_query, k, metric, use_mask != 0, d_out_rowids, d_out_dist, d_out_n, d_out_nan, &xa);
 }
 
 int clipdb_merge_batch_device(clipdb_ctx *c, const void *d_dist, int64_t dist_stride, int64_t dist_qstride,

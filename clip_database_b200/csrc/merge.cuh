@@ -86,13 +86,155 @@ struct ScanSync {
     unsigned long long nan_rows;      // admitted rows whose distance was NaN
 };
 
+// ---- fused shard exchange (multi-GPU) --------------------------------------------
+// Row-sharded search needs one exchange step: every GPU's k best (distance, rowid) pairs must
+// reach every GPU and be merged.  Instead of ending the kernel, calling an NCCL all-gather and
+// launching a merge, the scan kernel's last CTA does it itself over NVLink peer memory:
+//   1. it decodes its shard's merged list and STORES it straight into slot [my rank] of every
+//      peer's inbox (the inboxes are cudaMalloc'ed buffers mapped into every process with CUDA
+//      IPC; 8 x 252 B at k = 20),
+//   2. __threadfence_system, then st.release.sys of the query's epoch number into each slot,
+//   3. ld.acquire.sys-spins on the G slots of its OWN inbox until they carry this epoch
+//      (bounded by a timeout: a missing peer becomes an error code, never a hung GPU),
+//   4. sorts the G x k keys (distance, shard, position) = (distance, rowid) and decodes.
+// So a sharded query is ONE launch per GPU with no host round trip and no collective call.
+// Two inbox banks alternate by epoch parity: a peer can be at most one query ahead (it needs
+// this rank's record of query e to finish e), so bank (e+1)&1 is never read while written.
+constexpr int XCHG_MAX_WORLD = 16;
+constexpr int XCHG_K = 128;   // largest k of the fused path
+
+struct ExchangeSlot {
+    uint32_t epoch;
+    int32_t count;
+    long long nan;
+    float dist[XCHG_K];
+    long long rowid[XCHG_K];
+};
+
+struct ExchangeArgs {
+    ExchangeSlot *inbox[XCHG_MAX_WORLD];   // inbox[r] = rank r's inbox [2 banks][world slots], as mapped here
+    int world;                             // 0: no exchange
+    int rank;
+    int k;                                 // requested (global) k
+    uint32_t epoch;                        // same on every rank for the same query, never 0
+    unsigned long long timeout_ns;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// scratch[0 .. L) holds this shard's merged ascending list (the tournament's result).
+template <int L>
+__device__ __forceinline__ void exchange_merge_decode(uint64_t *scratch, const DecodeArgs &dec,
+                                                      const ExchangeArgs &xa, ScanSync *sync, int tid, int nthreads) {
+    __shared__ long long s_nan;
+    const int k = xa.k, G = xa.world, bank = static_cast<int>(xa.epoch & 1u);
+    int mine = 0;
+    for (int base = 0; base < k; base += nthreads) {
+        const int i = base + tid;
+        mine += __syncthreads_count(i < k && i < L && scratch[i] != KEY_EMPTY);
+    }
+    if (tid == 0) s_nan = static_cast<long long>(atomicExch(&sync->nan_rows, 0ull));
+    __syncthreads();
+    // 1. this shard's record into slot [rank] of every inbox (peer stores go over NVLink)
+    for (int w = tid; w < G * k; w += nthreads) {
+        const int r = w / k, j = w - r * k;
+        if (j < mine) {
+            ExchangeSlot *slot = xa.inbox[r] + bank * G + xa.rank;
+            const uint64_t key = scratch[j];
+            const uint32_t pos = static_cast<uint32_t>(key & 0xFFFFFFFFull);
+            slot->dist[j] = orderable_f32(static_cast<uint32_t>(key >> 32));
+            slot->rowid[j] = dec.rowids ? dec.rowids[pos] : dec.rowid_base + static_cast<int64_t>(pos);
+        }
+    }
+    if (tid < G) {
+        ExchangeSlot *slot = xa.inbox[tid] + bank * G + xa.rank;
+        slot->count = mine;
+        slot->nan = s_nan;
+    }
+    // 2. publish
+    __threadfence_system();
+    __syncthreads();
+    if (tid < G) st_release_sys(&(xa.inbox[tid] + bank * G + xa.rank)->epoch, xa.epoch);
+    // 3. wait for every shard's record in the own inbox
+    const ExchangeSlot *own = xa.inbox[xa.rank] + bank * G;
+    bool late = false;
+    if (tid < G) {
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(&own[tid].epoch) != xa.epoch) {
+            if (global_timer_ns() - t0 > xa.timeout_ns) {
+                late = true;
+                break;
+            }
+            __nanosleep(200);
+        }
+    }
+    if (__syncthreads_count(late)) {
+        if (tid == 0) {
+            *dec.out_n = -1;   // a peer never delivered: reported by the host as an error
+            sync->tile_counter = 0;
+            sync->done_counter = 0;
+        }
+        return;
+    }
+    // 4. merge: key = (distance, shard, position in the shard's list) = (distance, rowid)
+    const int total = G * k, padded = next_pow2(total);
+    for (int i = tid; i < padded; i += nthreads) {
+        uint64_t key = KEY_EMPTY;
+        if (i < total) {
+            const int l = i / k, p = i - l * k;
+            if (p < __ldcg(&own[l].count)) key = make_key(__ldcg(&own[l].dist[p]), static_cast<uint32_t>(i));
+        }
+        scratch[i] = key;
+    }
+    block_bitonic_sort(scratch, padded, tid, nthreads);
+    int found = 0;
+    for (int base = 0; base < k; base += nthreads) {
+        const int i = base + tid;
+        const bool valid = i < k && i < padded && scratch[i] != KEY_EMPTY;
+        if (valid) {
+            const int src = static_cast<int>(scratch[i] & 0xFFFFFFFFull);
+            const int l = src / k, p = src - l * k;
+            dec.out_dist[i] = __ldcg(&own[l].dist[p]);
+            dec.out_rowids[i] = __ldcg(&own[l].rowid[p]);
+        }
+        found += __syncthreads_count(valid);
+    }
+    if (tid == 0) {
+        *dec.out_n = found;
+        if (dec.out_nan) {
+            long long nan = 0;
+            for (int l = 0; l < G; l++) nan += __ldcg(&own[l].nan);
+            *dec.out_nan = nan;
+        }
+        sync->tile_counter = 0;
+        sync->done_counter = 0;
+    }
+}
+
 // lists: [n_lists][L] in global memory (written by other CTAs: read through L2), scratch: shared
 template <int L>
 __device__ __forceinline__ void merge_decode_reset(const uint64_t *lists, int n_lists, uint64_t *scratch,
-                                                   const DecodeArgs &dec, ScanSync *sync, int tid, int nthreads) {
+                                                   const DecodeArgs &dec, const ExchangeArgs &xa, ScanSync *sync,
+                                                   int tid, int nthreads) {
     for (int i = tid; i < n_lists * L; i += nthreads) scratch[i] = __ldcg(lists + i);
     __syncthreads();
     merge_sorted_lists_tournament<L>(scratch, n_lists, tid, nthreads);
+    if (xa.world > 1) {
+        exchange_merge_decode<L>(scratch, dec, xa, sync, tid, nthreads);
+        return;
+    }
     int found = 0;
     for (int base = 0; base < dec.k; base += nthreads) {
         const int i = base + tid;

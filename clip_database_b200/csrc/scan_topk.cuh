@@ -82,6 +82,7 @@ struct ScanArgs {
     int chunk_tiles;  // tiles claimed per atomicAdd (dynamic assignment)
     int fuse_tail;    // the last CTA to finish merges all lists and decodes the result (TMA kernel)
     DecodeArgs dec;   // used when fuse_tail != 0
+    ExchangeArgs xchg;  // world > 1: the tail also exchanges the result with the other shards' GPUs
 };
 
 // The exact finish (double sqrt, multiply, divide) is ~70 instructions.  A float32
@@ -349,7 +350,8 @@ __global__ void __launch_bounds__(CFG::THREADS, 1) scan_tma_kernel(const ScanArg
                        a.cand + static_cast<size_t>(blockIdx.x) * a.cand_stride, tid, CFG::THREADS);
     if (!a.fuse_tail) return;
     if (!last_cta_done(&a.sync->done_counter, tid)) return;
-    merge_decode_reset<32 * KPL>(a.cand, static_cast<int>(gridDim.x), scratch, a.dec, a.sync, tid, CFG::THREADS);
+    merge_decode_reset<32 * KPL>(a.cand, static_cast<int>(gridDim.x), scratch, a.dec, a.xchg, a.sync, tid,
+                                 CFG::THREADS);
 }
 
 // ---- direct-load variant, any dim -----------------------------------------------

@@ -466,6 +466,37 @@ class GpuIndex:
             ctypes.c_void_p(base + off_rowids), ctypes.c_void_p(base + off_dist),
             ctypes.c_void_p(base + off_count), ctypes.c_void_p(base + off_nan)))
 
+    # ---- fused shard exchange (one launch per sharded query, no collective call) ---------------
+    def exchange_init(self, world: int, rank: int) -> Tuple[bytes, int]:
+        """Allocate this rank's inbox.  Returns (CUDA IPC handle bytes for the other processes,
+        raw device pointer for ranks living in this process)."""
+        handle = (ctypes.c_uint8 * _lib.IPC_HANDLE_BYTES)()
+        ptr = ctypes.c_void_p()
+        self._check(self._L.clipdb_exchange_init(self._ctx, int(world), int(rank), handle, ctypes.byref(ptr)))
+        return bytes(handle), int(ptr.value)
+
+    def exchange_connect(self, handles: Sequence[bytes]) -> None:
+        """``handles``: every rank's IPC handle in rank order (one process per GPU)."""
+        blob = b"".join(handles)
+        buf = (ctypes.c_uint8 * len(blob)).from_buffer_copy(blob)
+        self._check(self._L.clipdb_exchange_connect(self._ctx, buf))
+
+    def exchange_connect_pointers(self, inboxes: Sequence[int], devices: Optional[Sequence[int]] = None) -> None:
+        """Same-process variant: every rank's inbox pointer (and CUDA device) in rank order."""
+        ptrs = (ctypes.c_void_p * len(inboxes))(*[ctypes.c_void_p(int(p)) for p in inboxes])
+        devs = (ctypes.c_int32 * len(inboxes))(*[int(d) for d in devices]) if devices is not None else None
+        self._check(self._L.clipdb_exchange_connect_pointers(self._ctx, ptrs, devs))
+
+    def search_sharded_device(self, d_query, k: int, out_rowids, out_dist, out_n, out_nan=None,
+                              metric="cosine", use_mask: bool = False) -> None:
+        """Async: this shard's scan + exchange with the peer GPUs + merge in ONE launch; the outputs
+        (torch CUDA tensors, int64 ``[k]``, float32 ``[k]``, int32 ``[1]``, int64 ``[1]``) hold the
+        answer over ALL shards.  ``out_n == -1``: a peer did not deliver in time."""
+        self._check(self._L.clipdb_search_sharded_device(
+            self._ctx, ctypes.c_void_p(d_query.data_ptr()), int(k), _metric(metric), int(bool(use_mask)),
+            ctypes.c_void_p(out_rowids.data_ptr()), ctypes.c_void_p(out_dist.data_ptr()),
+            ctypes.c_void_p(out_n.data_ptr()), ctypes.c_void_p(out_nan.data_ptr() if out_nan is not None else 0)))
+
     def merge_device(self, d_dist, d_rowids, d_counts, k: int, out_dist, out_rowids, out_n) -> None:
         """Async shard merge of ``[lists, k]`` gathered results (clipdb_merge_device)."""
         lists = d_dist.shape[0]

@@ -115,6 +115,19 @@ class CudaShardBackend:
         self.index.search_into_record(d_query, k, record, lay.off_rowids, lay.off_dist, lay.off_count,
                                       lay.off_nan, use_mask=use_mask)
 
+    # ---- fused exchange: scan + peer-memory exchange + merge in one launch per rank ----------
+    def connect_exchange(self, dist, group, world: int, rank: int) -> None:
+        """Allocate this rank's inbox, swap CUDA IPC handles with the other ranks (a host-side
+        all_gather_object, once) and map their inboxes.  Raises if peer mapping is impossible."""
+        handle, _ = self.index.exchange_init(world, rank)
+        handles = [None] * world
+        dist.all_gather_object(handles, handle, group=group)
+        self.index.exchange_connect(handles)
+        dist.barrier(group=group)
+
+    def fused_search(self, d_query, k: int, out_dist, out_rowids, out_n, out_nan, use_mask: bool) -> None:
+        self.index.search_sharded_device(d_query, k, out_rowids, out_dist, out_n, out_nan, use_mask=use_mask)
+
     def merge(self, gathered, k: int, lay: RecordLayout, out_dist, out_rowids, out_n) -> None:
         self.index.merge_records_device(gathered, k, lay.off_rowids, lay.off_dist, lay.off_count,
                                         out_dist, out_rowids, out_n)
@@ -164,6 +177,7 @@ class CudaShardBackend:
         self._out = t.zeros(lay.nbytes, dtype=t.uint8, device=self.device)
         self._h_out = t.zeros(lay.nbytes, dtype=t.uint8).pin_memory()
         kk = max(k, 1)
+        self.out_nan = self._out[lay.off_nan:lay.off_nan + 8].view(t.int64)
         return (self._out[lay.off_dist:lay.off_dist + 4 * kk].view(t.float32),
                 self._out[lay.off_rowids:lay.off_rowids + 8 * kk].view(t.int64),
                 self._out[lay.off_count:lay.off_count + 4].view(t.int32))
@@ -175,6 +189,9 @@ class CudaShardBackend:
         self.torch.cuda.current_stream(self.device).synchronize()
         h = self._h_out.numpy()
         m = int(h[lay.off_count:lay.off_count + 4].view(np.int32)[0])
+        if m < 0:
+            raise RuntimeError("sharded search: a peer GPU did not deliver its candidates in time "
+                               "(option xchg_timeout_ms); every rank must issue the same searches")
         ids = h[lay.off_rowids:lay.off_rowids + 8 * m].view(np.int64).copy()
         d = h[lay.off_dist:lay.off_dist + 4 * m].view(np.float32).copy()
         return ids, d
@@ -183,7 +200,12 @@ class CudaShardBackend:
 class ShardedIndex:
     """One rank's view of a row-sharded store."""
 
-    def __init__(self, backend, group=None):
+    FUSED_K_MAX = 128
+
+    def __init__(self, backend, group=None, fused="auto"):
+        """``fused``: True = single-query searches go through the fused peer-memory exchange
+        (one launch per rank, no collective), False = local search + NCCL all-gather + merge
+        kernel, "auto" = fused when the backend can map its peers' memory."""
         import torch.distributed as dist
         self.backend = backend
         self.dist = dist
@@ -191,6 +213,19 @@ class ShardedIndex:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._k = None
+        self.fused = False
+        if fused and self.world > 1 and hasattr(backend, "connect_exchange"):
+            ok = 1
+            try:
+                backend.connect_exchange(dist, group, self.world, self.rank)
+            except Exception:
+                if fused is True:
+                    raise
+                ok = 0
+            # every rank must take the same path
+            flags = [None] * self.world
+            dist.all_gather_object(flags, ok, group=group)
+            self.fused = all(flags)
 
     def _prepare(self, k: int) -> None:
         if self._k == k:
@@ -206,6 +241,10 @@ class ShardedIndex:
         (dist[k], rowids[k], n[1]) valid after the stream / collective completes;
         every rank holds the same merged answer."""
         self._prepare(k)
+        if self.fused and 1 <= k <= self.FUSED_K_MAX:
+            self.backend.fused_search(d_query, k, self.out_dist, self.out_rowids, self.out_n, self.backend.out_nan,
+                                      use_mask)
+            return self.out_dist, self.out_rowids, self.out_n
         self.backend.local_search(d_query, k, self.record, self.layout, use_mask)
         if self.world > 1:
             self.dist.all_gather_into_tensor(self.gathered.view(-1), self.record, group=self.group)
@@ -237,6 +276,8 @@ class ShardedIndex:
 
     def nan_rows(self) -> int:
         """Admitted rows with NaN distance over all shards for the last search."""
+        if self.fused and self._k is not None and 1 <= self._k <= self.FUSED_K_MAX:
+            return int(self.backend.out_nan.cpu()[0])
         src = self.gathered if self.world > 1 else self.record.view(1, -1)
         return int(src[:, :8].contiguous().view(-1).cpu().numpy().view(np.int64).sum())
 

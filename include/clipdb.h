@@ -253,6 +253,34 @@ int clipdb_merge_batch_device(clipdb_ctx *ctx, const void *d_dist, int64_t dist_
                               int32_t lists, int32_t nq, int32_t k,
                               float *d_out_dist, int64_t *d_out_rowids, int32_t *d_out_n);
 
+/* ---- fused shard exchange (multi-GPU, one launch per query) ---------------------------------
+ * No reference equivalent.  With the exchange connected, clipdb_search_sharded_device answers a
+ * query over ALL shards in one kernel launch per GPU: the scan kernel's last CTA stores its
+ * shard's k best (distance, rowid) pairs directly into every peer GPU's inbox over NVLink
+ * (peer memory mapped with CUDA IPC), signals with a system-scope release, waits for the other
+ * shards' records with acquire loads and merges — no NCCL call and no host round trip between
+ * the scan and the merged result.  Every rank ends up with the same answer, identical to the
+ * unsharded one (shards are contiguous rowid ranges, rank order = rowid order).
+ *
+ *   clipdb_exchange_init      allocates this rank's inbox; out_ipc_handle (nullable) receives
+ *                             CLIPDB_IPC_HANDLE_BYTES bytes to hand to the other ranks (e.g. with
+ *                             torch.distributed.all_gather_object), out_inbox (nullable) the raw
+ *                             device pointer (for ranks living in the same process).
+ *   clipdb_exchange_connect   world x CLIPDB_IPC_HANDLE_BYTES handle bytes in rank order
+ *                             (one process per GPU; the own slot is ignored).
+ *   clipdb_exchange_connect_pointers  same-process variant: inbox pointers (and their CUDA
+ *                             devices, nullable = same device) in rank order.
+ *   clipdb_search_sharded_device      device pointers, async; EVERY rank must issue the same
+ *                             sequence of calls.  Needs dim 1152, 1 <= k <= 128, a non-empty shard.
+ *                             If a peer does not deliver within option "xchg_timeout_ms"
+ *                             (default 10 s) *d_out_n is set to -1 instead of hanging the GPU. */
+#define CLIPDB_IPC_HANDLE_BYTES 64
+int clipdb_exchange_init(clipdb_ctx *ctx, int32_t world, int32_t rank, void *out_ipc_handle, void **out_inbox);
+int clipdb_exchange_connect(clipdb_ctx *ctx, const void *ipc_handles);
+int clipdb_exchange_connect_pointers(clipdb_ctx *ctx, void *const *inboxes, const int32_t *devices);
+int clipdb_search_sharded_device(clipdb_ctx *ctx, const float *d_query, int32_t k, int32_t metric, int32_t use_mask,
+                                 int64_t *d_out_rowids, float *d_out_dist, int32_t *d_out_n, int64_t *d_out_nan);
+
 /* ---- measurement ------------------------------------------------------------
  * With profiling enabled every scan kernel (the dominant, HBM-bound launch) is
  * bracketed by CUDA events on the launching stream; clipdb_profile_read syncs

@@ -1,0 +1,106 @@
+"""Fused shard exchange (clipdb_search_sharded_device): the scan kernel's last CTA pushes its
+shard's top-k into every peer's inbox, waits for theirs and merges — one launch per shard, no
+collective.  On a 1-GPU box the ranks are contexts on the SAME device (small grids so the
+kernels are co-resident) wired with raw pointers; the multi-process CUDA-IPC wiring over NVLink
+is covered by tests/test_gpu_sharded.py on >= 2 GPUs."""
+import threading
+
+import numpy as np
+import pytest
+
+from clip_database_b200 import synth
+from clip_database_b200.sharded import shard_bounds
+
+from conftest import have_gpu
+
+pytestmark = pytest.mark.gpu
+DIM = 1152
+
+
+def run_ranks(torch, shards, fn):
+    """fn(rank, idx, stream) on one thread per rank (ctypes releases the GIL)."""
+    errs = []
+
+    def work(r):
+        try:
+            fn(r, shards[r])
+        except Exception as e:      # noqa: BLE001
+            errs.append((r, e))
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(len(shards))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+
+
+@pytest.mark.parametrize("world,k", [(2, 20), (3, 100), (4, 1)])
+def test_same_device_ranks_equal_unsharded(world, k):
+    assert have_gpu()
+    import torch
+    from clip_database_b200 import GpuIndex
+    n = 60_000
+    rows = synth.unit_rows(n, DIM, 1234)
+    rows[n - 1] = rows[3]                         # a cross-shard exact tie
+    rows[20_001] = 0                              # a NaN row in some shard
+    queries = synth.unit_rows(5, DIM, 99)
+    queries[4] = rows[3]
+    with GpuIndex(0) as whole:
+        whole.load(rows, np.arange(1, n + 1))
+        want = whole.search(queries, k)
+    bounds = shard_bounds(n, world)
+    shards, inboxes = [], []
+    try:
+        for r, (lo, hi) in enumerate(bounds):
+            s = GpuIndex(0)
+            s.load(rows[lo:hi], np.arange(lo + 1, hi + 1))
+            s.set_option("scan_ctas", max(148 // world // 2, 1))   # all ranks' kernels co-resident on one GPU
+            s.set_option("xchg_timeout_ms", 20000)
+            _, ptr = s.exchange_init(world, r)
+            shards.append(s)
+            inboxes.append(ptr)
+        for s in shards:
+            s.exchange_connect_pointers(inboxes, [0] * world)
+        d_q = torch.from_numpy(queries).cuda()
+        outs = [(torch.empty(k, dtype=torch.int64, device="cuda"), torch.empty(k, dtype=torch.float32, device="cuda"),
+                 torch.zeros(1, dtype=torch.int32, device="cuda"), torch.zeros(1, dtype=torch.int64, device="cuda"))
+                for _ in range(world)]
+        torch.cuda.synchronize()
+        for qi in range(queries.shape[0]):
+            def one(r, s, qi=qi):
+                o_ids, o_d, o_n, o_nan = outs[r]
+                s.search_sharded_device(d_q[qi], k, o_ids, o_d, o_n, o_nan)
+                s.synchronize()
+            run_ranks(torch, shards, one)
+            for r in range(world):
+                o_ids, o_d, o_n, o_nan = outs[r]
+                assert int(o_n[0]) == want.counts[qi], "a peer timed out" if int(o_n[0]) < 0 else "count"
+                assert np.array_equal(o_ids.cpu().numpy(), want.rowids[qi])
+                assert np.array_equal(o_d.cpu().numpy().view(np.uint32), want.distances[qi].view(np.uint32))
+                assert int(o_nan[0]) == want.nan_rows[qi]
+    finally:
+        for s in shards:
+            s.close()
+
+
+def test_missing_peer_times_out_instead_of_hanging():
+    assert have_gpu()
+    import torch
+    from clip_database_b200 import GpuIndex
+    rows = synth.unit_rows(5000, DIM, 1)
+    with GpuIndex(0) as a, GpuIndex(0) as b:
+        a.load(rows[:2500])
+        b.load(rows[2500:])
+        for r, s in enumerate((a, b)):
+            s.set_option("scan_ctas", 32)
+            s.set_option("xchg_timeout_ms", 300)
+        _, pa = a.exchange_init(2, 0)
+        _, pb = b.exchange_init(2, 1)
+        a.exchange_connect_pointers([pa, pb], [0, 0])
+        b.exchange_connect_pointers([pa, pb], [0, 0])
+        q = torch.from_numpy(synth.unit_rows(1, DIM, 2)).cuda()
+        o = (torch.empty(5, dtype=torch.int64, device="cuda"), torch.empty(5, dtype=torch.float32, device="cuda"),
+             torch.zeros(1, dtype=torch.int32, device="cuda"))
+        a.search_sharded_device(q[0], 5, o[0], o[1], o[2])      # rank 1 never searches
+        a.synchronize()
+        assert int(o[2][0]) == -1

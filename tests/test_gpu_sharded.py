@@ -30,13 +30,25 @@ rows[n - 1] = rows[3]
 lo, hi = shard_bounds(n, world)[rank]
 idx = GpuIndex(rank)
 idx.load(rows[lo:hi], np.arange(lo + 1, hi + 1))
-sh = ShardedIndex(CudaShardBackend(idx))
+backend = CudaShardBackend(idx)
+sh = ShardedIndex(backend, fused=True)         # scan + peer-memory exchange + merge in one launch per rank
+assert sh.fused
+sh_nccl = ShardedIndex(CudaShardBackend(idx), fused=False)   # local search + NCCL all-gather + merge kernel
 queries = synth.unit_rows(4, 1152, 99)
 queries[3] = rows[3]
 out = []
 for q in queries:
+    before = idx.launch_count
     ids, d = sh.search(q, k)
-    out.append((ids.tolist(), d.tolist(), sh.nan_rows()))
+    assert idx.launch_count - before == 1, "fused sharded search must be ONE launch"
+    nan = sh.nan_rows()
+    ids2, d2 = sh_nccl.search(q, k)
+    assert np.array_equal(ids, ids2) and np.array_equal(d.view(np.uint32), d2.view(np.uint32))
+    assert nan == sh_nccl.nan_rows()
+    out.append((ids.tolist(), d.tolist(), nan))
+ids100, d100 = sh.search(queries[0], 100)
+ids100n, d100n = sh_nccl.search(queries[0], 100)
+assert np.array_equal(ids100, ids100n) and np.array_equal(d100.view(np.uint32), d100n.view(np.uint32))
 n2 = 140_000
 rows2 = synth.unit_rows(n2, 1152, 77)
 lo2, hi2 = shard_bounds(n2, world)[rank]
