@@ -58,9 +58,10 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--sample-stride", type=int, default=0, help="batch: pass A sampling stride (0 = auto)")
     ap.add_argument("--no-refine", action="store_true", help="batch: skip the second threshold")
-    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "fused", "nccl"],
                     help="N > 1: fused = the scan kernel's last CTA exchanges candidates over NVLink peer memory "
-                         "and merges (one launch per rank); nccl = all-gather + merge kernel")
+                         "and merges (one launch per rank); nccl = all-gather + merge kernel; auto = fused when "
+                         "every rank can map its peers' memory, else nccl")
     ap.add_argument("--variant", type=int, default=0, help="scan kernel: 0 auto, 1 TMA ring, 2 direct loads")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-rows", type=int, default=100_000)
@@ -546,7 +547,7 @@ def main():
     idx.attach(rows, rowid_base=1 + rank * rows_per_gpu)
     idx.set_option("scan_variant", args.variant)
     backend = CudaShardBackend(idx)          # puts the context on torch's current stream
-    sharded = ShardedIndex(backend, fused=(args.exchange == "fused")) if world > 1 else ShardedIndex(backend)
+    sharded = ShardedIndex(backend, fused={"auto": "auto", "fused": True, "nccl": False}[args.exchange]) if world > 1 else ShardedIndex(backend)
     args.exchange_used = ("fused peer-memory exchange in the scan kernel" if sharded.fused else
                           "NCCL all-gather + merge kernel") if world > 1 else "none (single GPU)"
 
