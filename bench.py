@@ -493,6 +493,95 @@ def run_binary_workload(args, torch, device, local_rank):
     return 0
 
 
+def run_sharded_batch_workload(args, torch, dist, idx, sharded, rows_per_gpu, device, rank, local_rank, world):
+    """BASELINE configs[4] with configs[2]'s queries: B queries per step against a store row-sharded
+    over `world` GPUs.  Per rank: tensor-core batched search of its shard; ONE NCCL all-gather of
+    B*k candidates per rank; per-query merge on every rank.  metric = queries/s (whole job)."""
+    B, k = args.batch, args.k
+    idx.enable_batch()
+    rng = np.random.default_rng(99)
+    n_sets = 4
+    host_q = rng.standard_normal((n_sets, B, DIM), dtype=np.float32)
+    host_q /= np.linalg.norm(host_q, axis=2, keepdims=True)
+    d_q = torch.from_numpy(host_q).to(device)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    for i in range(args.warmup):
+        sharded.search_batch_device(d_q[i % n_sets], k)
+    barrier()
+    if sampler:
+        sampler.start()
+    launches0 = idx.launch_count
+    idx.profile(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        out = sharded.search_batch_device(d_q[i % n_sets], k)
+    ev1.record()
+    barrier()
+    ms_step = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+    gemm_ms, gemm_n = idx.profile_read()
+    idx.profile(False)
+    launches = idx.launch_count - launches0
+    flagged = int((out[3].contiguous().view(torch.int32) != 0).sum())
+    for i in range(min(args.warmup, 3)):
+        sharded.search_batch(host_q[i % n_sets], k)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        last = sharded.search_batch(host_q[i % n_sets], k)
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+    if sampler:
+        sampler.stop()
+    assert np.all(last[2] == k) and np.all(np.diff(last[1], axis=1) >= 0)
+    # spot check against the exact single-query sharded search (fused exchange / NCCL)
+    j = B // 3
+    one_ids, one_d = sharded.search(host_q[(args.steps - 1) % n_sets][j], k)
+    assert np.array_equal(one_ids, last[0][j]) and np.array_equal(one_d.view(np.uint32), last[1][j].view(np.uint32))
+    gemm_avg = max_over_ranks(gemm_ms / max(gemm_n, 1))
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        flops = 2.0 * B * rows_per_gpu * DIM
+        emit({
+            "metric": "knn_batched_queries_per_s", "value": B * 1e3 / ms_step, "unit": "queries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16 pre-select + f32 re-rank", "data": "synthetic",
+            "config": {"workload": "row-sharded batched cosine KNN, B=%d queries per step, k=%d, %d x 1152 rows per GPU "
+                                   "x %d GPUs (BASELINE configs[4] store, configs[2] queries)" % (B, k, rows_per_gpu, world),
+                       "rows_per_gpu": rows_per_gpu, "rows_total": rows_per_gpu * world, "batch": B, "k": k, "dim": DIM,
+                       "l2": "inputs_larger_than_L2", "parallelism": "row-shard x%d" % world,
+                       "exchange": "one NCCL all-gather of B*k candidates per rank + merge kernel"},
+            "e2e": {"value": B * 1e3 / e2e_ms, "unit": "queries/s", "h2d_bytes_per_step": B * ROW_BYTES,
+                    "d2h_bytes_per_step": B * (k * 12 + 4) + 4 * B * world, "ms_per_step": e2e_ms,
+                    "api": "ShardedIndex.search_batch"},
+            "gpu_launches": int(launches), "flagged_queries_last_step": flagged,
+            "roofline": {"bound": "tensor", "kernel": "batch_gemm_pair_kernel<FILTER>",
+                         "achieved": flops / 1e12 / (gemm_avg / 1e3), "peak": peak, "unit": "TFLOP/s",
+                         "frac": flops / 1e12 / (gemm_avg / 1e3) / peak,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained", "flops_per_launch": flops,
+                         "avg_launch_ms": gemm_avg, "launches_timed": int(gemm_n), "traffic": None},
+            "clocks": sampler.summary() if sampler else None,
+        })
+    idx.close()
+    dist.destroy_process_group()
+    return 0
+
+
 _REAL_STDOUT = None
 
 
@@ -551,6 +640,8 @@ def main():
     args.exchange_used = ("fused peer-memory exchange in the scan kernel" if sharded.fused else
                           "NCCL all-gather + merge kernel") if world > 1 else "none (single GPU)"
 
+    if args.workload == "batch" and world > 1:
+        return run_sharded_batch_workload(args, torch, dist, idx, sharded, rows_per_gpu, device, rank, local_rank, world)
     if args.workload == "batch":
         return run_batch_workload(args, torch, idx, rows, rows_per_gpu, device, rank, local_rank)
 

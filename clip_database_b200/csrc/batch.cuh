@@ -937,19 +937,21 @@ __global__ void __launch_bounds__(BQ_SEL_THREADS) batch_rerank_kernel(const Rera
 #pragma unroll
             for (int j = 0; j < SCAN_CHUNKS; j++) v1[j] = ldg_stream(src1 + lane + 32 * j);
             {
-                float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+                RowSums sums;
+                sums.clear();
 #pragma unroll
-                for (int j = 0; j < SCAN_CHUNKS; j++) accumulate<METRIC_COSINE>(v0[j], qv[j], s0, s1);
-                const float t0 = warp_sum((s0[0] + s0[1]) + (s0[2] + s0[3]));
-                const float t1 = warp_sum((s1[0] + s1[1]) + (s1[2] + s1[3]));
+                for (int j = 0; j < SCAN_CHUNKS; j++) accumulate<METRIC_COSINE>(v0[j], qv[j], sums);
+                const float t0 = warp_sum(sums.first());
+                const float t1 = warp_sum(sums.second());
                 offer_row<KPL, METRIC_COSINE, false>(t0, t1, sqrt_b, rsqrt_b, pos0, top, nan_rows, nullptr, lane);
             }
             if (two) {
-                float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+                RowSums sums;
+                sums.clear();
 #pragma unroll
-                for (int j = 0; j < SCAN_CHUNKS; j++) accumulate<METRIC_COSINE>(v1[j], qv[j], s0, s1);
-                const float t0 = warp_sum((s0[0] + s0[1]) + (s0[2] + s0[3]));
-                const float t1 = warp_sum((s1[0] + s1[1]) + (s1[2] + s1[3]));
+                for (int j = 0; j < SCAN_CHUNKS; j++) accumulate<METRIC_COSINE>(v1[j], qv[j], sums);
+                const float t0 = warp_sum(sums.first());
+                const float t1 = warp_sum(sums.second());
                 offer_row<KPL, METRIC_COSINE, false>(t0, t1, sqrt_b, rsqrt_b, pos1, top, nan_rows, nullptr, lane);
             }
         }

@@ -1632,11 +1632,14 @@ int clipdb_search_sharded_device(clipdb_ctx *c, const float *d_query, int32_t k,
     xa.world = c->xchg_world;
     xa.rank = c->xchg_rank;
     xa.k = k;
-    if (++c->xchg_epoch == 0) c->xchg_epoch = 1;   // 0 means "never written"
-    xa.epoch = c->xchg_epoch;
+    uint32_t epoch = c->xchg_epoch + 1;
+    if (epoch == 0) epoch = 1;   // 0 means "never written"
+    xa.epoch = epoch;
     xa.timeout_ns = static_cast<unsigned long long>(c->xchg_timeout_ms) * 1000000ull;
     if (xa.world == 1) return search_one(c, d_query, k, metric, use_mask != 0, d_out_rowids, d_out_dist, d_out_n, d_out_nan);
-    return search_one(c, d_query, k, metric, use_mask != 0, d_out_rowids, d_out_dist, d_out_n, d_out_nan, &xa);
+    RC_TRY(search_one(c, d_query, k, metric, use_mask != 0, d_out_rowids, d_out_dist, d_out_n, d_out_nan, &xa));
+    c->xchg_epoch = epoch;   // only a launch that was enqueued consumes an epoch: the ranks stay in step
+    return CLIPDB_OK;
 }
 
 int clipdb_merge_batch_device(clipdb_ctx *c, const void *d_dist, int64_t dist_stride, int64_t dist_qstride,

@@ -149,24 +149,39 @@ __device__ __forceinline__ float finish_distance(float s0, float s1, double sqrt
     return static_cast<float>(sqrt(static_cast<double>(s0)));
 }
 
+// Packed accumulators: Blackwell issues two float32 FMAs per instruction (PTX fma.rn.f32x2,
+// SASS FFMA2) on adjacent register pairs, which is exactly how an LDS.128 / LDG.128 delivers a
+// float4.  Each lane is the same IEEE fma as the scalar form, so results are bit-identical; the
+// row loop drops from 72 to 36 FMA instructions per lane per row (less issue pressure and power
+// in a kernel that runs at the board's power cap).
+__device__ __forceinline__ void ffma2(float2 &acc, const float2 a, const float2 b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;"
+        : "+l"(reinterpret_cast<unsigned long long &>(acc))
+        : "l"(reinterpret_cast<const unsigned long long &>(a)), "l"(reinterpret_cast<const unsigned long long &>(b)));
+}
+
+struct RowSums {
+    float2 d01, d23;   // dot (cosine) / squared difference (L2) partial sums of elements x,y and z,w
+    float2 n01, n23;   // row squared-norm partial sums (cosine)
+    __device__ __forceinline__ void clear() {
+        d01 = d23 = n01 = n23 = make_float2(0.f, 0.f);
+    }
+    __device__ __forceinline__ float first() const { return (d01.x + d01.y) + (d23.x + d23.y); }
+    __device__ __forceinline__ float second() const { return (n01.x + n01.y) + (n23.x + n23.y); }
+};
+
 template <int METRIC>
-__device__ __forceinline__ void accumulate(const float4 v, const float4 q, float (&s0)[4],
-                                           float (&s1)[4]) {
+__device__ __forceinline__ void accumulate(const float4 v, const float4 q, RowSums &s) {
     if (METRIC == METRIC_COSINE) {
-        s0[0] = fmaf(v.x, q.x, s0[0]);
-        s0[1] = fmaf(v.y, q.y, s0[1]);
-        s0[2] = fmaf(v.z, q.z, s0[2]);
-        s0[3] = fmaf(v.w, q.w, s0[3]);
-        s1[0] = fmaf(v.x, v.x, s1[0]);
-        s1[1] = fmaf(v.y, v.y, s1[1]);
-        s1[2] = fmaf(v.z, v.z, s1[2]);
-        s1[3] = fmaf(v.w, v.w, s1[3]);
+        const float2 vlo = make_float2(v.x, v.y), vhi = make_float2(v.z, v.w);
+        ffma2(s.d01, vlo, make_float2(q.x, q.y));
+        ffma2(s.d23, vhi, make_float2(q.z, q.w));
+        ffma2(s.n01, vlo, vlo);
+        ffma2(s.n23, vhi, vhi);
     } else {
-        float dx = v.x - q.x, dy = v.y - q.y, dz = v.z - q.z, dw = v.w - q.w;
-        s0[0] = fmaf(dx, dx, s0[0]);
-        s0[1] = fmaf(dy, dy, s0[1]);
-        s0[2] = fmaf(dz, dz, s0[2]);
-        s0[3] = fmaf(dw, dw, s0[3]);
+        const float2 dlo = make_float2(v.x - q.x, v.y - q.y), dhi = make_float2(v.z - q.z, v.w - q.w);
+        ffma2(s.d01, dlo, dlo);
+        ffma2(s.d23, dhi, dhi);
     }
 }
 
@@ -316,13 +331,14 @@ __global__ void __launch_bounds__(CFG::THREADS, 1) scan_tma_kernel(const ScanArg
                 float4 v[SCAN_CHUNKS];
 #pragma unroll
                 for (int j = 0; j < SCAN_CHUNKS; j++) v[j] = src[lane + 32 * j];
-                float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+                RowSums sums;
+                sums.clear();
 #pragma unroll
-                for (int j = 0; j < SCAN_CHUNKS; j++) accumulate<METRIC>(v[j], q[j], s0, s1);
+                for (int j = 0; j < SCAN_CHUNKS; j++) accumulate<METRIC>(v[j], q[j], sums);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_bar[s]);  // row is in registers: free the slot
-                float t0 = warp_sum((s0[0] + s0[1]) + (s0[2] + s0[3]));
-                float t1 = (METRIC == METRIC_COSINE) ? warp_sum((s1[0] + s1[1]) + (s1[2] + s1[3])) : 0.f;
+                float t0 = warp_sum(sums.first());
+                float t1 = (METRIC == METRIC_COSINE) ? warp_sum(sums.second()) : 0.f;
                 offer_row<KPL, METRIC, WRITE_ALL>(t0, t1, sqrt_b, rsqrt_b, pos, top, nan_rows, a.all_keys, lane);
             } else {
                 if (WRITE_ALL && pos < a.n && lane == 0) a.all_keys[pos] = KEY_EMPTY;
@@ -405,28 +421,29 @@ __global__ void __launch_bounds__(LDG_THREADS) scan_ldg_kernel(const ScanArgs a)
             continue;
         }
         const float4 *src = reinterpret_cast<const float4 *>(a.rows + pos * ld);
-        float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+        RowSums sums;
+        sums.clear();
         if (DIM_T > 0) {
             constexpr int CH = DIM_T > 0 ? DIM_T / 128 : 1;
             float4 v[CH];
 #pragma unroll
             for (int j = 0; j < CH; j++) v[j] = ldg_stream(src + lane + 32 * j);
 #pragma unroll
-            for (int j = 0; j < CH; j++) accumulate<METRIC>(v[j], qs[lane + 32 * j], s0, s1);
+            for (int j = 0; j < CH; j++) accumulate<METRIC>(v[j], qs[lane + 32 * j], sums);
         } else {
             int c = lane;
             for (; c + 96 < chunks; c += 128) {
                 float4 v0 = ldg_stream(src + c), v1 = ldg_stream(src + c + 32);
                 float4 v2 = ldg_stream(src + c + 64), v3 = ldg_stream(src + c + 96);
-                accumulate<METRIC>(v0, qs[c], s0, s1);
-                accumulate<METRIC>(v1, qs[c + 32], s0, s1);
-                accumulate<METRIC>(v2, qs[c + 64], s0, s1);
-                accumulate<METRIC>(v3, qs[c + 96], s0, s1);
+                accumulate<METRIC>(v0, qs[c], sums);
+                accumulate<METRIC>(v1, qs[c + 32], sums);
+                accumulate<METRIC>(v2, qs[c + 64], sums);
+                accumulate<METRIC>(v3, qs[c + 96], sums);
             }
-            for (; c < chunks; c += 32) accumulate<METRIC>(ldg_stream(src + c), qs[c], s0, s1);
+            for (; c < chunks; c += 32) accumulate<METRIC>(ldg_stream(src + c), qs[c], sums);
         }
-        float t0 = warp_sum((s0[0] + s0[1]) + (s0[2] + s0[3]));
-        float t1 = (METRIC == METRIC_COSINE) ? warp_sum((s1[0] + s1[1]) + (s1[2] + s1[3])) : 0.f;
+        float t0 = warp_sum(sums.first());
+        float t1 = (METRIC == METRIC_COSINE) ? warp_sum(sums.second()) : 0.f;
         offer_row<KPL, METRIC, WRITE_ALL>(t0, t1, sqrt_b, rsqrt_b, pos, top, nan_rows, a.all_keys, lane);
     }
 

@@ -133,14 +133,15 @@ class CudaShardBackend:
                                         out_dist, out_rowids, out_n)
 
     def local_search_batch(self, d_queries, k: int, record, lay: BatchRecordLayout) -> None:
-        """nq queries against this rank's shard into a packed batch record.  Uses the tensor-core
-        batched path when the index has its bf16 store (256 queries per pass, flagged queries
-        re-run through the exact scan), else the exact scan per query."""
-        t = self.torch
+        """nq queries against this rank's shard into a packed batch record; async.  Uses the
+        tensor-core batched path when the index has its bf16 store (256 queries per pass); queries
+        it could not answer (candidate overflow, zero norm) are marked in the record's flags and
+        re-run through the exact path by ``ShardedIndex.search_batch`` on every rank."""
         nq, dim = d_queries.shape
         base = record.data_ptr()
         qp = d_queries.data_ptr()
         if not getattr(self.index, "batch_enabled", False) or k > 128:
+            record[lay.off_flags:lay.off_flags + 4 * nq].zero_()
             self.index.search_ptrs(qp, nq, k, base + lay.off_rowids, base + lay.off_dist, base + lay.off_count,
                                    base + lay.off_nan)
             return
@@ -149,11 +150,6 @@ class CudaShardBackend:
             self.index.search_batch_ptrs(qp + q0 * dim * 4, m, k, base + lay.off_rowids + q0 * k * 8,
                                          base + lay.off_dist + q0 * k * 4, base + lay.off_count + q0 * 4,
                                          base + lay.off_nan + q0 * 8, base + lay.off_flags + q0 * 4)
-        flags = record[lay.off_flags:lay.off_flags + 4 * nq].view(t.int32).cpu()      # syncs the stream
-        for q in t.nonzero(flags).flatten().tolist():
-            self.index.search_ptrs(qp + q * dim * 4, 1, k, base + lay.off_rowids + q * k * 8,
-                                   base + lay.off_dist + q * k * 4, base + lay.off_count + q * 4,
-                                   base + lay.off_nan + q * 8)
 
     def merge_batch(self, gathered, nq: int, k: int, lay: BatchRecordLayout, out_dist, out_rowids, out_n) -> None:
         self.index.merge_batch_records_device(gathered, nq, k, lay.off_rowids, lay.off_dist, lay.off_count,
@@ -254,25 +250,54 @@ class ShardedIndex:
         self.backend.merge(src, k, self.layout, self.out_dist, self.out_rowids, self.out_n)
         return self.out_dist, self.out_rowids, self.out_n
 
+    def search_batch_device(self, d_queries, k: int):
+        """Enqueue: local batched search -> ONE all-gather of nq*k candidates per rank -> per-query
+        merge.  Returns device tensors (dist [nq, k], rowids [nq, k], n [nq], flags [world, nq]);
+        ``flags != 0`` marks queries some shard could not answer through the batched path."""
+        nq = d_queries.shape[0]
+        key = (nq, k)
+        if getattr(self, "_bkey", None) != key:
+            lay = BatchRecordLayout(nq, k)
+            self._blay = lay
+            self._brecord = self.backend.new_buffer(lay.nbytes)
+            self._bgathered = self.backend.new_buffer(lay.nbytes * self.world).view(self.world, lay.nbytes)
+            self._bout = self.backend.new_batch_outputs(nq, k)
+            self._bkey = key
+        lay = self._blay
+        self.backend.local_search_batch(d_queries, k, self._brecord, lay)
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(self._bgathered.view(-1), self._brecord, group=self.group)
+            gathered = self._bgathered
+        else:
+            gathered = self._brecord.view(1, -1)
+        out_dist, out_rowids, out_n = self._bout
+        self.backend.merge_batch(gathered, nq, k, lay, out_dist, out_rowids, out_n)
+        flags = gathered[:, lay.off_flags:lay.off_flags + 4 * nq]
+        return out_dist, out_rowids, out_n, flags
+
     def search_batch(self, queries: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
         """nq host queries -> (rowids [nq, k], distances [nq, k], counts [nq]); synchronous.
         Every rank scans its shard for all queries, ONE all-gather moves nq*k candidates per
-        rank, every rank merges per query with the (distance, rowid) order."""
+        rank, every rank merges per query with the (distance, rowid) order.  Queries flagged by
+        any shard are re-run one at a time through the exact sharded search — on every rank,
+        since every rank sees the same gathered flags."""
         queries = np.ascontiguousarray(queries, dtype=np.float32)
         nq = queries.shape[0]
-        lay = BatchRecordLayout(nq, k)
-        record = self.backend.new_buffer(lay.nbytes)
         d_q = self.backend.queries_to_device(queries)
-        self.backend.local_search_batch(d_q, k, record, lay)
-        if self.world > 1:
-            gathered = self.backend.new_buffer(lay.nbytes * self.world)
-            self.dist.all_gather_into_tensor(gathered, record, group=self.group)
-            gathered = gathered.view(self.world, lay.nbytes)
-        else:
-            gathered = record.view(1, -1)
-        out_dist, out_rowids, out_n = self.backend.new_batch_outputs(nq, k)
-        self.backend.merge_batch(gathered, nq, k, lay, out_dist, out_rowids, out_n)
-        return (out_rowids.cpu().numpy().copy(), out_dist.cpu().numpy().copy(), out_n.cpu().numpy().copy())
+        out_dist, out_rowids, out_n, flags = self.search_batch_device(d_q, k)
+        flagged = np.flatnonzero(flags.contiguous().cpu().numpy().view(np.int32).reshape(-1, nq).any(axis=0))
+        ids = out_rowids.cpu().numpy().copy()
+        dist = out_dist.cpu().numpy().copy()
+        counts = out_n.cpu().numpy().copy()
+        for q in flagged.tolist():
+            r_ids, r_d = self.search(queries[q], k)
+            counts[q] = len(r_ids)
+            ids[q, :len(r_ids)] = r_ids
+            dist[q, :len(r_d)] = r_d
+        unused = np.arange(ids.shape[1])[None, :] >= counts[:, None]     # as GpuIndex.search leaves them
+        ids[unused] = -1
+        dist[unused] = np.nan
+        return ids, dist, counts
 
     def nan_rows(self) -> int:
         """Admitted rows with NaN distance over all shards for the last search."""

@@ -57,6 +57,7 @@ idx2.load(rows2[lo2:hi2], np.arange(lo2 + 1, hi2 + 1))
 idx2.enable_batch()
 sh2 = ShardedIndex(CudaShardBackend(idx2))
 bq = synth.unit_rows(40, 1152, 5)
+bq[7] = 0                                       # flagged by every shard -> re-run through the exact sharded search
 b_ids, b_d, b_n = sh2.search_batch(bq, 50)
 np.savez(os.path.join({out!r}, f"batch{{rank}}.npz"), ids=b_ids, d=b_d, n=b_n)
 idx2.close()
@@ -95,6 +96,7 @@ def test_nccl_sharded_search_equals_unsharded(tmp_path):
     # batched sharded search (tensor-core path per shard) == single-store exact search
     rows2 = synth.unit_rows(140_000, 1152, 77)
     bq = synth.unit_rows(40, 1152, 5)
+    bq[7] = 0
     from clip_database_b200 import GpuIndex
     with GpuIndex(0) as whole:
         whole.load(rows2, np.arange(1, rows2.shape[0] + 1))
