@@ -275,6 +275,7 @@ def run_batch_workload(args, torch, idx, rows, rows_per_gpu, device, rank, local
     idx.enable_batch()
     idx.set_option("batch_sample_stride", args.sample_stride)
     idx.set_option("batch_refine", 0 if args.no_refine else 1)
+    idx.set_option("batch_min_nq", 1)          # --batch 1: one query through the bf16 pre-selection
     rng = np.random.default_rng(99)
     n_sets = 4
     host_q = rng.standard_normal((n_sets, B, DIM), dtype=np.float32)
@@ -317,6 +318,7 @@ def run_batch_workload(args, torch, idx, rows, rows_per_gpu, device, rank, local
     assert np.all(last.counts == k)
 
     # spot check against the exact single-query path (same context, batch path bypassed by nq=1)
+    idx.set_option("batch_min_nq", 1 << 20)
     check = [idx.search(host_q[(args.steps - 1) % n_sets][j], k) for j in (0, B // 2, B - 1)]
     for j, c in zip((0, B // 2, B - 1), check):
         assert np.array_equal(c.rowids[0], last.rowids[j]) and np.array_equal(c.distances[0], last.distances[j])
@@ -350,6 +352,23 @@ def run_batch_workload(args, torch, idx, rows, rows_per_gpu, device, rank, local
     except Exception:
         pass
     gemm_avg = gemm_ms / max(gemm_n, 1)
+    tflops = flops / 1e12 / (gemm_avg / 1e3)
+    store_gbps = rows_per_gpu * DIM * 2 / 1e9 / (gemm_avg / 1e3)
+    if B > 128:     # 256 queries per pass: AI = 256 flop/B, above the ridge -> tensor-bound
+        roof = {"bound": "tensor", "kernel": "batch_gemm_pair_kernel<FILTER, 256>", "achieved": tflops, "peak": peak,
+                "unit": "TFLOP/s", "frac": tflops / peak, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained",
+                "flops_per_launch": flops, "avg_launch_ms": gemm_avg, "launches_timed": int(gemm_n),
+                "hbm_GBps_bf16_store": store_gbps, "live_cublas_tflops": live,
+                "frac_of_live_cublas": (tflops / live) if live else None,
+                "traffic": 23041031000.0 + 22817792.0 if rows_per_gpu == 10_000_000 and B == 256 else None,
+                "traffic_source": "profiles/r01v3_gemm_ncu_raw.csv (dram read + write, one launch)"}
+    else:           # 64 / 128 queries per pass: the contraction streams the bf16 store -> HBM-bound
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        roof = {"bound": "hbm", "kernel": "batch_gemm_pair_kernel<FILTER, %d>" % (64 if B <= 64 else 128),
+                "achieved": store_gbps, "peak": hbm_peak, "unit": "GB/s", "frac": store_gbps / hbm_peak,
+                "frac_of_nominal_8000": store_gbps / 8000.0, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)",
+                "algorithmic_bytes_per_launch": rows_per_gpu * DIM * 2, "avg_launch_ms": gemm_avg,
+                "launches_timed": int(gemm_n), "tensor_TFLOPs": tflops, "traffic": None}
     line = {
         "metric": "knn_batched_queries_per_s", "value": B * 1e3 / ms_step, "unit": "queries/s", "n_gpus": 1,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -367,15 +386,7 @@ def run_batch_workload(args, torch, idx, rows, rows_per_gpu, device, rank, local
         "gpu_launches": int(launches), "flagged_queries_last_step": flagged,
         "candidates_per_query": {"filter_mean": float(cand[:B].mean()), "filter_max": int(cand[:B].max()),
                                  "reranked_mean": float(surv[:B].mean()), "reranked_max": int(surv[:B].max())},
-        "roofline": {"bound": "tensor", "kernel": "batch_gemm_pair_kernel<FILTER>", "achieved": flops / 1e12 / (gemm_avg / 1e3),
-                     "peak": peak, "unit": "TFLOP/s", "frac": flops / 1e12 / (gemm_avg / 1e3) / peak,
-                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained", "flops_per_launch": flops,
-                     "avg_launch_ms": gemm_avg, "launches_timed": int(gemm_n),
-                     "hbm_GBps_bf16_store": rows_per_gpu * DIM * 2 / 1e9 / (gemm_avg / 1e3),
-                     "live_cublas_tflops": live,
-                     "frac_of_live_cublas": (flops / 1e12 / (gemm_avg / 1e3) / live) if live else None,
-                     "traffic": 23041031000.0 + 22817792.0 if rows_per_gpu == 10_000_000 and B == 256 else None,
-                     "traffic_source": "profiles/r01v3_gemm_ncu_raw.csv (dram read + write, one launch)"},
+        "roofline": roof,
         "clocks": sampler.summary(),
     }
     emit(line)

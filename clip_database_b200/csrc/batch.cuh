@@ -467,12 +467,26 @@ __global__ void __launch_bounds__(BQ_THREADS, 1) batch_gemm_kernel(const __grid_
 // rows an SM now ingests 295 KB of rows + 295 KB of queries instead of 295 + 590 KB: the
 // 1-CTA kernel is bound by that ingest (ncu: 69 GB through the SMs' L2 ports at 11.9 TB/s,
 // tensor pipe 61 % busy), not by HBM or the tensor pipe.
-constexpr int BP_STAGES = 6;
+// The kernel is instantiated for NQ = 64, 128 and 256 queries per pass (UMMA N).  At NQ = 256 the
+// pass is tensor-bound; with fewer queries the same MMAs shrink with N (UMMA 256 x NQ x 16), the
+// query block re-read per tile shrinks too, and the pass becomes a pure HBM stream of the bf16
+// store (23 GB at 10M rows): a handful of interactive queries — or ONE — costs ~3.3 ms instead of
+// one 6.2 ms float32 scan each, with identical results after the re-rank.  Smaller stages leave
+// room for a deeper ring.
 constexpr int BP_A_BYTES = BQ_M * BQ_BLOCK_K * 2;          // 16,384: this CTA's 128 rows
-constexpr int BP_B_BYTES = (BQ_N / 2) * BQ_BLOCK_K * 2;    // 16,384: this CTA's 128 queries
-constexpr int BP_STAGE_BYTES = BP_A_BYTES + BP_B_BYTES;
-constexpr int BP_SMEM_BYTES = BQ_HEADER + BP_STAGES * BP_STAGE_BYTES + 1024 + BQ_QUEUE_SMEM;
-constexpr uint32_t BP_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((BQ_N >> 3) << 17) | ((256u >> 4) << 24);
+constexpr int BP_SMEM_LIMIT = 232448;                      // 227 KB per CTA
+template <int NQ>
+struct PairCfg {
+    static_assert(NQ == 64 || NQ == 128 || NQ == 256, "queries per pass");
+    static constexpr int B_BYTES = (NQ / 2) * BQ_BLOCK_K * 2;   // this CTA's NQ/2 queries
+    static constexpr int STAGE_BYTES = BP_A_BYTES + B_BYTES;
+    static constexpr int FIT = (BP_SMEM_LIMIT - 64 - BQ_HEADER - 1024 - BQ_QUEUE_SMEM) / STAGE_BYTES;
+    static constexpr int STAGES = FIT > 10 ? 10 : FIT;          // 6 / 8 / 10 for NQ = 256 / 128 / 64
+    static constexpr int SMEM_BYTES = BQ_HEADER + STAGES * STAGE_BYTES + 1024 + BQ_QUEUE_SMEM;
+    static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((NQ >> 3) << 17) | ((256u >> 4) << 24);
+    static constexpr int TMEM_COLS = 2 * NQ;                    // two accumulator buffers
+    static_assert(STAGES * 16 + 32 + 8 <= 1024, "barriers must fit below the thresholds");
+};
 constexpr uint32_t BP_PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> CTA 0
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -535,10 +549,12 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity
     } while (!ok);
 }
 
-template <bool DUMP>
+template <bool DUMP, int NQ>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
     batch_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__ CUtensorMap map_qhalf,
                            const BatchGemmArgs a) {
+    using CFG = PairCfg<NQ>;
+    constexpr int BP_STAGES = CFG::STAGES, BP_STAGE_BYTES = CFG::STAGE_BYTES;
     extern __shared__ __align__(16) uint8_t bq_smem_raw[];
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(bq_smem_raw);   // waited on in the leader only
     uint64_t *empty_bar = full_bar + BP_STAGES;
@@ -569,8 +585,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
         mbar_fence_init();
     }
     if (!DUMP)
-        for (int i = tid; i < BQ_N; i += BQ_THREADS) thr_s[i] = a.thr[i];
-    if (warp == 1) tmem_alloc_pair(tmem_base_slot, BQ_TMEM_COLS);
+        for (int i = tid; i < NQ; i += BQ_THREADS) thr_s[i] = a.thr[i];
+    if (warp == 1) tmem_alloc_pair(tmem_base_slot, CFG::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();    // the peer's barriers exist before anything signals them
@@ -589,7 +605,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
                     if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * BP_STAGE_BYTES);  // both CTAs' bytes
                     uint8_t *stage = tiles + s * BP_STAGE_BYTES;
                     tma_load_2d_pair(stage, &map_rows, 0, (tile128 * BQ_K_BLOCKS + kb) * BQ_M, &full_bar[s]);
-                    tma_load_2d_pair(stage + BP_A_BYTES, &map_qhalf, kb * BQ_BLOCK_K, static_cast<int>(rank) * (BQ_N / 2),
+                    tma_load_2d_pair(stage + BP_A_BYTES, &map_qhalf, kb * BQ_BLOCK_K, static_cast<int>(rank) * (NQ / 2),
                                      &full_bar[s]);
                     if (++s == BP_STAGES) {
                         s = 0;
@@ -608,7 +624,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
                 const int acc = it & 1;
                 mbar_wait_cluster(&tmem_empty[acc], (static_cast<uint32_t>(it >> 1) & 1u) ^ 1u);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BQ_N);
+                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * NQ);
                 for (int kb = 0; kb < BQ_K_BLOCKS; kb++) {
                     mbar_wait_cluster(&full_bar[s], phase);
                     tc_fence_after();
@@ -617,7 +633,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
 #pragma unroll
                     for (int k = 0; k < BQ_BLOCK_K / BQ_UMMA_K; k++) {
                         umma_bf16_pair(tmem_d, umma_desc_sw128(a_addr + k * BQ_UMMA_K * 2),
-                                       umma_desc_sw128(b_addr + k * BQ_UMMA_K * 2), BP_IDESC,
+                                       umma_desc_sw128(b_addr + k * BQ_UMMA_K * 2), CFG::IDESC,
                                        static_cast<uint32_t>((kb | k) != 0));
                     }
                     umma_commit_pair(&empty_bar[s]);   // frees this stage in both CTAs
@@ -646,9 +662,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
             mbar_wait(&tmem_full[acc], static_cast<uint32_t>(it >> 1) & 1u);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_base) << 16) +
-                                   static_cast<uint32_t>(acc * BQ_N);
+                                   static_cast<uint32_t>(acc * NQ);
 #pragma unroll 1
-            for (int c = 0; c < BQ_N / 32; c++) {
+            for (int c = 0; c < NQ / 32; c++) {
                 uint32_t r[32];
                 tmem_ld32(taddr + c * 32, r);
                 tmem_ld_wait();
@@ -683,7 +699,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();    // no CTA leaves (or frees TMEM) while its peer may still touch it
-    if (warp == 1) tmem_dealloc_pair(tmem_base, BQ_TMEM_COLS);
+    if (warp == 1) tmem_dealloc_pair(tmem_base, CFG::TMEM_COLS);
 }
 
 // ---- per-query selection in two levels ----------------------------------------------------

@@ -91,7 +91,7 @@ struct clipdb_ctx {
     unsigned long long batch_bad_rows = 0;  // zero-norm / non-finite rows found when the copy was built
     Buffer bf16_rows, bad_rows, bq_queries, bq_qnorm, bq_scores, bq_thr, bq_flags, bq_count, bq_cand, bq_parts, bq_qerr, row_err;
     Buffer bq_cand_u, bq_margin, bq_surv, bq_surv_count;
-    CUtensorMap map_rows, map_q, map_qhalf;
+    CUtensorMap map_rows, map_q, map_qhalf[3];   // query-half boxes for 64 / 128 / 256 queries per pass
     int64_t bq_sample_groups_used = 0;  // groups the last pass A wrote
     int64_t batch_min_nq = 2;       // clipdb_search switches to the batched path from this nq (one batch
                                     // costs about one single-query scan, whatever its size)
@@ -99,6 +99,7 @@ struct clipdb_ctx {
     int64_t batch_cta_pair = 1;     // 1: cta_group::2 contraction (CTA pairs), 0: single-CTA kernel
     int64_t batch_sample_stride = 0; // pass A visits every s-th 128-row tile; 0 = auto (tiles/1024 clamped to 1..64)
     int64_t batch_refine = 1;       // 1: second threshold from the candidates' own scores before the re-rank
+    int64_t batch_npass = 0;        // 0: auto (64 / 128 / 256 queries per pass by batch size); else force >= that
 
     // scan-kernel event timing (clipdb_profile)
     bool profiling = false;
@@ -703,9 +704,15 @@ int batch_build_locked(clipdb_ctx *c) {
     RC_TRY(encode_bf16_map(c, &c->map_rows, c->bf16_rows.p, static_cast<uint64_t>(tiles) * BQ_K_BLOCKS * BQ_M, BQ_M,
                            BQ_BLOCK_K));
     RC_TRY(encode_bf16_map(c, &c->map_q, c->bq_queries.p, BQ_N, BQ_N));
-    RC_TRY(encode_bf16_map(c, &c->map_qhalf, c->bq_queries.p, BQ_N, BQ_N / 2));
-    CU_TRY(c, cudaFuncSetAttribute(batch_gemm_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_BYTES));
-    CU_TRY(c, cudaFuncSetAttribute(batch_gemm_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_BYTES));
+    RC_TRY(encode_bf16_map(c, &c->map_qhalf[0], c->bq_queries.p, BQ_N, 64 / 2));
+    RC_TRY(encode_bf16_map(c, &c->map_qhalf[1], c->bq_queries.p, BQ_N, 128 / 2));
+    RC_TRY(encode_bf16_map(c, &c->map_qhalf[2], c->bq_queries.p, BQ_N, 256 / 2));
+    CU_TRY(c, cudaFuncSetAttribute(batch_gemm_pair_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<64>::SMEM_BYTES));
+    CU_TRY(c, cudaFuncSetAttribute(batch_gemm_pair_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<64>::SMEM_BYTES));
+    CU_TRY(c, cudaFuncSetAttribute(batch_gemm_pair_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<128>::SMEM_BYTES));
+    CU_TRY(c, cudaFuncSetAttribute(batch_gemm_pair_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<128>::SMEM_BYTES));
+    CU_TRY(c, cudaFuncSetAttribute(batch_gemm_pair_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<256>::SMEM_BYTES));
+    CU_TRY(c, cudaFuncSetAttribute(batch_gemm_pair_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<256>::SMEM_BYTES));
     CU_TRY(c, cudaFuncSetAttribute(batch_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BQ_SMEM_BYTES));
     CU_TRY(c, cudaFuncSetAttribute(batch_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BQ_SMEM_BYTES));
     CU_TRY(c, cudaMemcpyAsync(&c->batch_bad_rows, c->bad_rows.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
@@ -722,6 +729,24 @@ int batch_build_locked(clipdb_ctx *c) {
 bool batch_eligible(const clipdb_ctx *c, int32_t nq, int32_t k, int32_t metric, int32_t use_mask) {
     return c->batch_enabled && metric == CLIPDB_METRIC_COSINE && (!use_mask || (c->mask && c->batch_bad_rows == 0)) &&
            k >= 1 && k <= FUSED_K_MAX && k <= c->n && nq >= 1 && nq <= BQ_N;
+}
+
+template <bool DUMP>
+void launch_pair_gemm(clipdb_ctx *c, int npass, int grid, const BatchGemmArgs &g) {
+    switch (npass) {
+        case 64:
+            batch_gemm_pair_kernel<DUMP, 64><<<grid, BQ_THREADS, PairCfg<64>::SMEM_BYTES, c->stream>>>(
+                c->map_rows, c->map_qhalf[0], g);
+            break;
+        case 128:
+            batch_gemm_pair_kernel<DUMP, 128><<<grid, BQ_THREADS, PairCfg<128>::SMEM_BYTES, c->stream>>>(
+                c->map_rows, c->map_qhalf[1], g);
+            break;
+        default:
+            batch_gemm_pair_kernel<DUMP, 256><<<grid, BQ_THREADS, PairCfg<256>::SMEM_BYTES, c->stream>>>(
+                c->map_rows, c->map_qhalf[2], g);
+            break;
+    }
 }
 
 template <int KPL>
@@ -800,6 +825,10 @@ int batch_search_device_locked(clipdb_ctx *c, const float *d_queries, int32_t nq
     // pass A: group maxima over a tile sample -> per-query thresholds
     const bool pair = c->batch_cta_pair != 0 && (c->sm_count % 2 == 0);
     const int pair_grid = c->sm_count & ~1;
+    // queries per pass (UMMA N): the smallest instantiation that holds the batch
+    int npass = nq <= 64 ? 64 : (nq <= 128 ? 128 : 256);
+    if (c->batch_npass == 64 || c->batch_npass == 128 || c->batch_npass == 256)
+        npass = c->batch_npass >= npass ? static_cast<int>(c->batch_npass) : npass;
     const int sstride = batch_sample_stride(c, tiles);
     // one maximum per (sampled 128-row tile, epilogue warp)
     g.tile_stride = pair ? (sstride >= 2 ? sstride / 2 : 1) : sstride;   // pair kernel: in 256-row pair tiles
@@ -809,7 +838,7 @@ int batch_search_device_locked(clipdb_ctx *c, const float *d_queries, int32_t nq
     g.scores = static_cast<float *>(c->bq_scores.p);
     if (pair) {
         const int grid = 2 * eff < pair_grid ? 2 * eff : pair_grid;
-        batch_gemm_pair_kernel<true><<<grid, BQ_THREADS, BP_SMEM_BYTES, c->stream>>>(c->map_rows, c->map_qhalf, g);
+        launch_pair_gemm<true>(c, npass, grid, g);
     } else {
         batch_gemm_kernel<true><<<eff < c->sm_count ? eff : c->sm_count, BQ_THREADS, BQ_SMEM_BYTES, c->stream>>>(
             c->map_rows, c->map_q, g);
@@ -829,7 +858,7 @@ int batch_search_device_locked(clipdb_ctx *c, const float *d_queries, int32_t nq
     if (pair) {
         const int ptiles = (tiles + 1) / 2;
         const int grid = 2 * ptiles < pair_grid ? 2 * ptiles : pair_grid;
-        batch_gemm_pair_kernel<false><<<grid, BQ_THREADS, BP_SMEM_BYTES, c->stream>>>(c->map_rows, c->map_qhalf, g);
+        launch_pair_gemm<false>(c, npass, grid, g);
     } else {
         batch_gemm_kernel<false><<<tiles < c->sm_count ? tiles : c->sm_count, BQ_THREADS, BQ_SMEM_BYTES, c->stream>>>(
             c->map_rows, c->map_q, g);
@@ -1037,6 +1066,7 @@ static int64_t *option_slot(clipdb_ctx *c, const char *name) {
     if (!strcmp(name, "batch_cta_pair")) return &c->batch_cta_pair;
     if (!strcmp(name, "batch_sample_stride")) return &c->batch_sample_stride;
     if (!strcmp(name, "batch_refine")) return &c->batch_refine;
+    if (!strcmp(name, "batch_npass")) return &c->batch_npass;
     return nullptr;
 }
 

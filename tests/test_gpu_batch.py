@@ -84,6 +84,35 @@ def test_sampling_stride_and_refinement_do_not_change_results(store, stride, ref
         batched.set_option("batch_refine", 1)
 
 
+@pytest.mark.parametrize("npass", [64, 128, 256])
+def test_queries_per_pass_variants_agree(store, npass):
+    """The contraction is instantiated for 64 / 128 / 256 queries per pass (UMMA N); a small batch
+    forced through a wider instantiation gives the same answer."""
+    rows, exact, batched = store
+    queries = synth.unit_rows(40, DIM, 321)
+    batched.set_option("batch_npass", npass)
+    try:
+        same(batched.search(queries, 100), exact.search(queries, 100))
+    finally:
+        batched.set_option("batch_npass", 0)
+
+
+def test_single_query_through_the_batched_path(store):
+    """batch_min_nq = 1: even one query is pre-selected on the bf16 store (half the bytes of the
+    float32 scan) and re-ranked exactly."""
+    rows, exact, batched = store
+    queries = synth.unit_rows(6, DIM, 55)
+    batched.set_option("batch_min_nq", 1)
+    try:
+        for q in queries:
+            before = batched.launch_count
+            got = batched.search(q, 20)
+            assert batched.launch_count - before == 7, "batched path was not taken"
+            same(got, exact.search(q, 20))
+    finally:
+        batched.set_option("batch_min_nq", 2)
+
+
 def test_batched_with_folder_mask():
     """The folder pre-filter bitset (idb:1509-1530) is honoured by the tensor-core path."""
     from clip_database_b200 import GpuIndex
