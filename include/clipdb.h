@@ -173,7 +173,10 @@ int clipdb_blend_search(clipdb_ctx *ctx, const float *e1, const float *e2, doubl
  * after clipdb_enable_batch are picked up: the bf16 copy is rebuilt before the next batched search.
  * With the batch store enabled, clipdb_search uses this path by itself for
  * nq >= 2 (option "batch_min_nq") and transparently re-runs flagged queries
- * through the exact scan.
+ * through the exact scan.  The contraction runs 64, 128 or 256 queries per pass
+ * (the smallest that holds the batch); below 256 it streams the bf16 copy at HBM
+ * rate, so with option "batch_min_nq" = 1 even a single query costs half the
+ * float32 scan's bytes, with identical results.
  *
  * clipdb_search_batch_device: device pointers, async, nq <= 256 per call.
  * d_flags[q] != 0 (CLIPDB_BATCH_*) marks queries whose result is NOT valid
