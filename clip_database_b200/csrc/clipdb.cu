@@ -657,11 +657,18 @@ int encode_bf16_map(clipdb_ctx *c, CUtensorMap *map, void *base, uint64_t rows, 
 
 constexpr int64_t BATCH_MIN_ROWS = 65536;
 
-// Pass A's sampling stride in 128-row tiles.  Auto: about 1000 sampled tiles (4000 group maxima
-// per query) however large the store, never sparser than every 64th tile; a power of two so the
-// CTA-pair kernel (256-row pair tiles) samples the same fraction.
-int batch_sample_stride(const clipdb_ctx *c, int64_t tiles) {
-    int64_t s = c->batch_sample_stride > 0 ? c->batch_sample_stride : tiles / 1024;
+// Pass A's sampling stride in 128-row tiles.  Sparser sampling makes pass A cheaper and the
+// thresholds looser: pass B then keeps about 1.25 * k * stride candidates per query (measured),
+// which must stay well inside the candidate capacity.  Auto: capacity / (4k), at most every 256th
+// tile, never fewer than 8k sampled 32-row groups; a power of two so the CTA-pair kernel (256-row
+// pair tiles) samples the same fraction.
+int batch_sample_stride(const clipdb_ctx *c, int64_t tiles, int k) {
+    int64_t s = c->batch_sample_stride;
+    if (s <= 0) {
+        const int64_t kk = k > 0 ? k : 1;
+        s = c->batch_cand_cap / (4 * kk);
+        if (s > tiles / (2 * kk)) s = tiles / (2 * kk);   // at least 8k group maxima to pick the k-th from
+    }
     if (s > BQ_SAMPLE_STRIDE_MAX) s = BQ_SAMPLE_STRIDE_MAX;
     int p = 1;
     while (p * 2 <= s) p *= 2;
@@ -829,7 +836,7 @@ int batch_search_device_locked(clipdb_ctx *c, const float *d_queries, int32_t nq
     int npass = nq <= 64 ? 64 : (nq <= 128 ? 128 : 256);
     if (c->batch_npass == 64 || c->batch_npass == 128 || c->batch_npass == 256)
         npass = c->batch_npass >= npass ? static_cast<int>(c->batch_npass) : npass;
-    const int sstride = batch_sample_stride(c, tiles);
+    const int sstride = batch_sample_stride(c, tiles, k);
     // one maximum per (sampled 128-row tile, epilogue warp)
     g.tile_stride = pair ? (sstride >= 2 ? sstride / 2 : 1) : sstride;   // pair kernel: in 256-row pair tiles
     const int eff = ((pair ? (tiles + 1) / 2 : tiles) + g.tile_stride - 1) / g.tile_stride;
