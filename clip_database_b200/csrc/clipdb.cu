@@ -80,7 +80,11 @@ struct clipdb_ctx {
     // workspaces (grown on demand)
     Buffer cand_a, cand_b, sync_buf, all_keys_a, all_keys_b, cub_tmp;
     bool sync_dirty = true;   // the scan kernels' counters may be non-zero
-    Buffer d_query, d_out_rowids, d_out_dist, d_out_n, d_out_nan;
+    Buffer d_query, d_results;   // host entry points: staged queries, one packed result block
+    int64_t *r_nan = nullptr, *r_ids = nullptr;
+    float *r_dist = nullptr;
+    int32_t *r_n = nullptr;
+    size_t r_bytes = 0;
     Buffer d_blend_in, d_blend_flags;
     Buffer pinned;      // host staging (inputs, then results)
     Buffer pinned_aux;  // host staging for the blended query read-back
@@ -1012,8 +1016,7 @@ void clipdb_destroy(clipdb_ctx *c) {
         release_codes(c);
         release_exchange(c);
         Buffer *bufs[] = {&c->d_code_query, &c->code_stage, &c->code_bad, &c->cand_a, &c->cand_b, &c->sync_buf, &c->all_keys_a, &c->all_keys_b,
-                          &c->cub_tmp, &c->d_query, &c->d_out_rowids, &c->d_out_dist, &c->d_out_n,
-                          &c->d_out_nan, &c->d_blend_in, &c->d_blend_flags, &c->bf16_rows,
+                          &c->cub_tmp, &c->d_query, &c->d_results, &c->d_blend_in, &c->d_blend_flags, &c->bf16_rows,
                           &c->bad_rows, &c->bq_queries, &c->bq_qnorm, &c->bq_scores, &c->bq_thr, &c->bq_flags,
                           &c->bq_count, &c->bq_cand, &c->bq_parts, &c->bq_qerr, &c->row_err, &c->bq_cand_u, &c->bq_margin,
                           &c->bq_surv, &c->bq_surv_count};
@@ -1263,28 +1266,40 @@ int clipdb_search_device(clipdb_ctx *c, const float *d_queries, int32_t nq, int3
                                 d_out_n, d_out_nan);
 }
 
-// shared tail of the host search entry points: results D2H + unpack
+// Host entry points write their results into ONE device block laid out
+//     nan int64[nq] | rowids int64[nq][k] | dist float32[nq][k] | n int32[nq]
+// so that they reach the host with a single D2H copy (small stores are latency-bound: the four
+// separate copies of the first version cost ~10 us of a 130 us query).
+static int ensure_result_buffers(clipdb_ctx *c, int32_t nq, int64_t kcols) {
+    const size_t q = static_cast<size_t>(nq > 0 ? nq : 1), kc = static_cast<size_t>(kcols > 0 ? kcols : 0);
+    const size_t b_nan = q * sizeof(int64_t), b_ids = q * kc * sizeof(int64_t), b_dist = q * kc * sizeof(float);
+    const size_t b_n = q * sizeof(int32_t);
+    RC_TRY(ensure_device(c, c->d_results, b_nan + b_ids + b_dist + b_n + 64));
+    uint8_t *d = static_cast<uint8_t *>(c->d_results.p);
+    c->r_nan = reinterpret_cast<int64_t *>(d);
+    c->r_ids = reinterpret_cast<int64_t *>(d + b_nan);
+    c->r_dist = reinterpret_cast<float *>(d + b_nan + b_ids);
+    c->r_n = reinterpret_cast<int32_t *>(d + b_nan + b_ids + b_dist);
+    c->r_bytes = b_nan + b_ids + b_dist + b_n;
+    return CLIPDB_OK;
+}
+
+// shared tail of the host search entry points: one D2H of the result block + unpack
 static int fetch_results(clipdb_ctx *c, int32_t nq, int64_t kcols, int64_t *out_rowids,
                          float *out_dist, int32_t *out_n, int64_t *out_nan) {
-    const size_t b_ids = static_cast<size_t>(nq) * kcols * sizeof(int64_t);
-    const size_t b_dist = static_cast<size_t>(nq) * kcols * sizeof(float);
-    const size_t b_n = static_cast<size_t>(nq) * sizeof(int32_t);
-    const size_t b_nan = static_cast<size_t>(nq) * sizeof(int64_t);
-    // pinned layout (8-byte aligned pieces first): nan | ids | dist | n
-    RC_TRY(ensure_pinned(c, b_nan + b_ids + b_dist + b_n + 64));
+    RC_TRY(ensure_pinned(c, c->r_bytes + 64));
     uint8_t *h = static_cast<uint8_t *>(c->pinned.p);
-    uint8_t *h_nan = h, *h_ids = h_nan + b_nan, *h_dist = h_ids + b_ids, *h_n = h_dist + b_dist;
-    CU_TRY(c, cudaMemcpyAsync(h_nan, c->d_out_nan.p, b_nan, cudaMemcpyDeviceToHost, c->stream));
-    if (kcols > 0) {
-        CU_TRY(c, cudaMemcpyAsync(h_ids, c->d_out_rowids.p, b_ids, cudaMemcpyDeviceToHost, c->stream));
-        CU_TRY(c, cudaMemcpyAsync(h_dist, c->d_out_dist.p, b_dist, cudaMemcpyDeviceToHost, c->stream));
-    }
-    CU_TRY(c, cudaMemcpyAsync(h_n, c->d_out_n.p, b_n, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(h, c->d_results.p, c->r_bytes, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
-    memcpy(out_n, h_n, b_n);
-    if (out_nan) memcpy(out_nan, h_nan, b_nan);
+    const uint8_t *d = static_cast<const uint8_t *>(c->d_results.p);
+    const uint8_t *h_nan = h;
+    const uint8_t *h_ids = h + (reinterpret_cast<const uint8_t *>(c->r_ids) - d);
+    const uint8_t *h_dist = h + (reinterpret_cast<const uint8_t *>(c->r_dist) - d);
+    const uint8_t *h_n = h + (reinterpret_cast<const uint8_t *>(c->r_n) - d);
+    memcpy(out_n, h_n, static_cast<size_t>(nq) * sizeof(int32_t));
+    if (out_nan) memcpy(out_nan, h_nan, static_cast<size_t>(nq) * sizeof(int64_t));
     for (int32_t q = 0; q < nq; q++) {
-        const int32_t m = reinterpret_cast<int32_t *>(h_n)[q];
+        const int32_t m = reinterpret_cast<const int32_t *>(h_n)[q];
         if (m > 0) {
             memcpy(out_rowids + q * kcols, h_ids + static_cast<size_t>(q) * kcols * sizeof(int64_t),
                    static_cast<size_t>(m) * sizeof(int64_t));
@@ -1292,15 +1307,6 @@ static int fetch_results(clipdb_ctx *c, int32_t nq, int64_t kcols, int64_t *out_
                    static_cast<size_t>(m) * sizeof(float));
         }
     }
-    return CLIPDB_OK;
-}
-
-static int ensure_result_buffers(clipdb_ctx *c, int32_t nq, int64_t kcols) {
-    const size_t cells = static_cast<size_t>(nq > 0 ? nq : 1) * (kcols > 0 ? kcols : 1);
-    RC_TRY(ensure_device(c, c->d_out_rowids, cells * sizeof(int64_t)));
-    RC_TRY(ensure_device(c, c->d_out_dist, cells * sizeof(float)));
-    RC_TRY(ensure_device(c, c->d_out_n, static_cast<size_t>(nq > 0 ? nq : 1) * sizeof(int32_t)));
-    RC_TRY(ensure_device(c, c->d_out_nan, static_cast<size_t>(nq > 0 ? nq : 1) * sizeof(int64_t)));
     return CLIPDB_OK;
 }
 
@@ -1324,10 +1330,10 @@ int clipdb_search(clipdb_ctx *c, const float *queries, int32_t nq, int32_t k, in
     CU_TRY(c, cudaMemcpyAsync(c->d_query.p, c->pinned.p, qbytes, cudaMemcpyHostToDevice, c->stream));
     // the pinned buffer is reused for results: the H2D above is ordered before them on the stream
     const float *dq = static_cast<const float *>(c->d_query.p);
-    int64_t *o_ids = static_cast<int64_t *>(c->d_out_rowids.p);
-    float *o_dist = static_cast<float *>(c->d_out_dist.p);
-    int32_t *o_n = static_cast<int32_t *>(c->d_out_n.p);
-    int64_t *o_nan = static_cast<int64_t *>(c->d_out_nan.p);
+    int64_t *o_ids = c->r_ids;
+    float *o_dist = c->r_dist;
+    int32_t *o_n = c->r_n;
+    int64_t *o_nan = c->r_nan;
     if (nq >= c->batch_min_nq && c->batch_enabled && c->batch_dirty) RC_TRY(batch_build_locked(c));
     if (nq >= c->batch_min_nq && batch_eligible(c, nq < BQ_N ? nq : BQ_N, k, metric, use_mask)) {
         // batched path: tensor-core pre-selection + exact re-rank, 256 queries per pass; queries
@@ -1372,9 +1378,7 @@ int clipdb_blend_search(clipdb_ctx *c, const float *e1, const float *e2, double 
     RC_TRY(ensure_device(c, c->d_query, static_cast<size_t>(dim) * sizeof(float) + sizeof(int32_t)));
     float *d_q = static_cast<float *>(c->d_query.p);
     RC_TRY(blend_device_locked(c, st.e1, st.e2, st.w, st.negs, st.neg_w, n_neg, dim, 1, d_q, st.flags));
-    RC_TRY(search_device_locked(c, d_q, 1, k, metric, use_mask, static_cast<int64_t *>(c->d_out_rowids.p),
-                                static_cast<float *>(c->d_out_dist.p), static_cast<int32_t *>(c->d_out_n.p),
-                                static_cast<int64_t *>(c->d_out_nan.p)));
+    RC_TRY(search_device_locked(c, d_q, 1, k, metric, use_mask, c->r_ids, c->r_dist, c->r_n, c->r_nan));
     // optional read-back of the blended query and the fallback flags, through their own
     // pinned area so the result staging below can reuse the main one
     float *h_aux = nullptr;
@@ -1576,10 +1580,8 @@ int clipdb_binary_search(clipdb_ctx *c, const uint8_t *query_code, int32_t k, in
     }
     CU_TRY(c, cudaMemcpyAsync(c->d_code_query.p, hq, BIN_ROW_BYTES, cudaMemcpyHostToDevice, c->stream));
     RC_TRY(binary_search_device_locked(c, static_cast<const uint32_t *>(c->d_code_query.p), k, score_mode, use_mask,
-                                       static_cast<int64_t *>(c->d_out_rowids.p),
-                                       reinterpret_cast<int32_t *>(c->d_out_dist.p),
-                                       static_cast<int32_t *>(c->d_out_n.p)));
-    CU_TRY(c, cudaMemsetAsync(c->d_out_nan.p, 0, sizeof(int64_t), c->stream));
+                                       c->r_ids, reinterpret_cast<int32_t *>(c->r_dist), c->r_n));
+    CU_TRY(c, cudaMemsetAsync(c->r_nan, 0, sizeof(int64_t), c->stream));
     return fetch_results(c, 1, kcols, out_ids, reinterpret_cast<float *>(out_scores), out_n, nullptr);
 }
 
