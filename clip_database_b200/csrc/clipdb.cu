@@ -88,6 +88,7 @@ struct clipdb_ctx {
     Buffer d_blend_in, d_blend_flags;
     Buffer pinned;      // host staging (inputs, then results)
     Buffer pinned_aux;  // host staging for the blended query read-back
+    Buffer pinned_flags; // host staging for the batched path's per-query flags
 
     // batched path (K4): bf16 copy of the store + workspaces
     bool batch_enabled = false;
@@ -659,7 +660,7 @@ int encode_bf16_map(clipdb_ctx *c, CUtensorMap *map, void *base, uint64_t rows, 
     return CLIPDB_OK;
 }
 
-constexpr int64_t BATCH_MIN_ROWS = 65536;
+constexpr int64_t BATCH_MIN_ROWS = 1;   // any non-empty store: with fewer sampled groups than k every row is a candidate
 
 // Pass A's sampling stride in 128-row tiles.  Sparser sampling makes pass A cheaper and the
 // thresholds looser: pass B then keeps about 1.25 * k * stride candidates per query (measured),
@@ -1023,6 +1024,7 @@ void clipdb_destroy(clipdb_ctx *c) {
         for (Buffer *b : bufs) free_buffer(*b);
         if (c->pinned.p) cudaFreeHost(c->pinned.p);
         if (c->pinned_aux.p) cudaFreeHost(c->pinned_aux.p);
+        if (c->pinned_flags.p) cudaFreeHost(c->pinned_flags.p);
         for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
         if (c->own_stream) cudaStreamDestroy(c->own_stream);
         cudaGetLastError();
@@ -1310,6 +1312,55 @@ static int fetch_results(clipdb_ctx *c, int32_t nq, int64_t kcols, int64_t *out_
     return CLIPDB_OK;
 }
 
+// Queries are in device memory, the result block is allocated: pick the path, run, fetch.
+// Batched path (bf16 pre-selection + exact re-rank) when the batch store is enabled and the
+// request qualifies; queries it flags (candidate overflow, zero norm) are re-run through the
+// exact scan.  The flags travel to the host with the results: one synchronisation per call.
+static int run_and_fetch(clipdb_ctx *c, const float *dq, int32_t nq, int32_t k, int32_t metric, int32_t use_mask,
+                         int64_t *out_rowids, float *out_dist, int32_t *out_n, int64_t *out_nan) {
+    const int64_t kcols = k > 0 ? k : 0;
+    int64_t *o_ids = c->r_ids;
+    float *o_dist = c->r_dist;
+    int32_t *o_n = c->r_n;
+    int64_t *o_nan = c->r_nan;
+    if (nq >= c->batch_min_nq && c->batch_enabled && c->batch_dirty) RC_TRY(batch_build_locked(c));
+    if (nq >= c->batch_min_nq && batch_eligible(c, nq < BQ_N ? nq : BQ_N, k, metric, use_mask)) {
+        RC_TRY(ensure_device(c, c->bq_flags, static_cast<size_t>(nq > BQ_N ? nq : BQ_N) * sizeof(int32_t)));
+        int32_t *d_flags = static_cast<int32_t *>(c->bq_flags.p);
+        for (int32_t q0 = 0; q0 < nq; q0 += BQ_N) {
+            const int32_t m = nq - q0 < BQ_N ? nq - q0 : BQ_N;
+            RC_TRY(batch_search_device_locked(c, dq + static_cast<size_t>(q0) * c->dim, m, k, use_mask, o_ids + q0 * kcols,
+                                              o_dist + q0 * kcols, o_n + q0, o_nan + q0, d_flags + q0));
+        }
+        const size_t fbytes = static_cast<size_t>(nq) * sizeof(int32_t);
+        if (c->pinned_flags.bytes < fbytes) {
+            if (c->pinned_flags.p) {
+                CU_TRY(c, cudaStreamSynchronize(c->stream));
+                CU_TRY(c, cudaFreeHost(c->pinned_flags.p));
+                c->pinned_flags.p = nullptr;
+                c->pinned_flags.bytes = 0;
+            }
+            const size_t want = fbytes < 4096 ? 4096 : fbytes;
+            CU_TRY(c, cudaMallocHost(&c->pinned_flags.p, want));
+            c->pinned_flags.bytes = want;
+        }
+        int32_t *flags = static_cast<int32_t *>(c->pinned_flags.p);
+        CU_TRY(c, cudaMemcpyAsync(flags, d_flags, fbytes, cudaMemcpyDeviceToHost, c->stream));
+        RC_TRY(fetch_results(c, nq, kcols, out_rowids, out_dist, out_n, out_nan));   // synchronises
+        bool rerun = false;
+        for (int32_t q = 0; q < nq; q++) {
+            if (!flags[q]) continue;
+            rerun = true;
+            RC_TRY(search_device_locked(c, dq + static_cast<size_t>(q) * c->dim, 1, k, metric, use_mask,
+                                        o_ids + q * kcols, o_dist + q * kcols, o_n + q, o_nan + q));
+        }
+        if (rerun) return fetch_results(c, nq, kcols, out_rowids, out_dist, out_n, out_nan);
+        return CLIPDB_OK;
+    }
+    RC_TRY(search_device_locked(c, dq, nq, k, metric, use_mask, o_ids, o_dist, o_n, o_nan));
+    return fetch_results(c, nq, kcols, out_rowids, out_dist, out_n, out_nan);
+}
+
 int clipdb_search(clipdb_ctx *c, const float *queries, int32_t nq, int32_t k, int32_t metric,
                   int32_t use_mask, int64_t *out_rowids, float *out_dist, int32_t *out_n,
                   int64_t *out_nan) {
@@ -1334,30 +1385,7 @@ int clipdb_search(clipdb_ctx *c, const float *queries, int32_t nq, int32_t k, in
     float *o_dist = c->r_dist;
     int32_t *o_n = c->r_n;
     int64_t *o_nan = c->r_nan;
-    if (nq >= c->batch_min_nq && c->batch_enabled && c->batch_dirty) RC_TRY(batch_build_locked(c));
-    if (nq >= c->batch_min_nq && batch_eligible(c, nq < BQ_N ? nq : BQ_N, k, metric, use_mask)) {
-        // batched path: tensor-core pre-selection + exact re-rank, 256 queries per pass; queries
-        // it flags (candidate overflow, zero norm) are re-run through the exact scan
-        RC_TRY(ensure_device(c, c->bq_flags, static_cast<size_t>(nq > BQ_N ? nq : BQ_N) * sizeof(int32_t)));
-        int32_t *d_flags = static_cast<int32_t *>(c->bq_flags.p);
-        for (int32_t q0 = 0; q0 < nq; q0 += BQ_N) {
-            const int32_t m = nq - q0 < BQ_N ? nq - q0 : BQ_N;
-            RC_TRY(batch_search_device_locked(c, dq + static_cast<size_t>(q0) * c->dim, m, k, use_mask, o_ids + q0 * kcols,
-                                              o_dist + q0 * kcols, o_n + q0, o_nan + q0, d_flags + q0));
-        }
-        std::vector<int32_t> flags(static_cast<size_t>(nq));
-        CU_TRY(c, cudaMemcpyAsync(flags.data(), d_flags, static_cast<size_t>(nq) * sizeof(int32_t),
-                                  cudaMemcpyDeviceToHost, c->stream));
-        CU_TRY(c, cudaStreamSynchronize(c->stream));
-        for (int32_t q = 0; q < nq; q++) {
-            if (!flags[q]) continue;
-            RC_TRY(search_device_locked(c, dq + static_cast<size_t>(q) * c->dim, 1, k, metric, use_mask,
-                                        o_ids + q * kcols, o_dist + q * kcols, o_n + q, o_nan + q));
-        }
-        return fetch_results(c, nq, kcols, out_rowids, out_dist, out_n, out_nan);
-    }
-    RC_TRY(search_device_locked(c, dq, nq, k, metric, use_mask, o_ids, o_dist, o_n, o_nan));
-    return fetch_results(c, nq, kcols, out_rowids, out_dist, out_n, out_nan);
+    return run_and_fetch(c, dq, nq, k, metric, use_mask, out_rowids, out_dist, out_n, out_nan);
 }
 
 int clipdb_blend_search(clipdb_ctx *c, const float *e1, const float *e2, double w0, double w1,
@@ -1378,7 +1406,6 @@ int clipdb_blend_search(clipdb_ctx *c, const float *e1, const float *e2, double 
     RC_TRY(ensure_device(c, c->d_query, static_cast<size_t>(dim) * sizeof(float) + sizeof(int32_t)));
     float *d_q = static_cast<float *>(c->d_query.p);
     RC_TRY(blend_device_locked(c, st.e1, st.e2, st.w, st.negs, st.neg_w, n_neg, dim, 1, d_q, st.flags));
-    RC_TRY(search_device_locked(c, d_q, 1, k, metric, use_mask, c->r_ids, c->r_dist, c->r_n, c->r_nan));
     // optional read-back of the blended query and the fallback flags, through their own
     // pinned area so the result staging below can reuse the main one
     float *h_aux = nullptr;
@@ -1398,7 +1425,8 @@ int clipdb_blend_search(clipdb_ctx *c, const float *e1, const float *e2, double 
         CU_TRY(c, cudaMemcpyAsync(h_aux, d_q, dim * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
         CU_TRY(c, cudaMemcpyAsync(h_aux + dim, st.flags, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     }
-    RC_TRY(fetch_results(c, 1, kcols, out_rowids, out_dist, out_n, out_nan));  // syncs the stream
+    // scan (or, with the batch store and batch_min_nq = 1, bf16 pre-selection + re-rank); syncs the stream
+    RC_TRY(run_and_fetch(c, d_q, 1, k, metric, use_mask, out_rowids, out_dist, out_n, out_nan));
     if (out_query) memcpy(out_query, h_aux, dim * sizeof(float));
     if (out_flags) memcpy(out_flags, h_aux + dim, sizeof(int32_t));
     return CLIPDB_OK;

@@ -98,13 +98,18 @@ class ImageDatabase:
 
     def __init__(self, db_path: str, device: int = 0, embedder: Optional[Embedder] = None,
                  nan_policy: str = "reference", verbose: bool = False,
-                 binary_score_mode: str = "reference"):
+                 binary_score_mode: str = "reference", batch_store: bool = False):
+        """``batch_store=True`` also keeps the bf16 copy of the store (half its size again) and sends
+        every search — single queries included — through the tensor-core pre-selection + exact
+        re-rank: same results, about half the latency per query, and ``search_embeddings`` answers
+        many sessions' queries in one pass."""
         if nan_policy not in ("reference", "exclude"):
             raise ValueError("nan_policy must be 'reference' or 'exclude'")
         if binary_score_mode not in ("reference", "popcount"):
             raise ValueError("binary_score_mode must be 'reference' (uint8 wrap-around, as the reference "
                              "computes it) or 'popcount'")
         self.binary_score_mode = binary_score_mode
+        self.batch_store = bool(batch_store)
         self._codes = None                 # loader.HostCodes once the sign-code fallback is needed
         self._code_mask_key: Optional[Tuple[str, ...]] = None
         self.db_path = db_path
@@ -141,6 +146,9 @@ class ImageDatabase:
         self._code_mask_key = None
         if host.rows.shape[0]:
             self.index.load(host.rows, host.rowids)
+            if self.batch_store and self.index.dim == schema.EMBEDDING_DIM:
+                self.index.enable_batch()
+                self.index.set_option("batch_min_nq", 1)
         self._log(f"loaded {host.rows.shape[0]} rows ({host.source}); {host.dropped} vec0 rows without "
                   f"a mapping were skipped")
 
@@ -231,6 +239,30 @@ class ImageDatabase:
         return self.search_embedding(e1, k=k, embedding2=e2, weights=weights, negative_embeddings=negs,
                                      negative_weights=neg_ws, filter_folders=filter_folders,
                                      profile=profile, show_duplicates=show_duplicates)
+
+    def search_embeddings(self, embeddings, k: int = 10, filter_folders: Optional[Sequence[str]] = None
+                          ) -> List[Result]:
+        """Many ready-made query embeddings (e.g. one per interactive session) in one call: with
+        ``batch_store=True`` they share one pass over the store.  Per query the same list as
+        ``search_embedding(..., show_duplicates=True)``: (file_path, similarity), best first."""
+        q = np.ascontiguousarray(embeddings, dtype=np.float32)
+        if q.ndim != 2 or q.shape[1] != self.embedding_dim:
+            raise ValueError(f"embeddings must be [nq, {self.embedding_dim}]")
+        if self._binary_count <= 0 or self._vec0_count <= 0 or self.index.num_rows == 0:
+            return [self.search_embedding(v, k=k, filter_folders=filter_folders, show_duplicates=True) for v in q]
+        k = int(k)
+        if k < 0:
+            k = self.index.num_rows
+        use_mask = self._install_mask(filter_folders)
+        res = self.index.search(q, k, use_mask=use_mask)
+        out: List[Result] = []
+        for i in range(q.shape[0]):
+            if res.nan_rows[i] > 0 and self.nan_policy == "reference" and k > 0:
+                out.append([])            # the reference's search() returns [] (see search_embedding)
+                continue
+            rowids, dist = res.row(i)
+            out.append([(self._paths[self._rowid_to_pos[int(r)]], 1.0 - float(d)) for r, d in zip(rowids, dist)])
+        return out
 
     def _install_mask(self, filter_folders: Optional[Sequence[str]]) -> bool:
         if not filter_folders:

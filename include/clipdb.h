@@ -168,7 +168,7 @@ int clipdb_blend_search(clipdb_ctx *ctx, const float *e1, const float *e2, doubl
  * store (2 bytes per element next to the 4-byte one) so that batches of queries
  * can be pre-selected by one tcgen05 tensor-core contraction and re-ranked with
  * the exact single-query arithmetic; results are identical to clipdb_search.
- * Requirements: dim == 1152, cosine, 1 <= k <= 128, >= 65536 rows; with a mask
+ * Requirements: dim == 1152, cosine, 1 <= k <= 128 (and <= rows); with a mask
  * (clipdb_set_mask) additionally a store without zero-norm rows.  Rows appended or updated
  * after clipdb_enable_batch are picked up: the bf16 copy is rebuilt before the next batched search.
  * With the batch store enabled, clipdb_search uses this path by itself for

@@ -113,6 +113,21 @@ def test_single_query_through_the_batched_path(store):
         batched.set_option("batch_min_nq", 2)
 
 
+@pytest.mark.parametrize("n,k", [(1, 1), (100, 20), (129, 100), (5000, 128), (40_000, 100)])
+def test_small_stores(n, k):
+    """Stores smaller than a few tiles: fewer sampled groups than k means every row is a
+    candidate; more rows than the candidate capacity means the exact scan takes over."""
+    from clip_database_b200 import GpuIndex
+    rows = synth.unit_rows(n, DIM, n)
+    queries = synth.unit_rows(9, DIM, n + 1)
+    with GpuIndex(0) as exact, GpuIndex(0) as batched:
+        exact.load(rows)
+        batched.load(rows)
+        batched.enable_batch()
+        kk = min(k, n)
+        same(batched.search(queries, kk), exact.search(queries, kk))
+
+
 def test_batched_with_folder_mask():
     """The folder pre-filter bitset (idb:1509-1530) is honoured by the tensor-core path."""
     from clip_database_b200 import GpuIndex

