@@ -512,6 +512,16 @@ __device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *m
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & BP_PEER_MASK), "r"(c0), "r"(c1)
         : "memory");
 }
+// same, with an L2 eviction-priority hint (the bf16 rows stream through once; the query block is the
+// data worth keeping in L2)
+__device__ __forceinline__ void tma_load_2d_pair_hint(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar,
+                                                      uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & BP_PEER_MASK), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
 __device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                                uint32_t accumulate) {
     asm volatile(
@@ -596,6 +606,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
     if (warp == 0) {
         // ===== TMA producer (both CTAs) =====
         if (lane == 0) {
+            const uint64_t stream_policy = l2_policy_evict_first();
             int s = 0;
             uint32_t phase = 0;
             for (int t = pair; t < eff_tiles; t += pairs) {
@@ -604,7 +615,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
                     mbar_wait(&empty_bar[s], phase ^ 1u);
                     if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * BP_STAGE_BYTES);  // both CTAs' bytes
                     uint8_t *stage = tiles + s * BP_STAGE_BYTES;
-                    tma_load_2d_pair(stage, &map_rows, 0, (tile128 * BQ_K_BLOCKS + kb) * BQ_M, &full_bar[s]);
+                    tma_load_2d_pair_hint(stage, &map_rows, 0, (tile128 * BQ_K_BLOCKS + kb) * BQ_M, &full_bar[s], stream_policy);
                     tma_load_2d_pair(stage + BP_A_BYTES, &map_qhalf, kb * BQ_BLOCK_K, static_cast<int>(rank) * (NQ / 2),
                                      &full_bar[s]);
                     if (++s == BP_STAGES) {
