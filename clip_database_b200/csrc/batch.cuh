@@ -240,6 +240,7 @@ struct BatchGemmArgs {
     int total_tiles;            // ceil(n / 128)
     int tile_stride;            // 1 (FILTER) or the sampling stride (DUMP)
     int cand_cap;
+    unsigned int *tile_counter; // CTA-pair kernel: dynamic tile scheduler, zeroed before the launch
 };
 
 // ---- filter epilogue ---------------------------------------------------------------------------
@@ -546,6 +547,18 @@ __device__ __forceinline__ void mbar_arrive_on_cta(uint64_t *bar, uint32_t cta) 
     // the filter's global atomics to drain (ERRBAR, visible in the first profile)
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
+// store a 32-bit value at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void st_shared_on_cta(const void *local, uint32_t cta, uint32_t v) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local)), "r"(cta));
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote), "r"(v) : "memory");
+}
+// arrive on the barrier at this offset in CTA `cta`, releasing this thread's earlier (remote) stores
+__device__ __forceinline__ void mbar_arrive_release_on_cta(uint64_t *bar, uint32_t cta) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
     do {
@@ -571,6 +584,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
     uint64_t *tmem_full = empty_bar + BP_STAGES;   // [2]
     uint64_t *tmem_empty = tmem_full + 2;          // [2], the leader's copy counts both CTAs' epilogues
     uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    // Dynamic tile scheduler.  The leader's producer thread claims pair tiles from a global counter
+    // (CTA pairs drift apart: with a static interleave the fastest SMs idled ~10 % of the launch,
+    // ncu smsp__cycles_active vs sm__cycles_elapsed) and publishes each claim in BOTH CTAs: a ring
+    // of BP_TQ tile indices guarded by one mbarrier per entry.  Everyone who needs the tile index
+    // (the peer's producer, the MMA issuer, all epilogue warps) waits on that entry; -1 ends the
+    // launch.  An entry is reused BP_TQ = 4 iterations later, by which time its readers are done:
+    // the producer cannot run ahead of iteration it-1's MMAs (the operand ring is shorter than a
+    // tile), those waited for the accumulator freed at the END of epilogue it-3.
+    constexpr int BP_TQ = 4;
+    uint64_t *tq_full = reinterpret_cast<uint64_t *>(bq_smem_raw + 512);
+    volatile int *tile_ring = reinterpret_cast<volatile int *>(bq_smem_raw + 512 + BP_TQ * 8);
     float *thr_s = reinterpret_cast<float *>(bq_smem_raw + 1024);
     const uint32_t raw_addr = smem_u32(bq_smem_raw);
     const uint32_t tiles_addr = (raw_addr + BQ_HEADER + 1023u) & ~1023u;
@@ -579,7 +603,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
-    const int pair = blockIdx.x >> 1, pairs = gridDim.x >> 1;
     const int total_pair_tiles = (a.total_tiles + 1) / 2;                       // 256 rows each
     const int eff_tiles = (total_pair_tiles + a.tile_stride - 1) / a.tile_stride;
 
@@ -592,6 +615,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
             mbar_init(&tmem_full[b], 1);
             mbar_init(&tmem_empty[b], 8);   // 4 epilogue warps in each of the two CTAs
         }
+        for (int i = 0; i < BP_TQ; i++) mbar_init(&tq_full[i], 1);
         mbar_fence_init();
     }
     if (!DUMP)
@@ -604,18 +628,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
     const uint32_t tmem_base = *tmem_base_slot;
 
     if (warp == 0) {
-        // ===== TMA producer (both CTAs) =====
+        // ===== TMA producer (both CTAs); the leader's also schedules =====
         if (lane == 0) {
             const uint64_t stream_policy = l2_policy_evict_first();
+            auto claim = [&]() {
+                const unsigned t = atomicAdd(a.tile_counter, 1u);
+                return t < static_cast<unsigned>(eff_tiles) ? static_cast<int>(t) : -1;
+            };
             int s = 0;
             uint32_t phase = 0;
-            for (int t = pair; t < eff_tiles; t += pairs) {
+            int next = leader ? claim() : 0;
+            for (int it = 0;; it++) {
+                const int slot = it & (BP_TQ - 1);
+                int t;
+                if (leader) {
+                    t = next;
+                    tile_ring[slot] = t;
+                    st_shared_on_cta(const_cast<int *>(tile_ring + slot), 1, static_cast<uint32_t>(t));
+                    mbar_arrive(&tq_full[slot]);
+                    mbar_arrive_release_on_cta(&tq_full[slot], 1);
+                    if (t >= 0) next = claim();   // claimed ahead: the latency hides behind this tile's loads
+                } else {
+                    mbar_wait_cluster(&tq_full[slot], static_cast<uint32_t>(it / BP_TQ) & 1u);
+                    t = tile_ring[slot];
+                }
+                if (t < 0) break;
                 const int tile128 = t * a.tile_stride * 2 + static_cast<int>(rank);
                 for (int kb = 0; kb < BQ_K_BLOCKS; kb++) {
                     mbar_wait(&empty_bar[s], phase ^ 1u);
                     if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * BP_STAGE_BYTES);  // both CTAs' bytes
                     uint8_t *stage = tiles + s * BP_STAGE_BYTES;
-                    tma_load_2d_pair_hint(stage, &map_rows, 0, (tile128 * BQ_K_BLOCKS + kb) * BQ_M, &full_bar[s], stream_policy);
+                    tma_load_2d_pair_hint(stage, &map_rows, 0, (tile128 * BQ_K_BLOCKS + kb) * BQ_M, &full_bar[s],
+                                          stream_policy);
                     tma_load_2d_pair(stage + BP_A_BYTES, &map_qhalf, kb * BQ_BLOCK_K, static_cast<int>(rank) * (NQ / 2),
                                      &full_bar[s]);
                     if (++s == BP_STAGES) {
@@ -630,8 +674,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
         if (leader && lane == 0) {
             int s = 0;
             uint32_t phase = 0;
-            int it = 0;
-            for (int t = pair; t < eff_tiles; t += pairs, it++) {
+            for (int it = 0;; it++) {
+                mbar_wait(&tq_full[it & (BP_TQ - 1)], static_cast<uint32_t>(it / BP_TQ) & 1u);
+                if (tile_ring[it & (BP_TQ - 1)] < 0) break;
                 const int acc = it & 1;
                 mbar_wait_cluster(&tmem_empty[acc], (static_cast<uint32_t>(it >> 1) & 1u) ^ 1u);
                 tc_fence_after();
@@ -664,8 +709,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
         hq.qry = hq.row + BQ_QUEUE_CAP;
         hq.u = hq.qry + BQ_QUEUE_CAP;
         hq.fill = 0;
-        int it = 0;
-        for (int t = pair; t < eff_tiles; t += pairs, it++) {
+        for (int it = 0;; it++) {
+            mbar_wait_cluster(&tq_full[it & (BP_TQ - 1)], static_cast<uint32_t>(it / BP_TQ) & 1u);
+            const int t = tile_ring[it & (BP_TQ - 1)];
+            if (t < 0) break;
             const int acc = it & 1;
             const long long t128 = static_cast<long long>(t) * a.tile_stride * 2 + rank;   // 128-row tile index
             const long long row = t128 * BQ_M + lane_base + lane;

@@ -95,7 +95,7 @@ struct clipdb_ctx {
     bool batch_dirty = false;            // rows changed since the bf16 copy was built (rebuilt on next use)
     unsigned long long batch_bad_rows = 0;  // zero-norm / non-finite rows found when the copy was built
     Buffer bf16_rows, bad_rows, bq_queries, bq_qnorm, bq_scores, bq_thr, bq_flags, bq_count, bq_cand, bq_parts, bq_qerr, row_err;
-    Buffer bq_cand_u, bq_margin, bq_surv, bq_surv_count;
+    Buffer bq_cand_u, bq_margin, bq_surv, bq_surv_count, bq_tilectr;
     CUtensorMap map_rows, map_q, map_qhalf[3];   // query-half boxes for 64 / 128 / 256 queries per pass
     int64_t bq_sample_groups_used = 0;  // groups the last pass A wrote
     int64_t batch_min_nq = 2;       // clipdb_search switches to the batched path from this nq (one batch
@@ -706,6 +706,7 @@ int batch_build_locked(clipdb_ctx *c) {
     RC_TRY(ensure_device(c, c->bq_margin, BQ_N * sizeof(float)));
     RC_TRY(ensure_device(c, c->bq_surv, static_cast<size_t>(BQ_N) * c->batch_cand_cap * sizeof(unsigned int)));
     RC_TRY(ensure_device(c, c->bq_surv_count, BQ_N * sizeof(unsigned int)));
+    RC_TRY(ensure_device(c, c->bq_tilectr, 2 * sizeof(unsigned int)));
     RC_TRY(ensure_device(c, c->bq_parts, static_cast<size_t>(BQ_N) * 8 * 128 * sizeof(uint64_t)));
     CU_TRY(c, cudaMemsetAsync(c->bad_rows.p, 0, sizeof(unsigned long long), c->stream));
     build_bf16_store_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(
@@ -834,6 +835,9 @@ int batch_search_device_locked(clipdb_ctx *c, const float *d_queries, int32_t nq
     g.total_tiles = tiles;
     g.cand_cap = static_cast<int>(c->batch_cand_cap);
 
+    // dynamic tile scheduler counters of the CTA-pair kernel: [0] pass A, [1] pass B
+    CU_TRY(c, cudaMemsetAsync(c->bq_tilectr.p, 0, 2 * sizeof(unsigned int), c->stream));
+    g.tile_counter = static_cast<unsigned int *>(c->bq_tilectr.p);
     // pass A: group maxima over a tile sample -> per-query thresholds
     const bool pair = c->batch_cta_pair != 0 && (c->sm_count % 2 == 0);
     const int pair_grid = c->sm_count & ~1;
@@ -866,6 +870,7 @@ int batch_search_device_locked(clipdb_ctx *c, const float *d_queries, int32_t nq
     // pass B: all tiles, keep (q,row) above the threshold
     CU_TRY(c, cudaMemsetAsync(c->bq_count.p, 0, BQ_N * sizeof(unsigned int), c->stream));
     g.tile_stride = 1;
+    g.tile_counter = static_cast<unsigned int *>(c->bq_tilectr.p) + 1;
     RC_TRY(profile_mark(c, true));
     if (pair) {
         const int ptiles = (tiles + 1) / 2;
@@ -1020,7 +1025,7 @@ void clipdb_destroy(clipdb_ctx *c) {
                           &c->cub_tmp, &c->d_query, &c->d_results, &c->d_blend_in, &c->d_blend_flags, &c->bf16_rows,
                           &c->bad_rows, &c->bq_queries, &c->bq_qnorm, &c->bq_scores, &c->bq_thr, &c->bq_flags,
                           &c->bq_count, &c->bq_cand, &c->bq_parts, &c->bq_qerr, &c->row_err, &c->bq_cand_u, &c->bq_margin,
-                          &c->bq_surv, &c->bq_surv_count};
+                          &c->bq_surv, &c->bq_surv_count, &c->bq_tilectr};
         for (Buffer *b : bufs) free_buffer(*b);
         if (c->pinned.p) cudaFreeHost(c->pinned.p);
         if (c->pinned_aux.p) cudaFreeHost(c->pinned_aux.p);
