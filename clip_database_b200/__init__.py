@@ -8,6 +8,7 @@ plus the query blend / negative-prompt arithmetic before it (:1378-1398, :545-60
   GpuIndex        one GPU's resident row store + kernels (ctypes over the C ABI)
   ImageDatabase   the reference's ``search()`` surface on top of it
   ShardedIndex    row-sharded multi-GPU search (torch.distributed)
+  dropin.install  patch the reference class's own search() to use this path
 
 Importing this package does not need a GPU; creating a ``GpuIndex`` does, and
 fails loudly without one (no CPU fallback).

@@ -158,6 +158,9 @@ class ImageDatabase:
         the number of rows appended.  In-place UPDATEs of old rows need ``reload()``."""
         last = int(self._rowids[-1]) if len(self._paths) else None
         host = loader.read_store(self.db_path, expect_dim=self.index.dim or None, min_rowid=last)
+        if host.binary_count != self._binary_count:
+            self._codes = None            # sign codes were added: the fallback store is re-read on next use
+            self._code_mask_key = None
         self._binary_count = host.binary_count
         self._vec0_count = self._vec0_count + host.vec0_count if last is not None else host.vec0_count
         m = host.rows.shape[0]
