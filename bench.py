@@ -360,8 +360,8 @@ def run_batch_workload(args, torch, idx, rows, rows_per_gpu, device, rank, local
                 "flops_per_launch": flops, "avg_launch_ms": gemm_avg, "launches_timed": int(gemm_n),
                 "hbm_GBps_bf16_store": store_gbps, "live_cublas_tflops": live,
                 "frac_of_live_cublas": (tflops / live) if live else None,
-                "traffic": 23041031000.0 + 22817792.0 if rows_per_gpu == 10_000_000 and B == 256 else None,
-                "traffic_source": "profiles/r01v3_gemm_ncu_raw.csv (dram read + write, one launch)"}
+                "traffic": 23040801000.0 + 9860352.0 if rows_per_gpu == 10_000_000 and B == 256 else None,
+                "traffic_source": "profiles/r01v4_gemm_ncu_raw.csv (dram read + write, one launch)"}
     else:           # 64 / 128 queries per pass: the contraction streams the bf16 store -> HBM-bound
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         roof = {"bound": "hbm", "kernel": "batch_gemm_pair_kernel<FILTER, %d>" % (64 if B <= 64 else 128),

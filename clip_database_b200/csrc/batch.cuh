@@ -241,6 +241,7 @@ struct BatchGemmArgs {
     int tile_stride;            // 1 (FILTER) or the sampling stride (DUMP)
     int cand_cap;
     unsigned int *tile_counter; // CTA-pair kernel: dynamic tile scheduler, zeroed before the launch
+    int static_tiles;           // CTA-pair kernel: 1 = static interleave (pair p takes tiles p, p + pairs, ...)
 };
 
 // ---- filter epilogue ---------------------------------------------------------------------------
@@ -631,8 +632,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
         // ===== TMA producer (both CTAs); the leader's also schedules =====
         if (lane == 0) {
             const uint64_t stream_policy = l2_policy_evict_first();
+            unsigned static_next = blockIdx.x >> 1;
             auto claim = [&]() {
-                const unsigned t = atomicAdd(a.tile_counter, 1u);
+                unsigned t;
+                if (a.static_tiles) {
+                    t = static_next;
+                    static_next += gridDim.x >> 1;
+                } else {
+                    t = atomicAdd(a.tile_counter, 1u);
+                }
                 return t < static_cast<unsigned>(eff_tiles) ? static_cast<int>(t) : -1;
             };
             int s = 0;
@@ -892,6 +900,13 @@ __global__ void __launch_bounds__(BQ_THR_THREADS) batch_threshold_kernel(const f
                                                                          int *__restrict__ flags) {
     __shared__ SelectSmem<BQ_THR_QPC> sm;
     const int q0 = blockIdx.x * BQ_THR_QPC;
+    if (q0 >= nq) {   // padding slots only: never produce candidates, nothing to select
+        if (threadIdx.x < BQ_THR_QPC) {
+            thr[q0 + threadIdx.x] = __int_as_float(0x7f800000);
+            margin[q0 + threadIdx.x] = 0.f;
+        }
+        return;
+    }
     const int mine = threadIdx.x < BQ_THR_QPC ? threadIdx.x : 0;
     const float tau = radix_select_kth_largest<BQ_THR_QPC, BQ_THR_THREADS>(
         sm, k, mine, [&](int ql, unsigned i) { return __ldg(scores + static_cast<long long>(i) * BQ_N + q0 + ql); },

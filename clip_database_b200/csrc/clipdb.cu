@@ -104,6 +104,7 @@ struct clipdb_ctx {
     int64_t batch_cta_pair = 1;     // 1: cta_group::2 contraction (CTA pairs), 0: single-CTA kernel
     int64_t batch_sample_stride = 0; // pass A visits every s-th 128-row tile; 0 = auto (tiles/1024 clamped to 1..64)
     int64_t batch_refine = 1;       // 1: second threshold from the candidates' own scores before the re-rank
+    int64_t batch_static_tiles = 0; // 1: static tile interleave in the CTA-pair kernel (for A/B measurements)
     int64_t batch_npass = 0;        // 0: auto (64 / 128 / 256 queries per pass by batch size); else force >= that
 
     // scan-kernel event timing (clipdb_profile)
@@ -838,6 +839,7 @@ int batch_search_device_locked(clipdb_ctx *c, const float *d_queries, int32_t nq
     // dynamic tile scheduler counters of the CTA-pair kernel: [0] pass A, [1] pass B
     CU_TRY(c, cudaMemsetAsync(c->bq_tilectr.p, 0, 2 * sizeof(unsigned int), c->stream));
     g.tile_counter = static_cast<unsigned int *>(c->bq_tilectr.p);
+    g.static_tiles = static_cast<int>(c->batch_static_tiles);
     // pass A: group maxima over a tile sample -> per-query thresholds
     const bool pair = c->batch_cta_pair != 0 && (c->sm_count % 2 == 0);
     const int pair_grid = c->sm_count & ~1;
@@ -1084,6 +1086,7 @@ static int64_t *option_slot(clipdb_ctx *c, const char *name) {
     if (!strcmp(name, "batch_sample_stride")) return &c->batch_sample_stride;
     if (!strcmp(name, "batch_refine")) return &c->batch_refine;
     if (!strcmp(name, "batch_npass")) return &c->batch_npass;
+    if (!strcmp(name, "batch_static_tiles")) return &c->batch_static_tiles;
     return nullptr;
 }
 
