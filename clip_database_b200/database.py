@@ -98,11 +98,14 @@ class ImageDatabase:
 
     def __init__(self, db_path: str, device: int = 0, embedder: Optional[Embedder] = None,
                  nan_policy: str = "reference", verbose: bool = False,
-                 binary_score_mode: str = "reference", batch_store: bool = False):
+                 binary_score_mode: str = "reference", batch_store: bool = False,
+                 devices: Optional[Sequence[int]] = None):
         """``batch_store=True`` also keeps the bf16 copy of the store (half its size again) and sends
         every search — single queries included — through the tensor-core pre-selection + exact
         re-rank: same results, about half the latency per query, and ``search_embeddings`` answers
-        many sessions' queries in one pass."""
+        many sessions' queries in one pass.  ``devices=[0, 1, ...]`` row-shards the store over
+        several GPUs of the box from this one process (``multigpu.MultiGpuIndex``: one launch per
+        GPU per query, candidates exchanged over NVLink inside the scan kernel)."""
         if nan_policy not in ("reference", "exclude"):
             raise ValueError("nan_policy must be 'reference' or 'exclude'")
         if binary_score_mode not in ("reference", "popcount"):
@@ -116,7 +119,13 @@ class ImageDatabase:
         self.embedder = embedder
         self.nan_policy = nan_policy
         self.verbose = verbose
-        self.index = GpuIndex(device)
+        if devices is not None and len(devices) > 1:
+            if batch_store:
+                raise ValueError("batch_store is a single-GPU option")
+            from .multigpu import MultiGpuIndex
+            self.index = MultiGpuIndex(devices)
+        else:
+            self.index = GpuIndex(device if not devices else int(devices[0]))
         self._paths: List[str] = []
         self._lowered: Optional[List[bytes]] = None
         self._image_ids = np.zeros(0, dtype=np.int64)
@@ -257,13 +266,17 @@ class ImageDatabase:
         if k < 0:
             k = self.index.num_rows
         use_mask = self._install_mask(filter_folders)
-        res = self.index.search(q, k, use_mask=use_mask)
+        multi = hasattr(self.index, "shards")
+        res = None if multi else self.index.search(q, k, use_mask=use_mask)
         out: List[Result] = []
         for i in range(q.shape[0]):
-            if res.nan_rows[i] > 0 and self.nan_policy == "reference" and k > 0:
+            if multi:
+                rowids, dist, nan = self.index.search_any_k(q[i], k, use_mask)
+            else:
+                (rowids, dist), nan = res.row(i), int(res.nan_rows[i])
+            if nan > 0 and self.nan_policy == "reference" and k > 0:
                 out.append([])            # the reference's search() returns [] (see search_embedding)
                 continue
-            rowids, dist = res.row(i)
             out.append([(self._paths[self._rowid_to_pos[int(r)]], 1.0 - float(d)) for r, d in zip(rowids, dist)])
         return out
 

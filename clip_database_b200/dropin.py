@@ -37,7 +37,8 @@ class _ReferenceEmbedder(Embedder):
 
 def install(reference_cls, device: int = 0, **database_kwargs):
     """Patch ``reference_cls.search`` in place; returns the class.  ``database_kwargs`` go to
-    ``clip_database_b200.ImageDatabase`` (``nan_policy``, ``binary_score_mode``, ``batch_store``)."""
+    ``clip_database_b200.ImageDatabase`` (``nan_policy``, ``binary_score_mode``, ``batch_store``,
+    ``devices=[...]`` to row-shard the store over several GPUs)."""
     if getattr(reference_cls, "_b200_original_search", None) is not None:
         uninstall(reference_cls)
     original = reference_cls.search

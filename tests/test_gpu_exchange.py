@@ -104,3 +104,39 @@ def test_missing_peer_times_out_instead_of_hanging():
         a.search_sharded_device(q[0], 5, o[0], o[1], o[2])      # rank 1 never searches
         a.synchronize()
         assert int(o[2][0]) == -1
+
+
+@pytest.mark.parametrize("k", [20, 100])
+def test_single_process_multi_gpu_index(k):
+    """MultiGpuIndex: the shards are contexts of this process — on every visible GPU when there are
+    several (real peer stores over NVLink), else three shards on the one GPU."""
+    assert have_gpu()
+    import torch
+    from clip_database_b200 import GpuIndex
+    from clip_database_b200.multigpu import MultiGpuIndex
+    n_dev = torch.cuda.device_count()
+    devices = list(range(min(n_dev, 4))) if n_dev > 1 else [0, 0, 0]
+    n = 50_000
+    rows = synth.unit_rows(n, DIM, 4321)
+    rows[n - 2] = rows[10]
+    rows[30_000] = 0
+    queries = synth.unit_rows(4, DIM, 77)
+    queries[3] = rows[10]
+    with GpuIndex(0) as whole:
+        whole.load(rows, np.arange(1, n + 1))
+        want = whole.search(queries, k)
+        mask = np.arange(n) % 5 != 0
+        whole.set_mask(mask)
+        want_masked = whole.search(queries, k, use_mask=True)
+    with MultiGpuIndex(devices, scan_ctas=None if n_dev > 1 else 24, timeout_ms=20000) as multi:
+        multi.load(rows, np.arange(1, n + 1))
+        for qi in range(4):
+            before = multi.launch_count
+            ids, dist, nan = multi.search(queries[qi], k)
+            assert multi.launch_count - before == len(devices), "one launch per shard"
+            assert np.array_equal(ids, want.rowids[qi]) and nan == want.nan_rows[qi]
+            assert np.array_equal(dist.view(np.uint32), want.distances[qi].view(np.uint32))
+        multi.set_mask(mask)
+        ids, dist, nan = multi.search(queries[3], k, use_mask=True)
+        assert np.array_equal(ids, want_masked.rowids[3])
+        assert np.array_equal(dist.view(np.uint32), want_masked.distances[3].view(np.uint32))

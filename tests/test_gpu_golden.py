@@ -134,3 +134,37 @@ def test_search_embeddings_equals_one_at_a_time(tmp_path):
     finally:
         one.close()
         many.close()
+
+
+@pytest.mark.parametrize("name", ["single_k20", "self_match_ties", "blend_07_03_negative", "folder_filter",
+                                  "orphan_rows", "zero_row_gives_empty", "k_exceeds_rows", "k_negative_unlimited",
+                                  "duplicate_filter_default"])
+def test_search_on_a_row_sharded_store(golden, name, tmp_path):
+    """ImageDatabase(devices=[...]): the store row-sharded over the box's GPUs from one process (two
+    shards on the one GPU when there is only one) returns what the reference returned."""
+    import torch
+    from clip_database_b200 import ImageDatabase
+    case = next(c for c in golden["cases"] if c["name"] == name)
+    rows, paths, kwargs, vectors, drop_m, drop_i = golden_cases.inputs_for(case)
+    db_path = str(tmp_path / (name + ".db"))
+    synth.write_reference_db(db_path, rows, paths, drop_mapping_for=drop_m, drop_image_for=drop_i)
+    n_dev = torch.cuda.device_count()
+    devices = list(range(min(n_dev, 4))) if n_dev > 1 else [0, 0]
+    db = ImageDatabase(db_path, embedder=TableEmbedder(vectors), devices=devices)
+    try:
+        results = db.search("q1", **kwargs)
+    finally:
+        db.close()
+    pos = {p: i for i, p in enumerate(paths)}
+    got_pos = np.array([pos[p] for p, _ in results], dtype=np.int64)
+    got_sim = np.array([s for _, s in results], dtype=np.float64)
+    exp_pos = np.array(case["expected_positions"], dtype=np.int64)
+    exp_sim = np.array(case["expected_similarities"], dtype=np.float64)
+    assert got_pos.shape == exp_pos.shape
+    assert np.all(np.abs(got_sim - exp_sim) <= tol(1.0 - exp_sim))
+    diff = got_pos != exp_pos
+    if diff.any():
+        e1, e2, weights, negs, ws = golden_cases.embedding_call(kwargs, vectors)
+        q = oblend.compose_query(e1, e2, weights, negs, ws)
+        own = 1.0 - ref.distances(rows[got_pos[diff]], q).astype(np.float64)
+        assert np.all(np.abs(own - exp_sim[diff]) <= tol(1.0 - exp_sim[diff])), name
