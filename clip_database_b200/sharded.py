@@ -3,16 +3,25 @@ reference is one process, one thread).
 
 The embedding matrix is split into contiguous rowid ranges, one per rank / GPU.
 Every rank scans its shard for the (replicated) query and produces a local top-k;
-the only exchange is ONE all-gather of a packed k-entry record per rank
-(8 + 12k + 4 bytes, 252 B at k = 20), after which every rank merges the G lists
-with the same (distance, rowid) order.  Because shards are contiguous in rowid
-order, (distance, shard, position) == (distance, rowid), so the sharded answer is
-bit-identical to the unsharded one.
+the only exchange step is that every rank's k candidates reach every rank, which then
+merges the G lists with the same (distance, rowid) order.  Because shards are
+contiguous in rowid order, (distance, shard, position) == (distance, rowid), so the
+sharded answer is bit-identical to the unsharded one.  Two ways to do the exchange:
 
-``ShardedIndex`` is the orchestration (record layout, collective, merge order);
+  fused (default)  ``clipdb_search_sharded_device``: the scan kernel's last CTA stores its
+                   shard's candidates into every peer GPU's inbox over NVLink (peer memory
+                   mapped with CUDA IPC), waits for theirs and merges — ONE launch per rank per
+                   query, no collective call.  ``torch.distributed`` is used once, to swap the
+                   64-byte IPC handles.
+  NCCL             ONE all-gather of a packed k-entry record per rank (8 + 12k + 4 bytes,
+                   252 B at k = 20) followed by a merge kernel.  Also used for batched
+                   searches (nq x k candidates per rank).
+
+``ShardedIndex`` is the orchestration (record layout, exchange, merge order);
 the per-rank work is delegated to a backend.  The product backend is
-``CudaShardBackend`` (CUDA kernels through the C ABI, NCCL collective); tests
-drive the same orchestration over gloo with a CPU stand-in backend.
+``CudaShardBackend`` (CUDA kernels through the C ABI); tests drive the same
+orchestration over gloo with a CPU stand-in backend.  ``multigpu.MultiGpuIndex`` is the
+single-process variant (the ranks are contexts of one process).
 """
 from __future__ import annotations
 
