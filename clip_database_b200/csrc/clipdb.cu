@@ -1097,6 +1097,10 @@ int clipdb_set_option(clipdb_ctx *c, const char *name, int64_t value) {
     if (!slot) return fail(c, CLIPDB_ERR_INVALID, "unknown option '%s'", name ? name : "(null)");
     if (value < 0 || value > (1 << 20)) return fail(c, CLIPDB_ERR_INVALID, "option '%s' out of range", name);
     if (slot == &c->ldg_ctas_per_sm && value == 0) value = 1;
+    if (slot == &c->batch_cand_cap) {
+        if (value < 256) return fail(c, CLIPDB_ERR_INVALID, "option 'batch_cand_cap' must be at least 256");
+        if (c->batch_enabled && value != *slot) c->batch_dirty = true;   // candidate buffers are sized at build time
+    }
     *slot = value;
     return CLIPDB_OK;
 }

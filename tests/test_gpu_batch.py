@@ -211,6 +211,19 @@ def test_batched_overflow_falls_back():
         same(batched.search(queries, 50), exact.search(queries, 50))
 
 
+def test_candidate_capacity_can_change_after_enable(store):
+    """batch_cand_cap sizes device buffers: changing it on a live batch store rebuilds them."""
+    rows, exact, batched = store
+    queries = synth.unit_rows(50, DIM, 909)
+    want = exact.search(queries, 100)
+    try:
+        for cap in (65536, 256, 32768):      # 256: every query overflows and is re-run exactly
+            batched.set_option("batch_cand_cap", cap)
+            same(batched.search(queries, 100), want)
+    finally:
+        batched.set_option("batch_cand_cap", 32768)
+
+
 def test_batch_device_entry_point(store):
     import torch
     rows, exact, batched = store
