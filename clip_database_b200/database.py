@@ -306,9 +306,9 @@ class ImageDatabase:
             return []
         if self._vec0_count <= 0:
             # vec0 is empty: the sign-code fallback (:1591-1629)
-            results = self._binary_fallback(embedding1, k, embedding2, weights, negative_embeddings,
-                                            negative_weights, filter_folders, timings)
-            return self._finish(results, show_duplicates, profile, timings)
+            results, codes = self._binary_fallback(embedding1, k, embedding2, weights, negative_embeddings,
+                                                   negative_weights, filter_folders, timings)
+            return self._finish(results, show_duplicates, profile, timings, codes=codes)
         try:
             k = int(k)
             t0 = time.time()
@@ -327,13 +327,15 @@ class ImageDatabase:
                 # SQLite stores a NaN distance as NULL, NULLs sort first, and the reference's
                 # `1.0 - distance` then raises inside its try block (:1588, :1637-1640)
                 raise TypeError("unsupported operand type(s) for -: 'float' and 'NoneType'")
-            top = [(self._paths[self._rowid_to_pos[int(r)]], 1.0 - float(d)) for r, d in zip(rowids, dist)]
+            positions = [self._rowid_to_pos[int(r)] for r in rowids]
+            top = [(self._paths[p], 1.0 - float(d)) for p, d in zip(positions, dist)]
             timings["db_query"] = time.time() - t0
             results = [(p, float(s)) for p, s in top]
+            image_ids = {self._paths[p]: int(self._image_ids[p]) for p in positions}
         except Exception as e:                       # error envelope, :1637-1640
             print(f"Error during search: {e}")
             return []
-        return self._finish(results, show_duplicates, profile, timings)
+        return self._finish(results, show_duplicates, profile, timings, image_ids=image_ids)
 
     # ---- sign-code fallback (vec0 empty, image_database.py:1591-1629) -------------------------
     def _filtered_statement_walks_the_path_index(self) -> bool:
@@ -386,16 +388,18 @@ class ImageDatabase:
             pos, scores = self.index.binary_search(code, kk, score_mode=self.binary_score_mode, use_mask=use_mask)
             results = [(paths[int(p)], float(int(s)) / self.embedding_dim) for p, s in zip(pos, scores)]
             timings["db_query"] = time.time() - t0
-            return results
+            # the stored sign codes of the results are already in host memory (the duplicate filter needs them)
+            return results, {paths[int(p)]: self._codes.codes[int(p)] for p in pos}
         except Exception as e:                       # error envelope, :1637-1640
             print(f"Error during search: {e}")
-            return []
+            return [], {}
 
-    def _finish(self, results: Result, show_duplicates: bool, profile: bool, timings) -> Result:
+    def _finish(self, results: Result, show_duplicates: bool, profile: bool, timings,
+                image_ids: Optional[Dict[str, int]] = None, codes: Optional[Dict[str, np.ndarray]] = None) -> Result:
         import time
         if not show_duplicates and len(results) > 0:
             t0 = time.time()
-            results = self._filter_duplicates(results, tolerance_bits=2)
+            results = self._filter_duplicates(results, tolerance_bits=2, image_ids=image_ids, codes=codes)
             timings["filter_duplicates"] = time.time() - t0
         if profile and timings:
             print("\n=== Search Performance Profile ===")
@@ -407,17 +411,29 @@ class ImageDatabase:
             print("=" * 40 + "\n")
         return results
 
-    def _filter_duplicates(self, results: Result, tolerance_bits: int = 2) -> Result:
-        """Fetch the k results' stored sign codes (as the reference does per search,
-        image_database.py:1232-1255) and apply ``filter_duplicates``."""
+    def _filter_duplicates(self, results: Result, tolerance_bits: int = 2,
+                           image_ids: Optional[Dict[str, int]] = None,
+                           codes: Optional[Dict[str, np.ndarray]] = None) -> Result:
+        """Apply ``filter_duplicates`` to the k results' stored sign codes.  The reference fetches
+        them per search with one ``SELECT id FROM images WHERE file_path = ?`` per result and one
+        ``IN (...)`` query (image_database.py:1232-1255); here the image ids come from the join
+        made at load time (same ids: ``ie.image_id = i.id``), so only the ``IN`` query remains, and
+        the sign-code fallback passes the codes it already holds."""
+        if codes is not None:
+            before = len(results)
+            out = filter_duplicates(results, codes, tolerance_bits)
+            if len(out) < before:
+                print(f"Filtered out {before - len(out)} duplicate(s) (tolerance: {tolerance_bits} bits)")
+            return out
         conn = loader.connect(self.db_path)
         try:
-            ids = {}
-            for path, _ in results:
-                row = conn.execute("SELECT id FROM images WHERE file_path = ?", (path,)).fetchone()
-                if row:
-                    ids[path] = row[0]
-            codes: Dict[str, np.ndarray] = {}
+            ids = dict(image_ids) if image_ids is not None else {}
+            if image_ids is None:
+                for path, _ in results:
+                    row = conn.execute("SELECT id FROM images WHERE file_path = ?", (path,)).fetchone()
+                    if row:
+                        ids[path] = row[0]
+            codes = {}
             if ids:
                 id_list = list(ids.values())
                 by_id = {}
