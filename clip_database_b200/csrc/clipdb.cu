@@ -100,7 +100,7 @@ struct clipdb_ctx {
     int64_t bq_sample_groups_used = 0;  // groups the last pass A wrote
     int64_t batch_min_nq = 2;       // clipdb_search switches to the batched path from this nq (one batch
                                     // costs about one single-query scan, whatever its size)
-    int64_t batch_cand_cap = 32768; // candidate rows kept per query
+    int64_t batch_cand_cap = 65536; // candidate rows kept per query (8x the ~8,000 the default sampling admits)
     int64_t batch_cta_pair = 1;     // 1: cta_group::2 contraction (CTA pairs), 0: single-CTA kernel
     int64_t batch_sample_stride = 0; // pass A visits every s-th 128-row tile; 0 = auto (tiles/1024 clamped to 1..64)
     int64_t batch_refine = 1;       // 1: second threshold from the candidates' own scores before the re-rank
@@ -665,14 +665,15 @@ constexpr int64_t BATCH_MIN_ROWS = 1;   // any non-empty store: with fewer sampl
 
 // Pass A's sampling stride in 128-row tiles.  Sparser sampling makes pass A cheaper and the
 // thresholds looser: pass B then keeps about 1.25 * k * stride candidates per query (measured),
-// which must stay well inside the candidate capacity.  Auto: capacity / (4k), at most every 256th
+// which must stay well inside the candidate capacity.  Auto: min(capacity, 32768) / (4k), at most every 256th
 // tile, never fewer than 8k sampled 32-row groups; a power of two so the CTA-pair kernel (256-row
 // pair tiles) samples the same fraction.
 int batch_sample_stride(const clipdb_ctx *c, int64_t tiles, int k) {
     int64_t s = c->batch_sample_stride;
     if (s <= 0) {
         const int64_t kk = k > 0 ? k : 1;
-        s = c->batch_cand_cap / (4 * kk);
+        const int64_t budget = c->batch_cand_cap < 32768 ? c->batch_cand_cap : 32768;   // keep 2x+ headroom
+        s = budget / (4 * kk);
         if (s > tiles / (2 * kk)) s = tiles / (2 * kk);   // at least 8k group maxima to pick the k-th from
     }
     if (s > BQ_SAMPLE_STRIDE_MAX) s = BQ_SAMPLE_STRIDE_MAX;

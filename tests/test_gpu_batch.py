@@ -217,11 +217,11 @@ def test_candidate_capacity_can_change_after_enable(store):
     queries = synth.unit_rows(50, DIM, 909)
     want = exact.search(queries, 100)
     try:
-        for cap in (65536, 256, 32768):      # 256: every query overflows and is re-run exactly
+        for cap in (131072, 256, 32768):     # 256: every query overflows and is re-run exactly
             batched.set_option("batch_cand_cap", cap)
             same(batched.search(queries, 100), want)
     finally:
-        batched.set_option("batch_cand_cap", 32768)
+        batched.set_option("batch_cand_cap", 65536)
 
 
 def test_batch_device_entry_point(store):
