@@ -56,6 +56,9 @@ def parse_args():
                          "batch: configs[2] (B queries per step through the tcgen05 contraction + fp32 re-rank); "
                          "binary: the sign-code fallback search (SURVEY §8 f-4) over bit-packed codes")
     ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--data", default="uniform", choices=["uniform", "clustered"],
+                    help="uniform: seeded random unit rows and queries (BASELINE configs); clustered: 1024 clusters, "
+                         "queries near stored rows (SURVEY §8d variant)")
     ap.add_argument("--sample-stride", type=int, default=0, help="batch: pass A sampling stride (0 = auto)")
     ap.add_argument("--no-refine", action="store_true", help="batch: skip the second threshold")
     ap.add_argument("--exchange", default="auto", choices=["auto", "fused", "nccl"],
@@ -252,19 +255,47 @@ def run_reference_arm(args):
 
 
 # ---------------------------------------------------------------- GPU arm -----------------
-def generate_rows(torch, device, n_rows, seed):
+N_CLUSTERS = 1024
+
+
+def generate_rows(torch, device, n_rows, seed, clustered=False):
     """randn float32 from a seeded CUDA generator, in chunks,
-    rows L2-normalised, written straight into the resident matrix."""
+    rows L2-normalised, written straight into the resident matrix.  ``clustered``: the §8d
+    variant — row r = normalise(centre[r % 1024] + noise) with |noise| ~ 0.75 |centre| (cosine
+    ~0.8 inside a cluster), so the top-k of a query near a stored row is a dense neighbourhood
+    instead of the tail of a noise distribution."""
     gen = torch.Generator(device=device)
     gen.manual_seed(seed)
     rows = torch.empty((n_rows, DIM), dtype=torch.float32, device=device)
+    centres = None
+    if clustered:
+        cgen = torch.Generator(device=device)
+        cgen.manual_seed(4242)                      # the same centres on every rank
+        centres = torch.randn((N_CLUSTERS, DIM), generator=cgen, device=device)
+        centres /= centres.norm(dim=1, keepdim=True)
     chunk = 500_000
     for lo in range(0, n_rows, chunk):
         hi = min(lo + chunk, n_rows)
         view = rows[lo:hi]
         view.normal_(generator=gen)
+        if clustered:
+            view.mul_(0.75 / DIM ** 0.5)
+            view.add_(centres[torch.arange(lo, hi, device=device) % N_CLUSTERS])
         view.div_(view.norm(dim=1, keepdim=True))
     return rows
+
+
+def make_queries(rows_t, n_q, seed, clustered):
+    """Host float32 unit queries: seeded noise, or (clustered) stored rows + 10 % noise."""
+    rng = np.random.default_rng(seed)
+    q = rng.standard_normal((n_q, DIM), dtype=np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    if clustered:
+        picks = rng.choice(rows_t.shape[0], n_q, replace=False)
+        base = rows_t[picks.tolist()].cpu().numpy()
+        q = base + 0.1 * q
+        q /= np.linalg.norm(q, axis=1, keepdims=True)
+    return np.ascontiguousarray(q, dtype=np.float32)
 
 
 def run_batch_workload(args, torch, idx, rows, rows_per_gpu, device, rank, local_rank):
@@ -276,10 +307,8 @@ def run_batch_workload(args, torch, idx, rows, rows_per_gpu, device, rank, local
     idx.set_option("batch_sample_stride", args.sample_stride)
     idx.set_option("batch_refine", 0 if args.no_refine else 1)
     idx.set_option("batch_min_nq", 1)          # --batch 1: one query through the bf16 pre-selection
-    rng = np.random.default_rng(99)
     n_sets = 4
-    host_q = rng.standard_normal((n_sets, B, DIM), dtype=np.float32)
-    host_q /= np.linalg.norm(host_q, axis=2, keepdims=True)
+    host_q = make_queries(rows, n_sets * B, 99, args.data == "clustered").reshape(n_sets, B, DIM)
     d_q = torch.from_numpy(host_q).to(device)
     o_ids = torch.empty((B, k), dtype=torch.int64, device=device)
     o_dist = torch.empty((B, k), dtype=torch.float32, device=device)
@@ -372,7 +401,8 @@ def run_batch_workload(args, torch, idx, rows, rows_per_gpu, device, rank, local
     line = {
         "metric": "knn_batched_queries_per_s", "value": B * 1e3 / ms_step, "unit": "queries/s", "n_gpus": 1,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16 pre-select + f32 re-rank", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16 pre-select + f32 re-rank",
+        "data": "synthetic" if args.data == "uniform" else "synthetic, clustered (1024 clusters, queries near stored rows)",
         "config": {"workload": "batched cosine KNN, B=%d queries per step, k=%d, %d x 1152 rows "
                                "(BASELINE configs[2]): tcgen05 contraction + fp32 re-rank" % (B, k, rows_per_gpu),
                    "rows_per_gpu": rows_per_gpu, "batch": B, "k": k, "dim": DIM,
@@ -642,7 +672,7 @@ def main():
     if args.workload == "binary":
         return run_binary_workload(args, torch, device, local_rank)
     rows_per_gpu = args.rows or (10_000_000 if world == 1 else 12_500_000)
-    rows = generate_rows(torch, device, rows_per_gpu, 1234 + rank)
+    rows = generate_rows(torch, device, rows_per_gpu, 1234 + rank, clustered=args.data == "clustered")
     idx = GpuIndex(local_rank)
     idx.attach(rows, rowid_base=1 + rank * rows_per_gpu)
     idx.set_option("scan_variant", args.variant)
@@ -657,8 +687,7 @@ def main():
         return run_batch_workload(args, torch, idx, rows, rows_per_gpu, device, rank, local_rank)
 
     n_q = 64
-    host_q = np.random.default_rng(99).standard_normal((n_q, DIM), dtype=np.float32)
-    host_q /= np.linalg.norm(host_q, axis=1, keepdims=True)
+    host_q = make_queries(rows, n_q, 99, args.data == "clustered")
     if args.workload == "blend":
         host_q2 = np.random.default_rng(100).standard_normal((n_q, DIM), dtype=np.float32)
         host_q2 /= np.linalg.norm(host_q2, axis=1, keepdims=True)
@@ -784,7 +813,8 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic" if args.data == "uniform" else "synthetic, clustered (1024 clusters, queries near stored rows)",
             "config": workload_config(args, rows_per_gpu, world),
             "queries_per_s": 1e3 / ms_per_step,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": ROW_BYTES * (3 if args.workload == "blend" else 1),

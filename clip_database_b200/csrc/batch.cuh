@@ -228,6 +228,17 @@ __global__ void __launch_bounds__(128) prep_queries_kernel(const float *__restri
 
 // ---- the contraction ---------------------------------------------------------------------------
 
+// Pass A visits one tile out of every `stride`.  A plain multiple of the stride would alias with
+// any periodic layout of the data (a power-of-two stride only ever sees rows r with r mod 1024 < 128:
+// whole clusters of a round-robin-clustered store were invisible to the sample and their queries got
+// noise-level thresholds), so the tile inside each window of `stride` is picked by a hash of the
+// window index.  Windows past the end of the store sample nothing (their rows fail the range test).
+__device__ __forceinline__ int sampled_tile(int t, int stride) {
+    if (stride <= 1) return t;
+    const uint32_t h = (static_cast<uint32_t>(t) * 0x9E3779B1u) >> 8;
+    return t * stride + static_cast<int>(h % static_cast<uint32_t>(stride));
+}
+
 struct BatchGemmArgs {
     const float *thr;           // [256] FILTER: keep iff u >= thr[q]
     float *scores;              // DUMP: [sample_groups][256] group maxima of u
@@ -361,7 +372,7 @@ __global__ void __launch_bounds__(BQ_THREADS, 1) batch_gemm_kernel(const __grid_
             int s = 0;
             uint32_t phase = 0;
             for (int t = first; t < eff_tiles; t += step) {
-                const int tile128 = t * a.tile_stride;
+                const int tile128 = sampled_tile(t, a.tile_stride);
                 for (int kb = 0; kb < BQ_K_BLOCKS; kb++) {
                     mbar_wait(&empty_bar[s], phase ^ 1u);
                     mbar_arrive_expect_tx(&full_bar[s], BQ_STAGE_BYTES);
@@ -417,7 +428,7 @@ __global__ void __launch_bounds__(BQ_THREADS, 1) batch_gemm_kernel(const __grid_
         int it = 0;
         for (int t = first; t < eff_tiles; t += step, it++) {
             const int acc = it & 1;
-            const long long row = static_cast<long long>(t) * a.tile_stride * BQ_M + lane_base + lane;
+            const long long row = static_cast<long long>(sampled_tile(t, a.tile_stride)) * BQ_M + lane_base + lane;
             const bool row_ok = row < a.n && row_admitted(a.mask, row);
             mbar_wait(&tmem_full[acc], static_cast<uint32_t>(it >> 1) & 1u);
             tc_fence_after();
@@ -661,7 +672,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
                     t = tile_ring[slot];
                 }
                 if (t < 0) break;
-                const int tile128 = t * a.tile_stride * 2 + static_cast<int>(rank);
+                const int tile128 = sampled_tile(t, a.tile_stride) * 2 + static_cast<int>(rank);
                 for (int kb = 0; kb < BQ_K_BLOCKS; kb++) {
                     mbar_wait(&empty_bar[s], phase ^ 1u);
                     if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * BP_STAGE_BYTES);  // both CTAs' bytes
@@ -722,7 +733,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
             const int t = tile_ring[it & (BP_TQ - 1)];
             if (t < 0) break;
             const int acc = it & 1;
-            const long long t128 = static_cast<long long>(t) * a.tile_stride * 2 + rank;   // 128-row tile index
+            const long long t128 = static_cast<long long>(sampled_tile(t, a.tile_stride)) * 2 + rank;   // 128-row tile index
             const long long row = t128 * BQ_M + lane_base + lane;
             const bool row_ok = row < a.n && row_admitted(a.mask, row);
             mbar_wait(&tmem_full[acc], static_cast<uint32_t>(it >> 1) & 1u);
