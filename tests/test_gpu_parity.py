@@ -478,3 +478,47 @@ def test_sharded_search_equals_unsharded(config1):
         assert np.array_equal(o_d.cpu().numpy(), full.distances[qi])
     for s in shards:
         s.close()
+
+
+def test_adversarial_row_order_every_row_is_admitted(gpu):
+    """Rows stored in order of DECREASING distance to the query: every row beats the current
+    k-th candidate of its warp (the admission path runs for every row instead of ~k/n of them).
+    Still exact, for both scan kernels and the sign-code scan."""
+    rows = synth.unit_rows(60_000, DIM, 606)
+    q = synth.unit_rows(1, DIM, 607)[0]
+    order = np.argsort(-ref.distances(rows, q), kind="stable")       # farthest first
+    rows = np.ascontiguousarray(rows[order[::1]])
+    with gpu(0) as idx:
+        idx.load(rows)
+        for variant in (1, 2):
+            idx.set_option("scan_variant", variant)
+            for k in (20, 128):
+                check_query(idx, rows, q, k, rowid_offset=0)
+        got = idx.search(q, 5)
+        assert got.rowids[0].tolist() == [59_999, 59_998, 59_997, 59_996, 59_995]
+
+
+def test_one_context_from_many_threads(config1):
+    """Calls on one context are serialised by the library: concurrent host threads get the
+    same answers as sequential calls."""
+    import threading
+    rows, queries, idx = config1
+    want = [idx.search(queries[i], 20) for i in range(8)]
+    got = [None] * 8
+    errs = []
+
+    def work(i):
+        try:
+            for _ in range(5):
+                got[i] = idx.search(queries[i], 20)
+        except Exception as e:      # noqa: BLE001
+            errs.append(e)
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    for i in range(8):
+        assert np.array_equal(got[i].rowids, want[i].rowids)
+        assert np.array_equal(got[i].distances.view(np.uint32), want[i].distances.view(np.uint32))
