@@ -483,7 +483,7 @@ def test_sharded_search_equals_unsharded(config1):
 def test_adversarial_row_order_every_row_is_admitted(gpu):
     """Rows stored in order of DECREASING distance to the query: every row beats the current
     k-th candidate of its warp (the admission path runs for every row instead of ~k/n of them).
-    Still exact, for both scan kernels and the sign-code scan."""
+    Still exact, for both scan kernels."""
     rows = synth.unit_rows(60_000, DIM, 606)
     q = synth.unit_rows(1, DIM, 607)[0]
     order = np.argsort(-ref.distances(rows, q), kind="stable")       # farthest first
