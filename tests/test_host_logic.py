@@ -122,3 +122,25 @@ def test_unit_rows_are_unit_and_seeded():
     assert np.allclose(np.linalg.norm(a, axis=1), 1.0, atol=1e-6)
     h = synth.fp16_normalised(a)
     assert np.all(np.abs(np.linalg.norm(h, axis=1) - 1.0) < 1e-3)
+
+
+def test_read_codes_order_and_validation(tmp_path):
+    """The sign-code loader runs the fallback's own statement: rows in binary_embeddings rowid
+    order, INNER JOINed to images; a blob of the wrong width is refused."""
+    import sqlite3
+    from clip_database_b200 import loader
+    rows = synth.unit_rows(50, 1152, 9)
+    db = str(tmp_path / "codes.db")
+    synth.write_reference_db(db, rows, vectors=False)
+    host = loader.read_codes(db, expect_dim=1152)
+    assert host.codes.shape == (50, 1152) and host.image_ids.tolist() == list(range(1, 51))
+    assert np.array_equal(host.codes, (rows >= 0).astype(np.uint8))
+    conn = sqlite3.connect(db)
+    conn.execute("DELETE FROM images WHERE id = 7")              # orphaned code: dropped by the join
+    conn.commit()
+    assert loader.read_codes(db).image_ids.tolist() == [i for i in range(1, 51) if i != 7]
+    conn.execute("UPDATE binary_embeddings SET embedding = ? WHERE image_id = 9", (b"\x01" * 100,))
+    conn.commit()
+    conn.close()
+    with pytest.raises(ValueError):
+        loader.read_codes(db, expect_dim=1152)
