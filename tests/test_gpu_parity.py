@@ -522,3 +522,30 @@ def test_one_context_from_many_threads(config1):
     for i in range(8):
         assert np.array_equal(got[i].rowids, want[i].rowids)
         assert np.array_equal(got[i].distances.view(np.uint32), want[i].distances.view(np.uint32))
+
+
+def test_clustered_store_and_queries_near_stored_rows(gpu):
+    """SURVEY §8d's clustered variant at config-1 scale: 64 clusters (cosine ~0.64 between mates),
+    queries = stored row + 10 % noise, so the top-k is a dense neighbourhood rather than the tail of
+    a noise distribution.  Oracle parity for the scan, bit equality for the batched path."""
+    rng = np.random.default_rng(2024)
+    n, clusters = 100_000, 64
+    centres = synth.unit_rows(clusters, DIM, 5150)
+    rows = centres[np.arange(n) % clusters] + 0.75 * rng.standard_normal((n, DIM), dtype=np.float32) / np.sqrt(DIM)
+    rows = (rows / np.linalg.norm(rows, axis=1, keepdims=True)).astype(np.float32)
+    picks = rng.choice(n, 12, replace=False)
+    queries = rows[picks] + 0.1 * synth.unit_rows(12, DIM, 77)
+    queries = (queries / np.linalg.norm(queries, axis=1, keepdims=True)).astype(np.float32)
+    with gpu(0) as idx:
+        idx.load(rows)
+        for q in queries[:6]:
+            for k in (20, 100):
+                check_query(idx, rows, q, k, rowid_offset=0)
+        exact = idx.search(queries, 100)
+        assert np.array_equal(exact.rowids[:, 0], picks)             # the perturbed row itself comes first
+        idx.enable_batch()
+        got = idx.search(queries, 100)
+        assert np.array_equal(got.rowids, exact.rowids)
+        assert np.array_equal(got.distances.view(np.uint32), exact.distances.view(np.uint32))
+        cand, surv = idx.batch_stats()
+        assert cand[:12].max() < idx.get_option("batch_cand_cap")
