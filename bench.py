@@ -611,11 +611,19 @@ def run_sharded_batch_workload(args, torch, dist, idx, sharded, rows_per_gpu, de
                     "d2h_bytes_per_step": B * (k * 12 + 4) + 4 * B * world, "ms_per_step": e2e_ms,
                     "api": "ShardedIndex.search_batch"},
             "gpu_launches": int(launches), "flagged_queries_last_step": flagged,
-            "roofline": {"bound": "tensor", "kernel": "batch_gemm_pair_kernel<FILTER>",
-                         "achieved": flops / 1e12 / (gemm_avg / 1e3), "peak": peak, "unit": "TFLOP/s",
-                         "frac": flops / 1e12 / (gemm_avg / 1e3) / peak,
-                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained", "flops_per_launch": flops,
-                         "avg_launch_ms": gemm_avg, "launches_timed": int(gemm_n), "traffic": None},
+            "roofline": ({"bound": "tensor", "kernel": "batch_gemm_pair_kernel<FILTER, 256>",
+                          "achieved": flops / 1e12 / (gemm_avg / 1e3), "peak": peak, "unit": "TFLOP/s",
+                          "frac": flops / 1e12 / (gemm_avg / 1e3) / peak,
+                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained", "flops_per_launch": flops,
+                          "avg_launch_ms": gemm_avg, "launches_timed": int(gemm_n), "traffic": None}
+                         if B > 128 else
+                         {"bound": "hbm", "kernel": "batch_gemm_pair_kernel<FILTER, %d>" % (64 if B <= 64 else 128),
+                          "achieved": rows_per_gpu * DIM * 2 / 1e9 / (gemm_avg / 1e3),
+                          "peak": float(peaks.get("hbm_gbs", 6650.0)), "unit": "GB/s",
+                          "frac": rows_per_gpu * DIM * 2 / 1e9 / (gemm_avg / 1e3) / float(peaks.get("hbm_gbs", 6650.0)),
+                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)",
+                          "algorithmic_bytes_per_launch": rows_per_gpu * DIM * 2, "avg_launch_ms": gemm_avg,
+                          "launches_timed": int(gemm_n), "traffic": None}),
             "clocks": sampler.summary() if sampler else None,
         })
     idx.close()
