@@ -160,7 +160,7 @@ __device__ __forceinline__ void exchange_merge_decode(uint64_t *scratch, const D
     }
     if (tid < G) {
         ExchangeSlot *slot = xa.inbox[tid] + bank * G + xa.rank;
-        slot->count = mine;
+        slot->count = mine | (k << 16);   // the requested k rides along: every rank must ask the same question
         slot->nan = s_nan;
     }
     // 2. publish
@@ -188,13 +188,22 @@ __device__ __forceinline__ void exchange_merge_decode(uint64_t *scratch, const D
         }
         return;
     }
+    // a peer that answered a different request (another k) would make the merge meaningless
+    if (__syncthreads_count(tid < G && (__ldcg(&own[tid < G ? tid : 0].count) >> 16) != k)) {
+        if (tid == 0) {
+            *dec.out_n = -2;
+            sync->tile_counter = 0;
+            sync->done_counter = 0;
+        }
+        return;
+    }
     // 4. merge: key = (distance, shard, position in the shard's list) = (distance, rowid)
     const int total = G * k, padded = next_pow2(total);
     for (int i = tid; i < padded; i += nthreads) {
         uint64_t key = KEY_EMPTY;
         if (i < total) {
             const int l = i / k, p = i - l * k;
-            if (p < __ldcg(&own[l].count)) key = make_key(__ldcg(&own[l].dist[p]), static_cast<uint32_t>(i));
+            if (p < (__ldcg(&own[l].count) & 0xFFFF)) key = make_key(__ldcg(&own[l].dist[p]), static_cast<uint32_t>(i));
         }
         scratch[i] = key;
     }

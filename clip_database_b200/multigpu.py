@@ -146,7 +146,8 @@ class MultiGpuIndex:
         h = self._h_out.numpy()
         m = int(h[lay.off_count:lay.off_count + 4].view(np.int32)[0])
         if m < 0:
-            raise RuntimeError("multi-GPU search: a shard did not deliver its candidates in time")
+            raise RuntimeError("multi-GPU search: a shard did not deliver its candidates in time"
+                               if m == -1 else "multi-GPU search: the shards were asked different questions")
         ids = h[lay.off_rowids:lay.off_rowids + 8 * m].view(np.int64).copy()
         dist = h[lay.off_dist:lay.off_dist + 4 * m].view(np.float32).copy()
         nan = int(h[lay.off_nan:lay.off_nan + 8].view(np.int64)[0])

@@ -194,6 +194,8 @@ class CudaShardBackend:
         self.torch.cuda.current_stream(self.device).synchronize()
         h = self._h_out.numpy()
         m = int(h[lay.off_count:lay.off_count + 4].view(np.int32)[0])
+        if m == -2:
+            raise RuntimeError("sharded search: the ranks asked different questions (k differs between ranks)")
         if m < 0:
             raise RuntimeError("sharded search: a peer GPU did not deliver its candidates in time "
                                "(option xchg_timeout_ms); every rank must issue the same searches")

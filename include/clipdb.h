@@ -276,7 +276,8 @@ int clipdb_merge_batch_device(clipdb_ctx *ctx, const void *d_dist, int64_t dist_
  *   clipdb_search_sharded_device      device pointers, async; EVERY rank must issue the same
  *                             sequence of calls.  Needs dim 1152, 1 <= k <= 128, a non-empty shard.
  *                             If a peer does not deliver within option "xchg_timeout_ms"
- *                             (default 10 s) *d_out_n is set to -1 instead of hanging the GPU. */
+ *                             (default 10 s) *d_out_n is set to -1 instead of hanging the GPU; -2 if
+ *                             the ranks passed different k. */
 #define CLIPDB_IPC_HANDLE_BYTES 64
 int clipdb_exchange_init(clipdb_ctx *ctx, int32_t world, int32_t rank, void *out_ipc_handle, void **out_inbox);
 int clipdb_exchange_connect(clipdb_ctx *ctx, const void *ipc_handles);

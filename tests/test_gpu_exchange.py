@@ -140,3 +140,29 @@ def test_single_process_multi_gpu_index(k):
         ids, dist, nan = multi.search(queries[3], k, use_mask=True)
         assert np.array_equal(ids, want_masked.rowids[3])
         assert np.array_equal(dist.view(np.uint32), want_masked.distances[3].view(np.uint32))
+
+
+def test_ranks_asking_different_k_are_detected():
+    assert have_gpu()
+    import torch
+    from clip_database_b200 import GpuIndex
+    rows = synth.unit_rows(5000, DIM, 1)
+    with GpuIndex(0) as a, GpuIndex(0) as b:
+        a.load(rows[:2500])
+        b.load(rows[2500:])
+        for s in (a, b):
+            s.set_option("scan_ctas", 32)
+            s.set_option("xchg_timeout_ms", 20000)
+        _, pa = a.exchange_init(2, 0)
+        _, pb = b.exchange_init(2, 1)
+        a.exchange_connect_pointers([pa, pb], [0, 0])
+        b.exchange_connect_pointers([pa, pb], [0, 0])
+        q = torch.from_numpy(synth.unit_rows(1, DIM, 2)).cuda()
+        outs = [(torch.empty(9, dtype=torch.int64, device="cuda"), torch.empty(9, dtype=torch.float32, device="cuda"),
+                 torch.zeros(1, dtype=torch.int32, device="cuda")) for _ in range(2)]
+        torch.cuda.synchronize()
+        a.search_sharded_device(q[0], 5, *outs[0])
+        b.search_sharded_device(q[0], 9, *outs[1])
+        a.synchronize()
+        b.synchronize()
+        assert int(outs[0][2][0]) == -2 and int(outs[1][2][0]) == -2
