@@ -606,7 +606,8 @@ def run_sharded_batch_workload(args, torch, dist, idx, sharded, rows_per_gpu, de
                                    "x %d GPUs (BASELINE configs[4] store, configs[2] queries)" % (B, k, rows_per_gpu, world),
                        "rows_per_gpu": rows_per_gpu, "rows_total": rows_per_gpu * world, "batch": B, "k": k, "dim": DIM,
                        "l2": "inputs_larger_than_L2", "parallelism": "row-shard x%d" % world,
-                       "exchange": "one NCCL all-gather of B*k candidates per rank + merge kernel"},
+                       "exchange": ("peer-memory exchange in the batched path's last kernel" if sharded.fused else
+                                    "one NCCL all-gather of B*k candidates per rank + merge kernel")},
             "e2e": {"value": B * 1e3 / e2e_ms, "unit": "queries/s", "h2d_bytes_per_step": B * ROW_BYTES,
                     "d2h_bytes_per_step": B * (k * 12 + 4) + 4 * B * world, "ms_per_step": e2e_ms,
                     "api": "ShardedIndex.search_batch"},

@@ -74,6 +74,8 @@ SIGNATURES = [
     ("clipdb_exchange_connect_pointers", c_int, [_CTX, c_void_p, c_void_p]),
     ("clipdb_search_sharded_device", c_int, [_CTX, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                              c_void_p]),
+    ("clipdb_search_batch_sharded_device", c_int, [_CTX, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                                   c_void_p, c_void_p, c_void_p]),
     ("clipdb_merge_device", c_int, [_CTX, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                     c_void_p, c_void_p, c_void_p]),
     ("clipdb_merge_strided_device", c_int, [_CTX, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,

@@ -994,6 +994,8 @@ struct RerankArgs {
     int *flags;                   // |= BQ_FLAG_OVERFLOW
     DecodeArgs dec;               // out arrays are [nq][k]; out_n/out_nan [nq]
     const unsigned long long *bad_rows;  // rows of the store with NaN distance for any query
+    ExchangeArgs xchg;            // world > 1: the finish kernel also exchanges each query's list with the
+                                  // other shards' GPUs and merges (merge.cuh); flags then hold the OR over shards
 };
 
 template <int KPL>
@@ -1060,9 +1062,11 @@ __global__ void __launch_bounds__(BQ_SEL_THREADS) batch_rerank_kernel(const Rera
                          lane);
 }
 
-// level 2 for the re-rank: merge the parts, decode the k best
+// level 2 for the re-rank: merge the parts, decode the k best (or, sharded: exchange this shard's k best
+// for the query with the peer GPUs over NVLink and decode the merged list)
+constexpr int BQ_FINISH_KEYS = 2048;   // >= parts * 128 and >= next_pow2(world * k)
 __global__ void __launch_bounds__(256) batch_rerank_finish_kernel(const RerankArgs a, int parts, int stride) {
-    __shared__ uint64_t s[BQ_RERANK_PARTS * 128];
+    __shared__ uint64_t s[BQ_FINISH_KEYS];
     const int q = blockIdx.x, tid = threadIdx.x;
     const int total = parts * stride, padded = next_pow2(total);
     for (int i = tid; i < padded; i += 256)
@@ -1071,6 +1075,19 @@ __global__ void __launch_bounds__(256) batch_rerank_finish_kernel(const RerankAr
     DecodeArgs d = a.dec;
     d.out_rowids += static_cast<size_t>(q) * a.k;
     d.out_dist += static_cast<size_t>(q) * a.k;
+    d.out_n += q;
+    if (d.out_nan) d.out_nan += q;
+    const bool overflow = a.cand_count[q] > static_cast<unsigned>(a.cand_cap);
+    if (a.xchg.world > 1) {
+        const int G = a.xchg.world, bank = static_cast<int>(a.xchg.epoch & 1u);
+        const int local_flags = a.flags[q] | (overflow ? BQ_FLAG_OVERFLOW : 0);
+        for (int i = padded + tid; i < BQ_FINISH_KEYS; i += 256) s[i] = KEY_EMPTY;
+        __syncthreads();
+        exchange_merge_decode<BQ_RERANK_PARTS * 128>(s, d, a.xchg, 2 * G + bank * G * XCHG_BATCH + q, XCHG_BATCH,
+                                                      static_cast<long long>(*a.bad_rows), local_flags, a.flags + q, tid,
+                                                      256);
+        return;
+    }
     int found = 0;
     for (int base = 0; base < a.k; base += 256) {
         const int i = base + tid;
@@ -1079,9 +1096,9 @@ __global__ void __launch_bounds__(256) batch_rerank_finish_kernel(const RerankAr
         found += __syncthreads_count(valid);
     }
     if (tid == 0) {
-        d.out_n[q] = found;
-        if (d.out_nan) d.out_nan[q] = static_cast<int64_t>(*a.bad_rows);
-        if (a.cand_count[q] > static_cast<unsigned>(a.cand_cap)) a.flags[q] |= BQ_FLAG_OVERFLOW;
+        *d.out_n = found;
+        if (d.out_nan) *d.out_nan = static_cast<int64_t>(*a.bad_rows);
+        if (overflow) a.flags[q] |= BQ_FLAG_OVERFLOW;
     }
 }
 

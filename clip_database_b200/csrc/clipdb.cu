@@ -74,7 +74,7 @@ struct clipdb_ctx {
     bool xchg_ipc[XCHG_MAX_WORLD] = {};       // peer pointer came from cudaIpcOpenMemHandle
     int xchg_world = 0, xchg_rank = 0;
     bool xchg_connected = false;
-    uint32_t xchg_epoch = 0;
+    uint32_t xchg_epoch = 0, xchg_batch_epoch = 0;   // single-query and batched passes count separately
     int64_t xchg_timeout_ms = 10000;
 
     // workspaces (grown on demand)
@@ -766,7 +766,8 @@ void launch_pair_gemm(clipdb_ctx *c, int npass, int grid, const BatchGemmArgs &g
 
 template <int KPL>
 int batch_launch_tail(clipdb_ctx *c, const float *d_queries, int32_t nq, int32_t k, int64_t *d_out_rowids,
-                      float *d_out_dist, int32_t *d_out_n, int64_t *d_out_nan, int32_t *d_flags, bool threshold) {
+                      float *d_out_dist, int32_t *d_out_n, int64_t *d_out_nan, int32_t *d_flags, bool threshold,
+                      const ExchangeArgs *bx = nullptr) {
     uint64_t *parts = static_cast<uint64_t *>(c->bq_parts.p);
     if (threshold) {
         batch_threshold_kernel<<<BQ_N / BQ_THR_QPC, BQ_THR_THREADS, 0, c->stream>>>(
@@ -800,6 +801,7 @@ int batch_launch_tail(clipdb_ctx *c, const float *d_queries, int32_t nq, int32_t
         r.dec.out_nan = d_out_nan;
         r.dec.k = k;
         r.bad_rows = static_cast<const unsigned long long *>(c->bad_rows.p);
+        if (bx) r.xchg = *bx;
         batch_rerank_kernel<KPL><<<dim3(nq, BQ_RERANK_PARTS), BQ_SEL_THREADS, 0, c->stream>>>(r);
         CU_TRY(c, cudaGetLastError());
         c->launches++;
@@ -812,7 +814,7 @@ int batch_launch_tail(clipdb_ctx *c, const float *d_queries, int32_t nq, int32_t
 
 int batch_search_device_locked(clipdb_ctx *c, const float *d_queries, int32_t nq, int32_t k, int32_t use_mask,
                                int64_t *d_out_rowids, float *d_out_dist, int32_t *d_out_n, int64_t *d_out_nan,
-                               int32_t *d_flags) {
+                               int32_t *d_flags, const ExchangeArgs *bx = nullptr) {
     if (!d_queries || !d_out_rowids || !d_out_dist || !d_out_n || !d_flags)
         return fail(c, CLIPDB_ERR_INVALID, "search_batch: null pointer");
     if (c->batch_enabled && c->batch_dirty) RC_TRY(batch_build_locked(c));   // rows were appended / updated
@@ -888,9 +890,9 @@ int batch_search_device_locked(clipdb_ctx *c, const float *d_queries, int32_t nq
     RC_TRY(profile_mark(c, false));
     // exact re-rank
     switch (kpl) {
-        case 1: return batch_launch_tail<1>(c, d_queries, nq, k, d_out_rowids, d_out_dist, d_out_n, d_out_nan, d_flags, false);
-        case 2: return batch_launch_tail<2>(c, d_queries, nq, k, d_out_rowids, d_out_dist, d_out_n, d_out_nan, d_flags, false);
-        default: return batch_launch_tail<4>(c, d_queries, nq, k, d_out_rowids, d_out_dist, d_out_n, d_out_nan, d_flags, false);
+        case 1: return batch_launch_tail<1>(c, d_queries, nq, k, d_out_rowids, d_out_dist, d_out_n, d_out_nan, d_flags, false, bx);
+        case 2: return batch_launch_tail<2>(c, d_queries, nq, k, d_out_rowids, d_out_dist, d_out_n, d_out_nan, d_flags, false, bx);
+        default: return batch_launch_tail<4>(c, d_queries, nq, k, d_out_rowids, d_out_dist, d_out_n, d_out_nan, d_flags, false, bx);
     }
 }
 
@@ -1636,12 +1638,13 @@ int clipdb_exchange_init(clipdb_ctx *c, int32_t world, int32_t rank, void *out_i
     DeviceGuard g(c->device);
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     release_exchange(c);
-    const size_t bytes = static_cast<size_t>(2) * world * sizeof(ExchangeSlot);
+    const size_t bytes = exchange_inbox_slots(world) * sizeof(ExchangeSlot);   // single-query + batched slots
     CU_TRY(c, cudaMalloc(reinterpret_cast<void **>(&c->xchg_inbox), bytes));
     CU_TRY(c, cudaMemset(c->xchg_inbox, 0, bytes));
     c->xchg_world = world;
     c->xchg_rank = rank;
     c->xchg_epoch = 0;
+    c->xchg_batch_epoch = 0;
     c->xchg_peer[rank] = c->xchg_inbox;
     c->xchg_connected = world == 1;
     if (out_ipc_handle) {
@@ -1719,6 +1722,31 @@ int clipdb_search_sharded_device(clipdb_ctx *c, const float *d_query, int32_t k,
     if (xa.world == 1) return search_one(c, d_query, k, metric, use_mask != 0, d_out_rowids, d_out_dist, d_out_n, d_out_nan);
     RC_TRY(search_one(c, d_query, k, metric, use_mask != 0, d_out_rowids, d_out_dist, d_out_n, d_out_nan, &xa));
     c->xchg_epoch = epoch;   // only a launch that was enqueued consumes an epoch: the ranks stay in step
+    return CLIPDB_OK;
+}
+
+int clipdb_search_batch_sharded_device(clipdb_ctx *c, const float *d_queries, int32_t nq, int32_t k, int32_t use_mask,
+                                       int64_t *d_out_rowids, float *d_out_dist, int32_t *d_out_n, int64_t *d_out_nan,
+                                       int32_t *d_flags) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->xchg_connected) return fail(c, CLIPDB_ERR_STATE, "sharded batch search: exchange not connected");
+    if (use_mask && !c->mask) return fail(c, CLIPDB_ERR_STATE, "search_batch: use_mask set but no mask installed");
+    DeviceGuard g(c->device);
+    if (c->xchg_world == 1)
+        return batch_search_device_locked(c, d_queries, nq, k, use_mask, d_out_rowids, d_out_dist, d_out_n, d_out_nan, d_flags);
+    ExchangeArgs xa{};
+    for (int r = 0; r < c->xchg_world; r++) xa.inbox[r] = c->xchg_peer[r];
+    xa.world = c->xchg_world;
+    xa.rank = c->xchg_rank;
+    xa.k = k;
+    uint32_t epoch = c->xchg_batch_epoch + 1;
+    if (epoch == 0) epoch = 1;
+    xa.epoch = epoch;
+    xa.timeout_ns = static_cast<unsigned long long>(c->xchg_timeout_ms) * 1000000ull;
+    RC_TRY(batch_search_device_locked(c, d_queries, nq, k, use_mask, d_out_rowids, d_out_dist, d_out_n, d_out_nan,
+                                      d_flags, &xa));
+    c->xchg_batch_epoch = epoch;
     return CLIPDB_OK;
 }
 

@@ -103,22 +103,34 @@ struct ScanSync {
 constexpr int XCHG_MAX_WORLD = 16;
 constexpr int XCHG_K = 128;   // largest k of the fused path
 
+constexpr int XCHG_BATCH = 256;   // queries per batched pass
+
 struct ExchangeSlot {
     uint32_t epoch;
-    int32_t count;
+    int32_t count;      // valid entries | requested k << 16
     long long nan;
+    int32_t flags;      // batched path: this shard could not answer the query (overflow / bad query)
+    int32_t pad;
     float dist[XCHG_K];
     long long rowid[XCHG_K];
 };
 
+// One rank's inbox = [2 banks][world] slots for single queries, followed by
+// [2 banks][world][XCHG_BATCH] slots for batched passes.  Slot of (bank, sender r[, query q]):
+//   single   bank * world + r
+//   batched  2 * world + (bank * world + r) * XCHG_BATCH + q
 struct ExchangeArgs {
-    ExchangeSlot *inbox[XCHG_MAX_WORLD];   // inbox[r] = rank r's inbox [2 banks][world slots], as mapped here
+    ExchangeSlot *inbox[XCHG_MAX_WORLD];   // inbox[r] = rank r's inbox, as mapped here
     int world;                             // 0: no exchange
     int rank;
     int k;                                 // requested (global) k
-    uint32_t epoch;                        // same on every rank for the same query, never 0
+    uint32_t epoch;                        // same on every rank for the same query / batch, never 0
     unsigned long long timeout_ns;
 };
+
+__host__ __device__ inline size_t exchange_inbox_slots(int world) {
+    return static_cast<size_t>(2) * world * (1 + XCHG_BATCH);
+}
 
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -134,24 +146,26 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     return t;
 }
 
-// scratch[0 .. L) holds this shard's merged ascending list (the tournament's result).
+// scratch[0 .. L) holds this shard's merged ascending list for one query.  `slot0` / `slot_stride`
+// address the slots of this query: sender r's slot is slot0 + r * slot_stride in every inbox.
+// `nan_local` / `flags_local`: this shard's NaN-row count and failure flags for the query.
+// On return every thread knows the outcome: >= 0 results written, -1 a peer never delivered,
+// -2 the ranks asked different questions.  `out_flags` (nullable) receives the OR of all shards' flags.
 template <int L>
-__device__ __forceinline__ void exchange_merge_decode(uint64_t *scratch, const DecodeArgs &dec,
-                                                      const ExchangeArgs &xa, ScanSync *sync, int tid, int nthreads) {
-    __shared__ long long s_nan;
-    const int k = xa.k, G = xa.world, bank = static_cast<int>(xa.epoch & 1u);
+__device__ __forceinline__ int exchange_merge_decode(uint64_t *scratch, const DecodeArgs &dec, const ExchangeArgs &xa,
+                                                     int slot0, int slot_stride, long long nan_local,
+                                                     int flags_local, int32_t *out_flags, int tid, int nthreads) {
+    const int k = xa.k, G = xa.world;
     int mine = 0;
     for (int base = 0; base < k; base += nthreads) {
         const int i = base + tid;
         mine += __syncthreads_count(i < k && i < L && scratch[i] != KEY_EMPTY);
     }
-    if (tid == 0) s_nan = static_cast<long long>(atomicExch(&sync->nan_rows, 0ull));
-    __syncthreads();
-    // 1. this shard's record into slot [rank] of every inbox (peer stores go over NVLink)
+    // 1. this shard's record into its slot of every inbox (peer stores go over NVLink)
     for (int w = tid; w < G * k; w += nthreads) {
         const int r = w / k, j = w - r * k;
         if (j < mine) {
-            ExchangeSlot *slot = xa.inbox[r] + bank * G + xa.rank;
+            ExchangeSlot *slot = xa.inbox[r] + slot0 + xa.rank * slot_stride;
             const uint64_t key = scratch[j];
             const uint32_t pos = static_cast<uint32_t>(key & 0xFFFFFFFFull);
             slot->dist[j] = orderable_f32(static_cast<uint32_t>(key >> 32));
@@ -159,20 +173,21 @@ __device__ __forceinline__ void exchange_merge_decode(uint64_t *scratch, const D
         }
     }
     if (tid < G) {
-        ExchangeSlot *slot = xa.inbox[tid] + bank * G + xa.rank;
+        ExchangeSlot *slot = xa.inbox[tid] + slot0 + xa.rank * slot_stride;
         slot->count = mine | (k << 16);   // the requested k rides along: every rank must ask the same question
-        slot->nan = s_nan;
+        slot->nan = nan_local;
+        slot->flags = flags_local;
     }
     // 2. publish
     __threadfence_system();
     __syncthreads();
-    if (tid < G) st_release_sys(&(xa.inbox[tid] + bank * G + xa.rank)->epoch, xa.epoch);
+    if (tid < G) st_release_sys(&(xa.inbox[tid] + slot0 + xa.rank * slot_stride)->epoch, xa.epoch);
     // 3. wait for every shard's record in the own inbox
-    const ExchangeSlot *own = xa.inbox[xa.rank] + bank * G;
+    const ExchangeSlot *own = xa.inbox[xa.rank] + slot0;
     bool late = false;
     if (tid < G) {
         const unsigned long long t0 = global_timer_ns();
-        while (ld_acquire_sys(&own[tid].epoch) != xa.epoch) {
+        while (ld_acquire_sys(&own[tid * slot_stride].epoch) != xa.epoch) {
             if (global_timer_ns() - t0 > xa.timeout_ns) {
                 late = true;
                 break;
@@ -180,22 +195,14 @@ __device__ __forceinline__ void exchange_merge_decode(uint64_t *scratch, const D
             __nanosleep(200);
         }
     }
-    if (__syncthreads_count(late)) {
-        if (tid == 0) {
-            *dec.out_n = -1;   // a peer never delivered: reported by the host as an error
-            sync->tile_counter = 0;
-            sync->done_counter = 0;
-        }
-        return;
+    if (__syncthreads_count(late)) {   // a peer never delivered: reported by the host as an error
+        if (tid == 0) *dec.out_n = -1;
+        return -1;
     }
     // a peer that answered a different request (another k) would make the merge meaningless
-    if (__syncthreads_count(tid < G && (__ldcg(&own[tid < G ? tid : 0].count) >> 16) != k)) {
-        if (tid == 0) {
-            *dec.out_n = -2;
-            sync->tile_counter = 0;
-            sync->done_counter = 0;
-        }
-        return;
+    if (__syncthreads_count(tid < G && (__ldcg(&own[(tid < G ? tid : 0) * slot_stride].count) >> 16) != k)) {
+        if (tid == 0) *dec.out_n = -2;
+        return -2;
     }
     // 4. merge: key = (distance, shard, position in the shard's list) = (distance, rowid)
     const int total = G * k, padded = next_pow2(total);
@@ -203,7 +210,8 @@ __device__ __forceinline__ void exchange_merge_decode(uint64_t *scratch, const D
         uint64_t key = KEY_EMPTY;
         if (i < total) {
             const int l = i / k, p = i - l * k;
-            if (p < (__ldcg(&own[l].count) & 0xFFFF)) key = make_key(__ldcg(&own[l].dist[p]), static_cast<uint32_t>(i));
+            const ExchangeSlot *src = own + l * slot_stride;
+            if (p < (__ldcg(&src->count) & 0xFFFF)) key = make_key(__ldcg(&src->dist[p]), static_cast<uint32_t>(i));
         }
         scratch[i] = key;
     }
@@ -215,21 +223,23 @@ __device__ __forceinline__ void exchange_merge_decode(uint64_t *scratch, const D
         if (valid) {
             const int src = static_cast<int>(scratch[i] & 0xFFFFFFFFull);
             const int l = src / k, p = src - l * k;
-            dec.out_dist[i] = __ldcg(&own[l].dist[p]);
-            dec.out_rowids[i] = __ldcg(&own[l].rowid[p]);
+            dec.out_dist[i] = __ldcg(&own[l * slot_stride].dist[p]);
+            dec.out_rowids[i] = __ldcg(&own[l * slot_stride].rowid[p]);
         }
         found += __syncthreads_count(valid);
     }
     if (tid == 0) {
         *dec.out_n = found;
-        if (dec.out_nan) {
-            long long nan = 0;
-            for (int l = 0; l < G; l++) nan += __ldcg(&own[l].nan);
-            *dec.out_nan = nan;
+        long long nan = 0;
+        int flags = 0;
+        for (int l = 0; l < G; l++) {
+            nan += __ldcg(&own[l * slot_stride].nan);
+            flags |= __ldcg(&own[l * slot_stride].flags);
         }
-        sync->tile_counter = 0;
-        sync->done_counter = 0;
+        if (dec.out_nan) *dec.out_nan = nan;
+        if (out_flags) *out_flags = flags;
     }
+    return found;
 }
 
 // lists: [n_lists][L] in global memory (written by other CTAs: read through L2), scratch: shared
@@ -241,7 +251,15 @@ __device__ __forceinline__ void merge_decode_reset(const uint64_t *lists, int n_
     __syncthreads();
     merge_sorted_lists_tournament<L>(scratch, n_lists, tid, nthreads);
     if (xa.world > 1) {
-        exchange_merge_decode<L>(scratch, dec, xa, sync, tid, nthreads);
+        __shared__ long long s_nan;
+        if (tid == 0) s_nan = static_cast<long long>(atomicExch(&sync->nan_rows, 0ull));
+        __syncthreads();
+        exchange_merge_decode<L>(scratch, dec, xa, static_cast<int>(xa.epoch & 1u) * xa.world, 1, s_nan, 0, nullptr,
+                                 tid, nthreads);
+        if (tid == 0) {
+            sync->tile_counter = 0;
+            sync->done_counter = 0;
+        }
         return;
     }
     int found = 0;

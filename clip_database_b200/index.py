@@ -497,6 +497,18 @@ class GpuIndex:
             ctypes.c_void_p(out_rowids.data_ptr()), ctypes.c_void_p(out_dist.data_ptr()),
             ctypes.c_void_p(out_n.data_ptr()), ctypes.c_void_p(out_nan.data_ptr() if out_nan is not None else 0)))
 
+    def search_batch_sharded_device(self, d_queries, k: int, out_rowids, out_dist, out_n, out_nan, flags,
+                                    use_mask: bool = False) -> None:
+        """Async batched search over ALL shards (<= 256 queries; ``enable_batch`` on every rank): the
+        batched path's last kernel exchanges each query's candidates with the peer GPUs and merges.
+        ``flags[q] != 0``: some shard could not answer query q through the batched path."""
+        nq = d_queries.shape[0]
+        self._check(self._L.clipdb_search_batch_sharded_device(
+            self._ctx, ctypes.c_void_p(d_queries.data_ptr()), nq, int(k), int(bool(use_mask)),
+            ctypes.c_void_p(out_rowids.data_ptr()), ctypes.c_void_p(out_dist.data_ptr()),
+            ctypes.c_void_p(out_n.data_ptr()), ctypes.c_void_p(out_nan.data_ptr() if out_nan is not None else 0),
+            ctypes.c_void_p(flags.data_ptr())))
+
     def merge_device(self, d_dist, d_rowids, d_counts, k: int, out_dist, out_rowids, out_n) -> None:
         """Async shard merge of ``[lists, k]`` gathered results (clipdb_merge_device)."""
         lists = d_dist.shape[0]

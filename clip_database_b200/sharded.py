@@ -137,6 +137,18 @@ class CudaShardBackend:
     def fused_search(self, d_query, k: int, out_dist, out_rowids, out_n, out_nan, use_mask: bool) -> None:
         self.index.search_sharded_device(d_query, k, out_rowids, out_dist, out_n, out_nan, use_mask=use_mask)
 
+    def fused_search_batch(self, d_queries, k: int, out_dist, out_rowids, out_n, out_nan, flags) -> None:
+        """<= 256 queries per pass; outputs are the merged answers over all shards."""
+        nq = d_queries.shape[0]
+        for q0 in range(0, nq, 256):
+            q1 = min(q0 + 256, nq)
+            self.index.search_batch_sharded_device(d_queries[q0:q1], k, out_rowids[q0:q1], out_dist[q0:q1],
+                                                   out_n[q0:q1], out_nan[q0:q1], flags[q0:q1])
+
+    @property
+    def batch_enabled(self) -> bool:
+        return bool(getattr(self.index, "batch_enabled", False))
+
     def merge(self, gathered, k: int, lay: RecordLayout, out_dist, out_rowids, out_n) -> None:
         self.index.merge_records_device(gathered, k, lay.off_rowids, lay.off_dist, lay.off_count,
                                         out_dist, out_rowids, out_n)
@@ -266,6 +278,18 @@ class ShardedIndex:
         merge.  Returns device tensors (dist [nq, k], rowids [nq, k], n [nq], flags [world, nq]);
         ``flags != 0`` marks queries some shard could not answer through the batched path."""
         nq = d_queries.shape[0]
+        if self.fused and self.world > 1 and 1 <= k <= self.FUSED_K_MAX and getattr(self.backend, "batch_enabled", False):
+            # the batched path's last kernel exchanges the candidates over peer memory: no collective call
+            fkey = ("fused", nq, k)
+            if getattr(self, "_bkey", None) != fkey:
+                t = self.backend.torch
+                self._bout = self.backend.new_batch_outputs(nq, k)
+                self._bnan = t.zeros(nq, dtype=t.int64, device=self.backend.device)
+                self._bflags = t.zeros(nq, dtype=t.int32, device=self.backend.device)
+                self._bkey = fkey
+            out_dist, out_rowids, out_n = self._bout
+            self.backend.fused_search_batch(d_queries, k, out_dist, out_rowids, out_n, self._bnan, self._bflags)
+            return out_dist, out_rowids, out_n, self._bflags
         key = (nq, k)
         if getattr(self, "_bkey", None) != key:
             lay = BatchRecordLayout(nq, k)
@@ -300,6 +324,9 @@ class ShardedIndex:
         ids = out_rowids.cpu().numpy().copy()
         dist = out_dist.cpu().numpy().copy()
         counts = out_n.cpu().numpy().copy()
+        if (counts < 0).any():
+            raise RuntimeError("sharded batch search: a peer GPU did not deliver in time, or the ranks asked "
+                               "different questions (every rank must issue the same searches)")
         for q in flagged.tolist():
             r_ids, r_d = self.search(queries[q], k)
             counts[q] = len(r_ids)

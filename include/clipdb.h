@@ -284,6 +284,14 @@ int clipdb_exchange_connect(clipdb_ctx *ctx, const void *ipc_handles);
 int clipdb_exchange_connect_pointers(clipdb_ctx *ctx, void *const *inboxes, const int32_t *devices);
 int clipdb_search_sharded_device(clipdb_ctx *ctx, const float *d_query, int32_t k, int32_t metric, int32_t use_mask,
                                  int64_t *d_out_rowids, float *d_out_dist, int32_t *d_out_n, int64_t *d_out_nan);
+/* Batched form (clipdb_enable_batch on every rank, nq <= 256 per call, every rank the same nq and k):
+ * the last kernel of the batched path exchanges each query's k candidates with the peer GPUs the
+ * same way, so the outputs hold the answers over ALL shards.  d_flags[q] != 0: SOME shard could
+ * not answer query q through the batched path; re-run it with clipdb_search_sharded_device (on
+ * every rank: all ranks see the same flags).  d_out_n[q] = -1 / -2 as above. */
+int clipdb_search_batch_sharded_device(clipdb_ctx *ctx, const float *d_queries, int32_t nq, int32_t k, int32_t use_mask,
+                                       int64_t *d_out_rowids, float *d_out_dist, int32_t *d_out_n,
+                                       int64_t *d_out_nan, int32_t *d_flags);
 
 /* ---- measurement ------------------------------------------------------------
  * With profiling enabled every scan kernel (the dominant, HBM-bound launch) is

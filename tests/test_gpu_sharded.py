@@ -55,10 +55,18 @@ lo2, hi2 = shard_bounds(n2, world)[rank]
 idx2 = GpuIndex(rank)
 idx2.load(rows2[lo2:hi2], np.arange(lo2 + 1, hi2 + 1))
 idx2.enable_batch()
-sh2 = ShardedIndex(CudaShardBackend(idx2))
+sh2 = ShardedIndex(CudaShardBackend(idx2), fused=True)     # candidates exchanged by the batched path's last kernel
+sh2_nccl = ShardedIndex(CudaShardBackend(idx2), fused=False)  # one NCCL all-gather + merge kernel
 bq = synth.unit_rows(40, 1152, 5)
 bq[7] = 0                                       # flagged by every shard -> re-run through the exact sharded search
 b_ids, b_d, b_n = sh2.search_batch(bq, 50)
+n_ids, n_d, n_n = sh2_nccl.search_batch(bq, 50)
+assert np.array_equal(b_ids, n_ids) and np.array_equal(b_n, n_n)
+assert np.array_equal(b_d.view(np.uint32), n_d.view(np.uint32))
+big = synth.unit_rows(300, 1152, 6)             # two passes (256 + 44)
+g_ids, g_d, g_n = sh2.search_batch(big, 20)
+h_ids, h_d, h_n = sh2_nccl.search_batch(big, 20)
+assert np.array_equal(g_ids, h_ids) and np.array_equal(g_d.view(np.uint32), h_d.view(np.uint32))
 np.savez(os.path.join({out!r}, f"batch{{rank}}.npz"), ids=b_ids, d=b_d, n=b_n)
 idx2.close()
 json.dump(out, open(os.path.join({out!r}, f"rank{{rank}}.json"), "w"))
