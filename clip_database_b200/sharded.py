@@ -278,8 +278,9 @@ class ShardedIndex:
         merge.  Returns device tensors (dist [nq, k], rowids [nq, k], n [nq], flags [world, nq]);
         ``flags != 0`` marks queries some shard could not answer through the batched path."""
         nq = d_queries.shape[0]
-        if self.fused and self.world > 1 and 1 <= k <= self.FUSED_K_MAX and getattr(self.backend, "batch_enabled", False):
-            # the batched path's last kernel exchanges the candidates over peer memory: no collective call
+        if self.fused and self.world > 1 and 1 <= k <= self.FUSED_K_MAX:
+            # no collective call: the candidates are exchanged over peer memory by the batched path's
+            # last kernel, or (no bf16 store) by each query's scan kernel
             fkey = ("fused", nq, k)
             if getattr(self, "_bkey", None) != fkey:
                 t = self.backend.torch
@@ -288,7 +289,13 @@ class ShardedIndex:
                 self._bflags = t.zeros(nq, dtype=t.int32, device=self.backend.device)
                 self._bkey = fkey
             out_dist, out_rowids, out_n = self._bout
-            self.backend.fused_search_batch(d_queries, k, out_dist, out_rowids, out_n, self._bnan, self._bflags)
+            if getattr(self.backend, "batch_enabled", False):
+                self.backend.fused_search_batch(d_queries, k, out_dist, out_rowids, out_n, self._bnan, self._bflags)
+            else:
+                self._bflags.zero_()
+                for q in range(nq):
+                    self.backend.fused_search(d_queries[q], k, out_dist[q], out_rowids[q], out_n[q:q + 1],
+                                              self._bnan[q:q + 1], False)
             return out_dist, out_rowids, out_n, self._bflags
         key = (nq, k)
         if getattr(self, "_bkey", None) != key:

@@ -46,6 +46,8 @@ for q in queries:
     assert np.array_equal(ids, ids2) and np.array_equal(d.view(np.uint32), d2.view(np.uint32))
     assert nan == sh_nccl.nan_rows()
     out.append((ids.tolist(), d.tolist(), nan))
+m_ids, m_d, m_n = sh.search_batch(queries, k)          # no bf16 store on this index: one fused scan per query
+assert np.array_equal(m_ids[0], out[0][0]) and np.array_equal(m_ids[3], out[3][0]) and m_n.tolist() == [k] * 4
 ids100, d100 = sh.search(queries[0], 100)
 ids100n, d100n = sh_nccl.search(queries[0], 100)
 assert np.array_equal(ids100, ids100n) and np.array_equal(d100.view(np.uint32), d100n.view(np.uint32))
