@@ -120,8 +120,6 @@ class ImageDatabase:
         self.nan_policy = nan_policy
         self.verbose = verbose
         if devices is not None and len(devices) > 1:
-            if batch_store:
-                raise ValueError("batch_store is a single-GPU option")
             from .multigpu import MultiGpuIndex
             self.index = MultiGpuIndex(devices)
         else:
@@ -157,7 +155,8 @@ class ImageDatabase:
             self.index.load(host.rows, host.rowids)
             if self.batch_store and self.index.dim == schema.EMBEDDING_DIM:
                 self.index.enable_batch()
-                self.index.set_option("batch_min_nq", 1)
+                if not hasattr(self.index, "shards"):
+                    self.index.set_option("batch_min_nq", 1)
         self._log(f"loaded {host.rows.shape[0]} rows ({host.source}); {host.dropped} vec0 rows without "
                   f"a mapping were skipped")
 
@@ -267,7 +266,11 @@ class ImageDatabase:
             k = self.index.num_rows
         use_mask = self._install_mask(filter_folders)
         multi = hasattr(self.index, "shards")
-        res = None if multi else self.index.search(q, k, use_mask=use_mask)
+        if multi and getattr(self.index, "batch_enabled", False) and not use_mask and 1 <= k <= 128:
+            res = self.index.search_batch(q, k)          # one batched pass per 256 queries on every GPU
+            multi = False
+        else:
+            res = None if multi else self.index.search(q, k, use_mask=use_mask)
         out: List[Result] = []
         for i in range(q.shape[0]):
             if multi:

@@ -153,6 +153,57 @@ class MultiGpuIndex:
         nan = int(h[lay.off_nan:lay.off_nan + 8].view(np.int64)[0])
         return ids, dist, nan
 
+    # ---- batched (bf16 pre-selection on every shard, candidates exchanged by the last kernel) ---
+    def enable_batch(self) -> None:
+        """bf16 copy on every shard.  The shards must be on DIFFERENT GPUs: the batched path's last
+        kernel waits for the other shards while their contractions need whole SMs."""
+        if len(set(self.devices)) != len(self.devices):
+            raise ValueError("the batched multi-GPU path needs one GPU per shard")
+        for idx in self.shards:
+            idx.enable_batch()
+        self.batch_enabled = True
+
+    def search_batch(self, queries: np.ndarray, k: int) -> SearchResult:
+        """nq queries over all shards: one batched pass per 256 queries on every GPU; queries some
+        shard could not answer through the batched path are re-run through ``search``."""
+        t = self.torch
+        if not getattr(self, "batch_enabled", False):
+            raise RuntimeError("call enable_batch() first")
+        if not 1 <= k <= self.FUSED_K_MAX:
+            raise ValueError(f"k must be 1..{self.FUSED_K_MAX} on the multi-GPU path")
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        nq = q.shape[0]
+        h_q = t.from_numpy(q).pin_memory()
+        outs = []
+        for r, (d, idx) in enumerate(zip(self.devices, self.shards)):
+            with t.cuda.device(d), t.cuda.stream(self._streams[r]):
+                dev = t.device("cuda", d)
+                dq = h_q.to(dev, non_blocking=True)
+                o = (t.empty((nq, k), dtype=t.int64, device=dev), t.empty((nq, k), dtype=t.float32, device=dev),
+                     t.zeros(nq, dtype=t.int32, device=dev), t.zeros(nq, dtype=t.int64, device=dev),
+                     t.zeros(nq, dtype=t.int32, device=dev))
+                for q0 in range(0, nq, 256):
+                    q1 = min(q0 + 256, nq)
+                    idx.search_batch_sharded_device(dq[q0:q1], k, o[0][q0:q1], o[1][q0:q1], o[2][q0:q1], o[3][q0:q1],
+                                                    o[4][q0:q1])
+                outs.append((dq, o))
+        for s in self._streams:
+            s.synchronize()
+        ids, dist, n, nan, flags = (x.cpu().numpy() for x in outs[0][1])
+        if (n < 0).any():
+            raise RuntimeError("multi-GPU batch search: a shard did not deliver in time")
+        res = SearchResult(ids.copy(), dist.copy(), n.copy(), nan.copy())
+        for qi in np.flatnonzero(flags).tolist():
+            r_ids, r_d, r_nan = self.search(q[qi], k)
+            res.counts[qi] = len(r_ids)
+            res.rowids[qi, :len(r_ids)] = r_ids
+            res.distances[qi, :len(r_d)] = r_d
+            res.nan_rows[qi] = r_nan
+        unused = np.arange(k)[None, :] >= res.counts[:, None]
+        res.rowids[unused] = -1
+        res.distances[unused] = np.nan
+        return res
+
     def search_any_k(self, query: np.ndarray, k: int, use_mask: bool = False) -> Tuple[np.ndarray, np.ndarray, int]:
         """Any k: the fused path for 1 <= k <= 128, else per-shard searches merged on the host with
         the same (distance, rowid) order (shards are contiguous rowid ranges)."""

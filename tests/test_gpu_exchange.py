@@ -166,3 +166,32 @@ def test_ranks_asking_different_k_are_detected():
         a.synchronize()
         b.synchronize()
         assert int(outs[0][2][0]) == -2 and int(outs[1][2][0]) == -2
+
+
+def test_single_process_multi_gpu_batch():
+    """MultiGpuIndex.search_batch: bf16 pre-selection on every GPU, candidates exchanged by the batched
+    path's last kernel over peer memory.  Needs one GPU per shard (skipped on a 1-GPU box)."""
+    assert have_gpu()
+    import torch
+    from clip_database_b200 import GpuIndex
+    from clip_database_b200.multigpu import MultiGpuIndex
+    n_dev = torch.cuda.device_count()
+    if n_dev < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n = 90_000
+    rows = synth.unit_rows(n, DIM, 808)
+    rows[n - 3] = rows[20]
+    queries = synth.unit_rows(300, DIM, 809)
+    queries[11] = 0                                   # flagged on every shard -> re-run through the fused scan
+    queries[12] = rows[20]
+    with GpuIndex(0) as whole:
+        whole.load(rows, np.arange(1, n + 1))
+        want = whole.search(queries, 50)
+    with MultiGpuIndex(list(range(min(n_dev, 4)))) as multi:
+        multi.load(rows, np.arange(1, n + 1))
+        multi.enable_batch()
+        got = multi.search_batch(queries, 50)
+    assert np.array_equal(got.counts, want.counts)
+    assert np.array_equal(got.rowids, want.rowids)
+    assert np.array_equal(got.distances.view(np.uint32), want.distances.view(np.uint32))
+    assert got.rowids[12, :2].tolist() == [21, n - 2]
