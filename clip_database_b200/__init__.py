@@ -7,7 +7,8 @@ plus the query blend / negative-prompt arithmetic before it (:1378-1398, :545-60
 
   GpuIndex        one GPU's resident row store + kernels (ctypes over the C ABI)
   ImageDatabase   the reference's ``search()`` surface on top of it
-  ShardedIndex    row-sharded multi-GPU search (torch.distributed)
+  ShardedIndex    row-sharded multi-GPU search, one process per GPU (torch.distributed)
+  MultiGpuIndex   the same sharding from ONE process (clip_database_b200.multigpu)
   dropin.install  patch the reference class's own search() to use this path
 
 Importing this package does not need a GPU; creating a ``GpuIndex`` does, and
