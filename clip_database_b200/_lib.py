@@ -21,7 +21,7 @@ SCORE_POPCOUNT = 1
 IPC_HANDLE_BYTES = 64
 BLEND_POSITIVE_ZERO_NORM = 1
 BLEND_NEGATIVE_ZERO_NORM = 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # every symbol include/clipdb.h declares: (name, restype, argtypes)
 _F = POINTER(c_float)

@@ -28,7 +28,7 @@ using namespace clipdb;
 
 namespace {
 
-constexpr int ABI_VERSION = 2;
+constexpr int ABI_VERSION = 3;
 constexpr int FUSED_K_MAX = 128;        // largest k served by the register-resident lists
 constexpr int MERGE_SHARD_MAX_KEYS = 16384;
 
