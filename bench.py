@@ -59,7 +59,7 @@ def parse_args():
     ap.add_argument("--data", default="uniform", choices=["uniform", "clustered"],
                     help="uniform: seeded random unit rows and queries (BASELINE configs); clustered: 1024 clusters, "
                          "queries near stored rows (SURVEY §8d variant)")
-    ap.add_argument("--sample-stride", type=int, default=0, help="batch: pass A sampling stride (0 = auto)")
+    ap.add_argument("--sample-stride", type=int, default=0, help="batch: pass A samples 1/s of the rows (0 = auto)")
     ap.add_argument("--no-refine", action="store_true", help="batch: skip the second threshold")
     ap.add_argument("--exchange", default="auto", choices=["auto", "fused", "nccl"],
                     help="N > 1: fused = the scan kernel's last CTA exchanges candidates over NVLink peer memory "

@@ -53,7 +53,7 @@ constexpr int BQ_HEADER = 2048;  // barriers, TMEM base, thresholds
 constexpr int BQ_QUEUE_SMEM = 4 * 256 * 12;  // = BQ_QUEUE_BYTES (the epilogue warps' hit queues)
 constexpr int BQ_SMEM_BYTES = BQ_HEADER + BQ_STAGES * BQ_STAGE_BYTES + 1024 + BQ_QUEUE_SMEM;  // + alignment slack
 constexpr int BQ_TMEM_COLS = 512;
-constexpr int BQ_SAMPLE_STRIDE_MAX = 256;  // pass A visits at most every 256th tile (host picks the stride)
+constexpr int BQ_SAMPLE_STRIDE_MAX = 256;  // pass A samples at least 1/256 of the rows (host picks the ratio)
 // |cos^ - cos| <= e_d + e_q (1 + e_d) + slack, where e_d = max over rows of ||d^ - d|| / ||d|| and
 // e_q = ||q^ - q|| / ||q|| are the MEASURED bf16 rounding-error norms (Cauchy-Schwarz on
 // q.(d^-d) + (q^-q).d^) and the slack covers the tensor core's fp32 accumulation of 1152 exact

@@ -102,7 +102,7 @@ struct clipdb_ctx {
                                     // costs about one single-query scan, whatever its size)
     int64_t batch_cand_cap = 65536; // candidate rows kept per query (8x the ~8,000 the default sampling admits)
     int64_t batch_cta_pair = 1;     // 1: cta_group::2 contraction (CTA pairs), 0: single-CTA kernel
-    int64_t batch_sample_stride = 0; // pass A visits every s-th 128-row tile; 0 = auto (tiles/1024 clamped to 1..64)
+    int64_t batch_sample_stride = 0; // pass A samples 1/s of the rows; 0 = auto (see batch_sample_stride())
     int64_t batch_refine = 1;       // 1: second threshold from the candidates' own scores before the re-rank
     int64_t batch_static_tiles = 0; // 1: static tile interleave in the CTA-pair kernel (for A/B measurements)
     int64_t batch_npass = 0;        // 0: auto (64 / 128 / 256 queries per pass by batch size); else force >= that
@@ -663,17 +663,18 @@ int encode_bf16_map(clipdb_ctx *c, CUtensorMap *map, void *base, uint64_t rows, 
 
 constexpr int64_t BATCH_MIN_ROWS = 1;   // any non-empty store: with fewer sampled groups than k every row is a candidate
 
-// Pass A's sampling stride in 128-row tiles.  Sparser sampling makes pass A cheaper and the
-// thresholds looser: pass B then keeps about 1.25 * k * stride candidates per query (measured),
-// which must stay well inside the candidate capacity.  Auto: min(capacity, 32768) / (4k), at most every 256th
-// tile, never fewer than 8k sampled 32-row groups; a power of two so the CTA-pair kernel (256-row
-// pair tiles) samples the same fraction.
+// Pass A's sampling ratio s: it visits one tile (single-CTA kernel: 128 rows; CTA-pair kernel: 256
+// rows) out of every s, i.e. 1/s of the rows.  Sparser sampling makes pass A cheaper and the
+// thresholds looser: pass B then keeps about 2.5 * k * s candidates per query (measured on unit
+// random data), which must stay well inside the candidate capacity and, past ~8,000 per query,
+// starts to cost pass B more than pass A saves (profiles/r01v4_ab_tests.txt).  Auto: min(capacity,
+// 32768) / (8k), at most 256, never fewer than 8k sampled 32-row groups; a power of two.
 int batch_sample_stride(const clipdb_ctx *c, int64_t tiles, int k) {
     int64_t s = c->batch_sample_stride;
     if (s <= 0) {
         const int64_t kk = k > 0 ? k : 1;
         const int64_t budget = c->batch_cand_cap < 32768 ? c->batch_cand_cap : 32768;   // keep 2x+ headroom
-        s = budget / (4 * kk);
+        s = budget / (8 * kk);
         if (s > tiles / (2 * kk)) s = tiles / (2 * kk);   // at least 8k group maxima to pick the k-th from
     }
     if (s > BQ_SAMPLE_STRIDE_MAX) s = BQ_SAMPLE_STRIDE_MAX;
@@ -852,7 +853,7 @@ int batch_search_device_locked(clipdb_ctx *c, const float *d_queries, int32_t nq
         npass = c->batch_npass >= npass ? static_cast<int>(c->batch_npass) : npass;
     const int sstride = batch_sample_stride(c, tiles, k);
     // one maximum per (sampled 128-row tile, epilogue warp)
-    g.tile_stride = pair ? (sstride >= 2 ? sstride / 2 : 1) : sstride;   // pair kernel: in 256-row pair tiles
+    g.tile_stride = sstride;   // in the kernel's own tiles (pair kernel: 256-row pair tiles): 1/sstride of the rows
     const int eff = ((pair ? (tiles + 1) / 2 : tiles) + g.tile_stride - 1) / g.tile_stride;
     g.sample_groups = static_cast<long long>(eff) * (pair ? 8 : 4);
     RC_TRY(ensure_device(c, c->bq_scores, static_cast<size_t>(BQ_N) * g.sample_groups * sizeof(float)));
