@@ -139,26 +139,47 @@ class ImageDatabase:
             print(*a, flush=True)
 
     def reload(self) -> None:
-        """(Re)read the whole database into HBM."""
-        host = loader.read_store(self.db_path)
-        self._binary_count = host.binary_count
-        self._vec0_count = host.vec0_count
-        self._paths = list(host.file_paths)
+        """(Re)read the whole database into HBM.  With several GPUs every shard's rowid range is read
+        and uploaded on its own, so the float32 matrix never has to fit host memory at once."""
+        multi = hasattr(self.index, "shards")
+        world = self.index.world if multi else 1
+        sharded_load = multi
+        if multi:
+            n_joined = loader.shard_rowid_range(self.db_path, 0, world)[2]
+            if 0 < n_joined < world:
+                raise ValueError(f"{n_joined} rows cannot be sharded over {world} GPUs")
+            sharded_load = n_joined > 0              # a binary-only database has no float rows to shard
+        parts = []
+        for rank in range(world if sharded_load else 1):
+            if sharded_load:
+                lo, hi, _ = loader.shard_rowid_range(self.db_path, rank, world)
+                host = loader.read_store(self.db_path, min_rowid=lo, max_rowid=hi)
+                self.index.load_shard(rank, host.rows, host.rowids)
+                host.rows = None                     # uploaded: free the host copy before the next range
+            else:
+                host = loader.read_store(self.db_path)
+            parts.append(host)
+        if sharded_load:
+            self.index.finish_load()
+        first = parts[0]
+        self._binary_count = first.binary_count
+        self._vec0_count = sum(p.vec0_count for p in parts)
+        self._paths = [fp for p in parts for fp in p.file_paths]
         self._lowered = None
-        self._image_ids = host.image_ids
-        self._rowids = host.rowids
-        self._rowid_to_pos = {int(r): i for i, r in enumerate(host.rowids)}
+        self._image_ids = np.concatenate([p.image_ids for p in parts])
+        self._rowids = np.concatenate([p.rowids for p in parts])
+        self._rowid_to_pos = {int(r): i for i, r in enumerate(self._rowids)}
         self._mask_key = None
         self._codes = None
         self._code_mask_key = None
-        if host.rows.shape[0]:
-            self.index.load(host.rows, host.rowids)
-            if self.batch_store and self.index.dim == schema.EMBEDDING_DIM:
-                self.index.enable_batch()
-                if not hasattr(self.index, "shards"):
-                    self.index.set_option("batch_min_nq", 1)
-        self._log(f"loaded {host.rows.shape[0]} rows ({host.source}); {host.dropped} vec0 rows without "
-                  f"a mapping were skipped")
+        if not multi and first.rows.shape[0]:
+            self.index.load(first.rows, first.rowids)
+        if self.batch_store and self._rowids.shape[0] and self.index.dim == schema.EMBEDDING_DIM:
+            self.index.enable_batch()
+            if not multi:
+                self.index.set_option("batch_min_nq", 1)
+        self._log(f"loaded {self._rowids.shape[0]} rows ({first.source}); "
+                  f"{sum(p.dropped for p in parts)} vec0 rows without a mapping were skipped")
 
     def refresh(self) -> int:
         """Append rows the scanner added since the last load (new vec0 rowids are always

@@ -100,27 +100,59 @@ def _try_load_sqlite_vec(conn: sqlite3.Connection) -> bool:
         return False
 
 
-def _iter_vec0(conn: sqlite3.Connection, min_rowid: Optional[int]) -> Tuple[str, Iterator[Tuple[int, bytes]]]:
-    """(source, iterator of (rowid, float32 blob)) in ascending rowid order."""
+def _iter_vec0(conn: sqlite3.Connection, min_rowid: Optional[int], max_rowid: Optional[int] = None
+               ) -> Tuple[str, Iterator[Tuple[int, bytes]]]:
+    """(source, iterator of (rowid, float32 blob)) in ascending rowid order, for rowids in
+    (min_rowid, max_rowid]."""
     kind = _table_kind(conn, "vec0")
     lo = -(1 << 63) if min_rowid is None else min_rowid
+    hi = (1 << 63) - 1 if max_rowid is None else max_rowid
     if kind == "virtual":
         if _try_load_sqlite_vec(conn):
-            cur = conn.execute("SELECT rowid, embedding FROM vec0 WHERE rowid > ? ORDER BY rowid", (lo,))
+            cur = conn.execute("SELECT rowid, embedding FROM vec0 WHERE rowid > ? AND rowid <= ? ORDER BY rowid", (lo, hi))
             return "sqlite-vec", iter(cur)
         if _table_kind(conn, "vec0_rowids") is None:
             raise RuntimeError("vec0 is a sqlite-vec virtual table, the extension is not importable "
                                "and its shadow tables are missing")
-        return "shadow-tables", _iter_shadow(conn, lo)
+        return "shadow-tables", _iter_shadow(conn, lo, hi)
     if kind == "table":
-        cur = conn.execute("SELECT rowid, embedding FROM vec0 WHERE rowid > ? ORDER BY rowid", (lo,))
+        cur = conn.execute("SELECT rowid, embedding FROM vec0 WHERE rowid > ? AND rowid <= ? ORDER BY rowid", (lo, hi))
         return "plain-table", iter(cur)
     if _table_kind(conn, "vec0_rowids") is not None:
-        return "shadow-tables", _iter_shadow(conn, lo)
+        return "shadow-tables", _iter_shadow(conn, lo, hi)
     raise RuntimeError("database has no vec0 table")
 
 
-def _iter_shadow(conn: sqlite3.Connection, lo: int) -> Iterator[Tuple[int, bytes]]:
+def _vec0_rowids(conn: sqlite3.Connection) -> List[int]:
+    """Every vec0 rowid (no blobs), ascending."""
+    kind = _table_kind(conn, "vec0")
+    if kind == "table" or (kind == "virtual" and _try_load_sqlite_vec(conn)):
+        return [r[0] for r in conn.execute("SELECT rowid FROM vec0 ORDER BY rowid")]
+    if _table_kind(conn, "vec0_rowids") is not None:
+        return [r[0] for r in conn.execute("SELECT rowid FROM vec0_rowids ORDER BY rowid")]
+    raise RuntimeError("database has no vec0 table")
+
+
+def shard_rowid_range(db_path: str, rank: int, world: int) -> Tuple[Optional[int], Optional[int], int]:
+    """Row-sharding of a real database: the rows the search statement scans (vec0 INNER JOIN
+    image_embeddings INNER JOIN images), in rowid order, cut into `world` contiguous ranges of
+    equal size (+-1).  Returns (min_rowid exclusive, max_rowid inclusive, total joined rows) for
+    `rank` — only that range's blobs need to be read by that rank."""
+    conn = connect(db_path)
+    try:
+        partner = {r[0] for r in conn.execute(
+            "SELECT ie.rowid FROM image_embeddings ie JOIN images i ON ie.image_id = i.id")}
+        joined = [r for r in _vec0_rowids(conn) if r in partner]
+    finally:
+        conn.close()
+    n = len(joined)
+    lo, hi = n * rank // world, n * (rank + 1) // world
+    if hi <= lo:
+        return None, None, n
+    return (joined[lo - 1] if lo > 0 else None), joined[hi - 1], n
+
+
+def _iter_shadow(conn: sqlite3.Connection, lo: int, hi: int = (1 << 63) - 1) -> Iterator[Tuple[int, bytes]]:
     """Walk sqlite-vec's chunked storage in rowid order."""
     chunk_cache = {}
 
@@ -136,8 +168,8 @@ def _iter_shadow(conn: sqlite3.Connection, lo: int) -> Iterator[Tuple[int, bytes
             chunk_cache[cid] = (size, valid, memoryview(vectors))
         return chunk_cache[cid]
 
-    cur = conn.execute("SELECT rowid, chunk_id, chunk_offset FROM vec0_rowids WHERE rowid > ? "
-                       "ORDER BY rowid", (lo,))
+    cur = conn.execute("SELECT rowid, chunk_id, chunk_offset FROM vec0_rowids WHERE rowid > ? AND rowid <= ? "
+                       "ORDER BY rowid", (lo, hi))
     for rowid, cid, off in cur.fetchall():
         size, valid, vectors = chunk(cid)
         if off >= size or not valid[off]:
@@ -146,10 +178,12 @@ def _iter_shadow(conn: sqlite3.Connection, lo: int) -> Iterator[Tuple[int, bytes
         yield rowid, bytes(vectors[off * stride:(off + 1) * stride])
 
 
-def read_store(db_path: str, expect_dim: Optional[int] = None, min_rowid: Optional[int] = None) -> HostStore:
+def read_store(db_path: str, expect_dim: Optional[int] = None, min_rowid: Optional[int] = None,
+               max_rowid: Optional[int] = None) -> HostStore:
     """Everything the resident index needs, in scan order.  ``min_rowid`` restricts
     the read to rowids greater than it (incremental refresh after the scanner
-    appended rows; the reference never deletes from vec0)."""
+    appended rows; the reference never deletes from vec0); ``max_rowid`` (inclusive) bounds it
+    from above (one rank's range of a row-sharded store, see ``shard_rowid_range``)."""
     conn = connect(db_path)
     try:
         try:
@@ -158,10 +192,11 @@ def read_store(db_path: str, expect_dim: Optional[int] = None, min_rowid: Option
             binary_count = -1   # table not accessible: the reference returns [] (:1496-1500)
         join = conn.execute(
             "SELECT ie.rowid, ie.image_id, i.file_path FROM image_embeddings ie "
-            "JOIN images i ON ie.image_id = i.id WHERE ie.rowid > ? ORDER BY ie.rowid",
-            (-(1 << 63) if min_rowid is None else min_rowid,)).fetchall()
+            "JOIN images i ON ie.image_id = i.id WHERE ie.rowid > ? AND ie.rowid <= ? ORDER BY ie.rowid",
+            (-(1 << 63) if min_rowid is None else min_rowid,
+             (1 << 63) - 1 if max_rowid is None else max_rowid)).fetchall()
         partner = {r[0]: (r[1], r[2]) for r in join}
-        source, it = _iter_vec0(conn, min_rowid)
+        source, it = _iter_vec0(conn, min_rowid, max_rowid)
         rowids, image_ids, paths, blobs = [], [], [], []
         vec0_count = 0
         dim = expect_dim

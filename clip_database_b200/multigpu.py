@@ -64,6 +64,25 @@ class MultiGpuIndex:
         self.num_rows = n
         self._connect()
 
+    def load_shard(self, rank: int, rows: np.ndarray, rowids: np.ndarray) -> None:
+        """Load one shard at a time (a store larger than host memory is read range by range,
+        ``loader.shard_rowid_range``); call ``finish_load`` after the last one."""
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        if rows.shape[0] < 1:
+            raise ValueError("every shard needs at least one row")
+        self.shards[rank].load(rows, np.ascontiguousarray(rowids, dtype=np.int64))
+        self._shard_rows = getattr(self, "_shard_rows", {})
+        self._shard_rows[rank] = rows.shape[0]
+
+    def finish_load(self) -> None:
+        counts = [self._shard_rows[r] for r in range(self.world)]
+        self.bounds, at = [], 0
+        for c in counts:
+            self.bounds.append((at, at + c))
+            at += c
+        self.num_rows = at
+        self._connect()
+
     def _connect(self) -> None:
         if self._connected:
             return

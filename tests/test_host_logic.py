@@ -144,3 +144,26 @@ def test_read_codes_order_and_validation(tmp_path):
     conn.close()
     with pytest.raises(ValueError):
         loader.read_codes(db, expect_dim=1152)
+
+
+@pytest.mark.parametrize("layout", ["standin", "shadow"])
+def test_sharded_loading_covers_the_store_exactly_once(tmp_path, layout):
+    """Each rank of a row-sharded deployment reads only its rowid range; the ranges are contiguous,
+    equal (+-1) in JOINED rows and their concatenation is the whole store."""
+    from clip_database_b200 import loader
+    rows = synth.unit_rows(103, 1152, 12)
+    db = str(tmp_path / "s.db")
+    synth.write_reference_db(db, rows, vec0_layout=layout, rowid_start=5, drop_mapping_for=[0, 50], drop_image_for=[102])
+    whole = loader.read_store(db)
+    assert whole.rows.shape[0] == 100
+    for world in (1, 3, 8):
+        parts = []
+        for rank in range(world):
+            lo, hi, n = loader.shard_rowid_range(db, rank, world)
+            assert n == 100
+            part = loader.read_store(db, min_rowid=lo, max_rowid=hi)
+            assert abs(part.rows.shape[0] - 100 / world) < 1
+            parts.append(part)
+        assert np.array_equal(np.concatenate([p.rowids for p in parts]), whole.rowids)
+        assert np.array_equal(np.concatenate([p.rows for p in parts]), whole.rows)
+        assert sum((p.file_paths for p in parts), []) == whole.file_paths
