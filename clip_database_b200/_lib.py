@@ -21,7 +21,9 @@ SCORE_POPCOUNT = 1
 IPC_HANDLE_BYTES = 64
 BLEND_POSITIVE_ZERO_NORM = 1
 BLEND_NEGATIVE_ZERO_NORM = 2
-ABI_VERSION = 3
+ABI_VERSION = 4
+PLACE_DEVICE = 0
+PLACE_HOST = 1
 
 # every symbol include/clipdb.h declares: (name, restype, argtypes)
 _F = POINTER(c_float)
@@ -33,6 +35,7 @@ _CTX = c_void_p
 
 SIGNATURES = [
     ("clipdb_abi_version", c_int, []),
+    ("clipdb_source_hash", c_char_p, []),
     ("clipdb_create", c_int, [c_int, POINTER(_CTX)]),
     ("clipdb_destroy", None, [_CTX]),
     ("clipdb_last_error", c_char_p, [_CTX]),
@@ -46,6 +49,8 @@ SIGNATURES = [
     ("clipdb_append_rows", c_int, [_CTX, c_void_p, c_void_p, c_int64]),
     ("clipdb_update_row", c_int, [_CTX, c_int64, c_void_p]),
     ("clipdb_attach_rows", c_int, [_CTX, c_void_p, c_void_p, c_int64, c_int32, c_int64]),
+    ("clipdb_reserve_rows", c_int, [_CTX, c_int64, c_int32, c_int32, c_int32]),
+    ("clipdb_stage_buffer", c_int, [_CTX, c_int64, POINTER(c_void_p)]),
     ("clipdb_num_rows", c_int64, [_CTX]),
     ("clipdb_dim", c_int32, [_CTX]),
     ("clipdb_set_mask", c_int, [_CTX, c_void_p, c_int64]),
@@ -76,6 +81,9 @@ SIGNATURES = [
                                              c_void_p]),
     ("clipdb_search_batch_sharded_device", c_int, [_CTX, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                                    c_void_p, c_void_p, c_void_p]),
+    ("clipdb_exchange_abort", c_int, [_CTX, c_int32]),
+    ("clipdb_exchange_set_epoch", c_int, [_CTX, c_uint32, c_uint32]),
+    ("clipdb_exchange_stats", c_int, [_CTX, c_int32, c_int32, _D, _I64]),
     ("clipdb_merge_device", c_int, [_CTX, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                     c_void_p, c_void_p, c_void_p]),
     ("clipdb_merge_strided_device", c_int, [_CTX, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
@@ -105,10 +113,16 @@ def load() -> ctypes.CDLL:
     if _lib is not None:
         return _lib
     path = lib_path()
-    if not os.path.exists(path):
-        raise RuntimeError(
-            f"{path} is missing: the CUDA extension is not built and there is no CPU fallback. "
-            "Run `python -m clip_database_b200.build` (or __graft_entry__.build()).")
+    if _build.is_stale():
+        # missing, or compiled from other sources than the ones next to it (the library is not under
+        # version control): never run old kernels silently — rebuild when a compiler is here, else refuse
+        try:
+            _build.build()
+        except RuntimeError as e:
+            raise RuntimeError(
+                f"{path} is missing or was not built from the current sources, and it cannot be rebuilt "
+                f"here ({e}).  There is no CPU fallback: run `python -m clip_database_b200.build` where "
+                "nvcc is available.") from e
     L = ctypes.CDLL(path)
     for name, restype, argtypes in SIGNATURES:
         fn = getattr(L, name)  # AttributeError = symbol not exported

@@ -5,11 +5,12 @@ repository snapshot to the GPU box; it is git-ignored (``*.so``).
 """
 from __future__ import annotations
 
+import hashlib
 import os
 import shutil
 import subprocess
 import sys
-from typing import List
+from typing import List, Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
@@ -38,18 +39,40 @@ def _inputs() -> List[str]:
     return files
 
 
-def is_stale() -> bool:
+def source_hash() -> str:
+    """SHA-256 over the names and contents of everything the library is compiled from.  The same
+    string is compiled into the library (``clipdb_source_hash()``), so staleness does not depend on
+    file times (which a copy of the tree to another machine does not preserve)."""
+    h = hashlib.sha256()
+    for f in sorted(_inputs()):
+        h.update(os.path.basename(f).encode() + b"\0")
+        h.update(open(f, "rb").read())
+        h.update(b"\0")
+    return h.hexdigest()
+
+
+def built_hash() -> Optional[str]:
+    """The source hash recorded in the built library (read from the file, not by loading it: a stale
+    library must not already be mapped when the rebuilt one is dlopen'ed), or None."""
     if not os.path.exists(LIB_PATH):
-        return True
-    built = os.path.getmtime(LIB_PATH)
-    return any(os.path.getmtime(f) > built for f in _inputs())
+        return None
+    marker = b"clipdb-source-hash:"
+    data = open(LIB_PATH, "rb").read()
+    at = data.find(marker)
+    if at < 0:
+        return None
+    return data[at + len(marker):at + len(marker) + 64].split(b"\0", 1)[0].decode("ascii", "replace")
+
+
+def is_stale() -> bool:
+    return built_hash() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Build ``libclipdb_b200.so`` if missing or older than its sources."""
+    """Build ``libclipdb_b200.so`` if missing or compiled from other sources than the ones here."""
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", INCLUDE, "-o", LIB_PATH]
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-DCLIPDB_SOURCE_HASH=\"%s\"" % source_hash(), "-I", INCLUDE, "-o", LIB_PATH]
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

@@ -144,8 +144,10 @@ __device__ __forceinline__ size_t tiled_offset(long long row, int k) {  // eleme
 // u = q^ . n^ directly and the epilogue needs no per-row scale), the count of rows whose norm is 0
 // or not finite (stored as NaN: never pass a >= test), and the largest rounding-error norm
 // ||n^ - n|| over the store (float32 n; its own 2^-23-level error is inside BQ_ACCUM_SLACK).
-__global__ void __launch_bounds__(256) build_bf16_store_kernel(const float *__restrict__ rows, long long n,
-                                                               __nv_bfloat16 *__restrict__ out,
+// Converts rows [row_begin, row_end); `rows` is biased so that rows + r * 1152 addresses row r (the source may
+// be the resident store, its host-resident tier, or the caller's buffer of rows being appended).
+__global__ void __launch_bounds__(256) build_bf16_store_kernel(const float *__restrict__ rows, long long row_begin,
+                                                               long long row_end, __nv_bfloat16 *__restrict__ out,
                                                                unsigned long long *__restrict__ bad_rows,
                                                                unsigned int *__restrict__ max_row_err_bits) {
     const int lane = threadIdx.x & 31;
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(256) build_bf16_store_kernel(const float *__re
     const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
     unsigned bad = 0;
     float worst = 0.f;
-    for (long long r = warp; r < n; r += warps) {
+    for (long long r = row_begin + warp; r < row_end; r += warps) {
         const float4 *src = reinterpret_cast<const float4 *>(rows + r * SCAN_DIM);
         float4 v[SCAN_CHUNKS];
         float ss = 0.f;
@@ -984,6 +986,8 @@ __global__ void __launch_bounds__(BQ_SELECT_THREADS) batch_refine_kernel(const f
 // ---- exact re-rank: K1's arithmetic over each query's candidate rows ------------------------------
 struct RerankArgs {
     const float *rows;            // fp32 store
+    const float *rows_hi;         // tiered store: host-resident rows, read zero-copy over PCIe (row_address)
+    long long split;
     const float *queries;         // [nq][1152] fp32
     const unsigned int *cand_count;   // pass B's count (overflow check)
     const unsigned int *surv_rows;    // [nq][cand_cap] candidates that passed the second threshold
@@ -1031,8 +1035,8 @@ __global__ void __launch_bounds__(BQ_SEL_THREADS) batch_rerank_kernel(const Rera
             const bool two = j0 + 1 < count;
             const long long pos0 = list[j0];
             const long long pos1 = list[two ? j0 + 1 : j0];
-            const float4 *src0 = reinterpret_cast<const float4 *>(a.rows + pos0 * SCAN_DIM);
-            const float4 *src1 = reinterpret_cast<const float4 *>(a.rows + pos1 * SCAN_DIM);
+            const float4 *src0 = reinterpret_cast<const float4 *>(row_address(a.rows, a.rows_hi, a.split, pos0, SCAN_DIM));
+            const float4 *src1 = reinterpret_cast<const float4 *>(row_address(a.rows, a.rows_hi, a.split, pos1, SCAN_DIM));
             float4 v0[SCAN_CHUNKS], v1[SCAN_CHUNKS];
 #pragma unroll
             for (int j = 0; j < SCAN_CHUNKS; j++) v0[j] = ldg_stream(src0 + lane + 32 * j);

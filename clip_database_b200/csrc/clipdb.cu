@@ -7,6 +7,7 @@
 // device or a failed launch is an error code.
 #include <cuda_runtime.h>
 
+#include <climits>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -28,7 +29,10 @@ using namespace clipdb;
 
 namespace {
 
-constexpr int ABI_VERSION = 3;
+constexpr int ABI_VERSION = 4;
+#ifndef CLIPDB_SOURCE_HASH
+#define CLIPDB_SOURCE_HASH "unknown"
+#endif
 constexpr int FUSED_K_MAX = 128;        // largest k served by the register-resident lists
 constexpr int MERGE_SHARD_MAX_KEYS = 16384;
 
@@ -49,7 +53,10 @@ struct clipdb_ctx {
     int64_t launches = 0;
 
     // resident store
-    float *rows = nullptr;
+    float *rows = nullptr;           // HBM tier: rows [0, min(n, split))
+    float *rows_host = nullptr;      // tiered store (clipdb_reserve_rows): pinned host memory, rows [split, cap)
+    float *rows_host_dev = nullptr;  // the same memory as the device addresses it
+    int64_t split = LLONG_MAX;       // first row position that lives in rows_host (LLONG_MAX: all rows in HBM)
     int64_t *rowids = nullptr;
     bool owns_rows = false;
     int64_t n = 0, cap = 0;
@@ -76,6 +83,10 @@ struct clipdb_ctx {
     bool xchg_connected = false;
     uint32_t xchg_epoch = 0, xchg_batch_epoch = 0;   // single-query and batched passes count separately
     int64_t xchg_timeout_ms = 10000;
+    int *xchg_abort_host = nullptr;   // mapped host flag the waiting kernels poll (clipdb_exchange_abort)
+    int *xchg_abort_dev = nullptr;
+    Buffer xchg_stats;                // XCHG_STATS_WORDS uint64: per-launch timeline sums (clipdb_exchange_stats)
+    bool xchg_stats_on = false;
 
     // workspaces (grown on demand)
     Buffer cand_a, cand_b, sync_buf, all_keys_a, all_keys_b, cub_tmp;
@@ -87,12 +98,15 @@ struct clipdb_ctx {
     size_t r_bytes = 0;
     Buffer d_blend_in, d_blend_flags;
     Buffer pinned;      // host staging (inputs, then results)
+    Buffer stage;       // pinned host buffer lent to the caller (clipdb_stage_buffer)
     Buffer pinned_aux;  // host staging for the blended query read-back
     Buffer pinned_flags; // host staging for the batched path's per-query flags
 
     // batched path (K4): bf16 copy of the store + workspaces
     bool batch_enabled = false;
-    bool batch_dirty = false;            // rows changed since the bf16 copy was built (rebuilt on next use)
+    bool batch_dirty = false;            // the bf16 copy must be rebuilt from scratch before its next use
+    int64_t bf16_built = 0;              // rows [0, bf16_built) of the bf16 copy are current
+    int64_t bf16_cap_rows = 0;           // rows the bf16 buffer has room for (a multiple of 128)
     unsigned long long batch_bad_rows = 0;  // zero-norm / non-finite rows found when the copy was built
     Buffer bf16_rows, bad_rows, bq_queries, bq_qnorm, bq_scores, bq_thr, bq_flags, bq_count, bq_cand, bq_parts, bq_qerr, row_err;
     Buffer bq_cand_u, bq_margin, bq_surv, bq_surv_count, bq_tilectr;
@@ -123,6 +137,7 @@ struct clipdb_ctx {
     int64_t scan_assign = 2;   // SCAN_ASSIGN_* (dynamic: +5 % over static interleaving, profiles/r01_sweep2.json)
     int64_t scan_chunk = 4;    // tiles per atomicAdd (dynamic assignment)
     int64_t fuse_tail = 1;     // 1: the scan's last CTA merges and decodes (one launch per query); 0: merge-tree kernels
+    int64_t host_tier_from_row = 0;  // clipdb_reserve_rows(CLIPDB_PLACE_HOST): rows below this position stay in HBM
 };
 
 namespace {
@@ -214,7 +229,10 @@ void release_store(clipdb_ctx *c) {
         if (c->rows) cudaFree(c->rows);
         if (c->rowids) cudaFree(c->rowids);
     }
+    if (c->rows_host) cudaFreeHost(c->rows_host);
     c->rows = nullptr;
+    c->rows_host = c->rows_host_dev = nullptr;
+    c->split = LLONG_MAX;
     c->rowids = nullptr;
     c->owns_rows = false;
     c->n = c->cap = 0;
@@ -224,7 +242,17 @@ void release_store(clipdb_ctx *c) {
     c->mask = nullptr;
     c->mask_words = 0;
     c->batch_enabled = false;   // the bf16 copy described the old rows
+    c->bf16_built = c->bf16_cap_rows = 0;
     free_buffer(c->bf16_rows);
+}
+
+// where row `pos` of the store lives, as the HOST addresses it (cudaMemcpy destinations)
+float *store_row_host_view(clipdb_ctx *c, int64_t pos) {
+    return pos < c->split ? c->rows + pos * c->ld : c->rows_host + (pos - c->split) * c->ld;
+}
+// biased base of the host tier for the kernels: rows_hi + pos * ld addresses row pos >= split
+const float *store_rows_hi(const clipdb_ctx *c) {
+    return c->rows_host_dev ? c->rows_host_dev - c->split * c->ld : nullptr;
 }
 
 void release_exchange(clipdb_ctx *c) {
@@ -237,6 +265,8 @@ void release_exchange(clipdb_ctx *c) {
     c->xchg_inbox = nullptr;
     c->xchg_world = 0;
     c->xchg_connected = false;
+    if (c->xchg_abort_host) cudaFreeHost(c->xchg_abort_host);
+    c->xchg_abort_host = c->xchg_abort_dev = nullptr;
     cudaGetLastError();
 }
 
@@ -255,18 +285,24 @@ void release_codes(clipdb_ctx *c) {
     c->code_mask_words = 0;
 }
 
-// copy `m` rows of `dim` floats (host or device) into the store at row `at`
+// copy `m` rows of `dim` floats (host or device) into the store at row `at`; a range that crosses the
+// tier boundary of a tiered store is copied in two pieces
 int copy_rows_in(clipdb_ctx *c, const float *src, const int64_t *src_ids, int64_t at, int64_t m) {
     if (m == 0) return CLIPDB_OK;
-    float *dst = c->rows + at * c->ld;
-    if (c->ld == c->dim) {
-        CU_TRY(c, cudaMemcpyAsync(dst, src, static_cast<size_t>(m) * c->dim * sizeof(float),
-                                  cudaMemcpyDefault, c->stream));
-    } else {
-        CU_TRY(c, cudaMemsetAsync(dst, 0, static_cast<size_t>(m) * c->ld * sizeof(float), c->stream));
-        CU_TRY(c, cudaMemcpy2DAsync(dst, c->ld * sizeof(float), src, c->dim * sizeof(float),
-                                    c->dim * sizeof(float), static_cast<size_t>(m),
-                                    cudaMemcpyDefault, c->stream));
+    for (int64_t lo = at; lo < at + m;) {
+        const int64_t hi = (lo < c->split && at + m > c->split) ? c->split : at + m;
+        float *dst = store_row_host_view(c, lo);
+        const float *from = src + (lo - at) * c->dim;
+        const size_t rows_here = static_cast<size_t>(hi - lo);
+        if (c->ld == c->dim) {
+            CU_TRY(c, cudaMemcpyAsync(dst, from, rows_here * c->dim * sizeof(float), cudaMemcpyDefault, c->stream));
+        } else {
+            if (lo < c->split) CU_TRY(c, cudaMemsetAsync(dst, 0, rows_here * c->ld * sizeof(float), c->stream));
+            else memset(dst, 0, rows_here * c->ld * sizeof(float));
+            CU_TRY(c, cudaMemcpy2DAsync(dst, c->ld * sizeof(float), from, c->dim * sizeof(float),
+                                        c->dim * sizeof(float), rows_here, cudaMemcpyDefault, c->stream));
+        }
+        lo = hi;
     }
     if (c->rowids) {
         if (!src_ids) return fail(c, CLIPDB_ERR_INVALID, "store has explicit rowids; rowids required");
@@ -277,14 +313,25 @@ int copy_rows_in(clipdb_ctx *c, const float *src, const int64_t *src_ids, int64_
     return CLIPDB_OK;
 }
 
-int alloc_store(clipdb_ctx *c, int64_t cap, int32_t dim, bool with_ids) {
+// device_rows < 0 (or >= cap): every row in HBM; otherwise rows [0, device_rows rounded down to 128) in HBM
+// and the rest in pinned, device-mapped host memory (the tiered store of clipdb_reserve_rows)
+int alloc_store(clipdb_ctx *c, int64_t cap, int32_t dim, bool with_ids, int64_t device_rows = -1) {
     release_store(c);
     c->dim = dim;
     c->ld = (dim + 3) & ~3;
     c->cap = cap > 0 ? cap : 1;
     c->owns_rows = true;
+    int64_t dev_cap = c->cap;
+    if (device_rows >= 0 && device_rows < c->cap) dev_cap = device_rows & ~static_cast<int64_t>(127);
     CU_TRY(c, cudaMalloc(reinterpret_cast<void **>(&c->rows),
-                         static_cast<size_t>(c->cap) * c->ld * sizeof(float)));
+                         static_cast<size_t>(dev_cap > 0 ? dev_cap : 1) * c->ld * sizeof(float)));
+    if (dev_cap < c->cap) {
+        CU_TRY(c, cudaHostAlloc(reinterpret_cast<void **>(&c->rows_host),
+                                static_cast<size_t>(c->cap - dev_cap) * c->ld * sizeof(float),
+                                cudaHostAllocMapped | cudaHostAllocPortable));
+        CU_TRY(c, cudaHostGetDevicePointer(reinterpret_cast<void **>(&c->rows_host_dev), c->rows_host, 0));
+        c->split = dev_cap;
+    }
     if (with_ids)
         CU_TRY(c, cudaMalloc(reinterpret_cast<void **>(&c->rowids),
                              static_cast<size_t>(c->cap) * sizeof(int64_t)));
@@ -479,6 +526,8 @@ int search_one(clipdb_ctx *c, const float *d_query, int k, int metric, bool use_
 
     ScanArgs a{};
     a.rows = c->rows;
+    a.rows_hi = store_rows_hi(c);
+    a.split = c->split;
     a.query = d_query;
     a.mask = use_mask ? c->mask : nullptr;
     RC_TRY(prepare_sync(c, &a.sync));
@@ -661,7 +710,6 @@ int encode_bf16_map(clipdb_ctx *c, CUtensorMap *map, void *base, uint64_t rows, 
     return CLIPDB_OK;
 }
 
-constexpr int64_t BATCH_MIN_ROWS = 1;   // any non-empty store: with fewer sampled groups than k every row is a candidate
 
 // Pass A's sampling ratio s: it visits one tile (single-CTA kernel: 128 rows; CTA-pair kernel: 256
 // rows) out of every s, i.e. 1/s of the rows.  Sparser sampling makes pass A cheaper and the
@@ -683,24 +731,70 @@ int batch_sample_stride(const clipdb_ctx *c, int64_t tiles, int k) {
     return p;
 }
 
+// bf16 buffer with room for `cap_rows` rows (whole 128-row tiles, zero filled); rows already converted
+// survive a growth.  The TMA map covers the whole buffer, so it only changes when the buffer does.
+int batch_ensure_store(clipdb_ctx *c, int64_t cap_rows) {
+    const int64_t tiles = (cap_rows + BQ_M - 1) / BQ_M;
+    const int64_t want_rows = (tiles > 0 ? tiles : 1) * BQ_M;
+    if (c->bf16_rows.p && c->bf16_cap_rows >= want_rows) return CLIPDB_OK;
+    const size_t bytes = static_cast<size_t>(want_rows) * SCAN_DIM * 2;
+    void *fresh = nullptr;
+    CU_TRY(c, cudaMalloc(&fresh, bytes));
+    const size_t keep = c->bf16_rows.p ? static_cast<size_t>((c->bf16_built + BQ_M - 1) / BQ_M) * BQ_M * SCAN_DIM * 2 : 0;
+    if (keep) CU_TRY(c, cudaMemcpyAsync(fresh, c->bf16_rows.p, keep, cudaMemcpyDeviceToDevice, c->stream));
+    CU_TRY(c, cudaMemsetAsync(static_cast<uint8_t *>(fresh) + keep, 0, bytes - keep, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    free_buffer(c->bf16_rows);
+    c->bf16_rows.p = fresh;
+    c->bf16_rows.bytes = bytes;
+    c->bf16_cap_rows = want_rows;
+    return encode_bf16_map(c, &c->map_rows, c->bf16_rows.p, static_cast<uint64_t>(want_rows / BQ_M) * BQ_K_BLOCKS * BQ_M,
+                           BQ_M, BQ_BLOCK_K);
+}
+
+// convert rows [begin, end) into the bf16 copy.  `src` (nullable) = a DEVICE-addressable buffer holding exactly
+// those rows (the caller's chunk being appended: saves re-reading it from the store, which for the host tier
+// of a tiered store means a second trip over PCIe); otherwise they are read from the store itself.
+int batch_convert_rows(clipdb_ctx *c, int64_t begin, int64_t end, const float *src) {
+    auto launch = [&](const float *biased_base, int64_t lo, int64_t hi) -> int {
+        if (hi <= lo) return CLIPDB_OK;
+        const int64_t warps_wanted = hi - lo;
+        int64_t blocks = (warps_wanted + 7) / 8;
+        if (blocks > static_cast<int64_t>(c->sm_count) * 8) blocks = static_cast<int64_t>(c->sm_count) * 8;
+        build_bf16_store_kernel<<<static_cast<unsigned>(blocks), 256, 0, c->stream>>>(
+            biased_base, lo, hi, static_cast<__nv_bfloat16 *>(c->bf16_rows.p),
+            static_cast<unsigned long long *>(c->bad_rows.p), static_cast<unsigned int *>(c->row_err.p));
+        CU_TRY(c, cudaGetLastError());
+        c->launches++;
+        return CLIPDB_OK;
+    };
+    if (src) {
+        RC_TRY(launch(src - begin * SCAN_DIM, begin, end));
+    } else {
+        int64_t mid = begin > c->split ? begin : c->split;   // first row of the range that lives in the host tier
+        if (mid > end) mid = end;
+        RC_TRY(launch(c->rows, begin, mid));
+        RC_TRY(launch(store_rows_hi(c), mid, end));
+    }
+    CU_TRY(c, cudaMemcpyAsync(&c->batch_bad_rows, c->bad_rows.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                              c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (end > c->bf16_built) c->bf16_built = end;
+    return CLIPDB_OK;
+}
+
+// (re)build whatever part of the bf16 copy is missing: everything after clipdb_enable_batch or when the copy
+// was invalidated, otherwise only the rows appended since (each append converts its own rows, so this is
+// normally a no-op).
 int batch_build_locked(clipdb_ctx *c) {
     if (!c->rows || c->dim != SCAN_DIM || c->ld != SCAN_DIM)
-        return fail(c, CLIPDB_ERR_UNSUPPORTED, "batched path needs a loaded store with dim == %d", SCAN_DIM);
-    if (c->n < BATCH_MIN_ROWS)
-        return fail(c, CLIPDB_ERR_UNSUPPORTED, "batched path needs at least %lld rows", (long long)BATCH_MIN_ROWS);
-    const int64_t tiles = (c->n + BQ_M - 1) / BQ_M;
-    // pre-tiled bf16 copy: whole 128-row tiles (the last one zero padded)
-    const size_t bf16_bytes = static_cast<size_t>(tiles) * BQ_M * SCAN_DIM * 2;
-    RC_TRY(ensure_device(c, c->bf16_rows, bf16_bytes));
-    if (c->n % BQ_M)
-        CU_TRY(c, cudaMemsetAsync(static_cast<uint8_t *>(c->bf16_rows.p) + static_cast<size_t>(tiles - 1) * BQ_M * SCAN_DIM * 2,
-                                  0, static_cast<size_t>(BQ_M) * SCAN_DIM * 2, c->stream));
+        return fail(c, CLIPDB_ERR_UNSUPPORTED, "batched path needs a loaded (or reserved) store with dim == %d", SCAN_DIM);
+    const bool first = !c->batch_enabled;
     RC_TRY(ensure_device(c, c->bad_rows, sizeof(unsigned long long)));
     RC_TRY(ensure_device(c, c->bq_queries, static_cast<size_t>(BQ_N) * SCAN_DIM * 2));
     RC_TRY(ensure_device(c, c->bq_qnorm, BQ_N * sizeof(float)));
     RC_TRY(ensure_device(c, c->bq_qerr, BQ_N * sizeof(float)));
     RC_TRY(ensure_device(c, c->row_err, sizeof(unsigned int)));
-    CU_TRY(c, cudaMemsetAsync(c->row_err.p, 0, sizeof(unsigned int), c->stream));
     RC_TRY(ensure_device(c, c->bq_thr, BQ_N * sizeof(float)));
     RC_TRY(ensure_device(c, c->bq_flags, BQ_N * sizeof(int32_t)));
     RC_TRY(ensure_device(c, c->bq_count, BQ_N * sizeof(unsigned int)));
@@ -711,29 +805,28 @@ int batch_build_locked(clipdb_ctx *c) {
     RC_TRY(ensure_device(c, c->bq_surv_count, BQ_N * sizeof(unsigned int)));
     RC_TRY(ensure_device(c, c->bq_tilectr, 2 * sizeof(unsigned int)));
     RC_TRY(ensure_device(c, c->bq_parts, static_cast<size_t>(BQ_N) * 8 * 128 * sizeof(uint64_t)));
-    CU_TRY(c, cudaMemsetAsync(c->bad_rows.p, 0, sizeof(unsigned long long), c->stream));
-    build_bf16_store_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(
-        c->rows, c->n, static_cast<__nv_bfloat16 *>(c->bf16_rows.p),
-        static_cast<unsigned long long *>(c->bad_rows.p), static_cast<unsigned int *>(c->row_err.p));
-    CU_TRY(c, cudaGetLastError());
-    c->launches++;
-    RC_TRY(encode_bf16_map(c, &c->map_rows, c->bf16_rows.p, static_cast<uint64_t>(tiles) * BQ_K_BLOCKS * BQ_M, BQ_M,
-                           BQ_BLOCK_K));
-    RC_TRY(encode_bf16_map(c, &c->map_q, c->bq_queries.p, BQ_N, BQ_N));
-    RC_TRY(encode_bf16_map(c, &c->map_qhalf[0], c->bq_queries.p, BQ_N, 64 / 2));
-    RC_TRY(encode_bf16_map(c, &c->map_qhalf[1], c->bq_queries.p, BQ_N, 128 / 2));
-    RC_TRY(encode_bf16_map(c, &c->map_qhalf[2], c->bq_queries.p, BQ_N, 256 / 2));
-    CU_TRY(c, cudaFuncSetAttribute(batch_gemm_pair_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<64>::SMEM_BYTES));
-    CU_TRY(c, cudaFuncSetAttribute(batch_gemm_pair_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<64>::SMEM_BYTES));
-    CU_TRY(c, cudaFuncSetAttribute(batch_gemm_pair_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<128>::SMEM_BYTES));
-    CU_TRY(c, cudaFuncSetAttribute(batch_gemm_pair_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<128>::SMEM_BYTES));
-    CU_TRY(c, cudaFuncSetAttribute(batch_gemm_pair_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<256>::SMEM_BYTES));
-    CU_TRY(c, cudaFuncSetAttribute(batch_gemm_pair_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<256>::SMEM_BYTES));
-    CU_TRY(c, cudaFuncSetAttribute(batch_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BQ_SMEM_BYTES));
-    CU_TRY(c, cudaFuncSetAttribute(batch_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BQ_SMEM_BYTES));
-    CU_TRY(c, cudaMemcpyAsync(&c->batch_bad_rows, c->bad_rows.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                              c->stream));
-    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (first || c->batch_dirty) {
+        c->bf16_built = 0;
+        CU_TRY(c, cudaMemsetAsync(c->row_err.p, 0, sizeof(unsigned int), c->stream));
+        CU_TRY(c, cudaMemsetAsync(c->bad_rows.p, 0, sizeof(unsigned long long), c->stream));
+        c->batch_bad_rows = 0;
+    }
+    RC_TRY(batch_ensure_store(c, c->cap > c->n ? c->cap : c->n));
+    if (first) {
+        RC_TRY(encode_bf16_map(c, &c->map_q, c->bq_queries.p, BQ_N, BQ_N));
+        RC_TRY(encode_bf16_map(c, &c->map_qhalf[0], c->bq_queries.p, BQ_N, 64 / 2));
+        RC_TRY(encode_bf16_map(c, &c->map_qhalf[1], c->bq_queries.p, BQ_N, 128 / 2));
+        RC_TRY(encode_bf16_map(c, &c->map_qhalf[2], c->bq_queries.p, BQ_N, 256 / 2));
+        CU_TRY(c, cudaFuncSetAttribute(batch_gemm_pair_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<64>::SMEM_BYTES));
+        CU_TRY(c, cudaFuncSetAttribute(batch_gemm_pair_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<64>::SMEM_BYTES));
+        CU_TRY(c, cudaFuncSetAttribute(batch_gemm_pair_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<128>::SMEM_BYTES));
+        CU_TRY(c, cudaFuncSetAttribute(batch_gemm_pair_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<128>::SMEM_BYTES));
+        CU_TRY(c, cudaFuncSetAttribute(batch_gemm_pair_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<256>::SMEM_BYTES));
+        CU_TRY(c, cudaFuncSetAttribute(batch_gemm_pair_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<256>::SMEM_BYTES));
+        CU_TRY(c, cudaFuncSetAttribute(batch_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BQ_SMEM_BYTES));
+        CU_TRY(c, cudaFuncSetAttribute(batch_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BQ_SMEM_BYTES));
+    }
+    if (c->bf16_built < c->n) RC_TRY(batch_convert_rows(c, c->bf16_built, c->n, nullptr));
     c->batch_enabled = true;
     c->batch_dirty = false;
     return CLIPDB_OK;
@@ -786,6 +879,8 @@ int batch_launch_tail(clipdb_ctx *c, const float *d_queries, int32_t nq, int32_t
         c->launches++;
         RerankArgs r{};
         r.rows = c->rows;
+        r.rows_hi = store_rows_hi(c);
+        r.split = c->split;
         r.queries = d_queries;
         r.cand_count = static_cast<const unsigned int *>(c->bq_count.p);
         r.surv_rows = static_cast<const unsigned int *>(c->bq_surv.p);
@@ -988,6 +1083,11 @@ extern "C" {
 
 int clipdb_abi_version(void) { return ABI_VERSION; }
 
+// the marker lets a binding read the hash out of the file without loading it (a stale library must not be
+// dlopen'ed in the process that is about to rebuild and load the fresh one)
+static const char SOURCE_HASH_MARKER[] = "clipdb-source-hash:" CLIPDB_SOURCE_HASH;
+const char *clipdb_source_hash(void) { return SOURCE_HASH_MARKER + 19; }
+
 int clipdb_create(int device, clipdb_ctx **out) {
     if (!out) return CLIPDB_ERR_INVALID;
     *out = nullptr;
@@ -1031,9 +1131,10 @@ void clipdb_destroy(clipdb_ctx *c) {
                           &c->cub_tmp, &c->d_query, &c->d_results, &c->d_blend_in, &c->d_blend_flags, &c->bf16_rows,
                           &c->bad_rows, &c->bq_queries, &c->bq_qnorm, &c->bq_scores, &c->bq_thr, &c->bq_flags,
                           &c->bq_count, &c->bq_cand, &c->bq_parts, &c->bq_qerr, &c->row_err, &c->bq_cand_u, &c->bq_margin,
-                          &c->bq_surv, &c->bq_surv_count, &c->bq_tilectr};
+                          &c->bq_surv, &c->bq_surv_count, &c->bq_tilectr, &c->xchg_stats};
         for (Buffer *b : bufs) free_buffer(*b);
         if (c->pinned.p) cudaFreeHost(c->pinned.p);
+        if (c->stage.p) cudaFreeHost(c->stage.p);
         if (c->pinned_aux.p) cudaFreeHost(c->pinned_aux.p);
         if (c->pinned_flags.p) cudaFreeHost(c->pinned_flags.p);
         for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -1083,6 +1184,7 @@ static int64_t *option_slot(clipdb_ctx *c, const char *name) {
     if (!strcmp(name, "scan_assign")) return &c->scan_assign;
     if (!strcmp(name, "scan_chunk")) return &c->scan_chunk;
     if (!strcmp(name, "fuse_tail")) return &c->fuse_tail;
+    if (!strcmp(name, "host_tier_from_row")) return &c->host_tier_from_row;
     if (!strcmp(name, "xchg_timeout_ms")) return &c->xchg_timeout_ms;
     if (!strcmp(name, "batch_min_nq")) return &c->batch_min_nq;
     if (!strcmp(name, "batch_cand_cap")) return &c->batch_cand_cap;
@@ -1099,7 +1201,8 @@ int clipdb_set_option(clipdb_ctx *c, const char *name, int64_t value) {
     std::lock_guard<std::mutex> lk(c->mu);
     int64_t *slot = option_slot(c, name);
     if (!slot) return fail(c, CLIPDB_ERR_INVALID, "unknown option '%s'", name ? name : "(null)");
-    if (value < 0 || value > (1 << 20)) return fail(c, CLIPDB_ERR_INVALID, "option '%s' out of range", name);
+    if (value < 0 || (value > (1 << 20) && slot != &c->host_tier_from_row))
+        return fail(c, CLIPDB_ERR_INVALID, "option '%s' out of range", name);
     if (slot == &c->ldg_ctas_per_sm && value == 0) value = 1;
     if (slot == &c->batch_cand_cap) {
         if (value < 256) return fail(c, CLIPDB_ERR_INVALID, "option 'batch_cand_cap' must be at least 256");
@@ -1147,26 +1250,46 @@ int clipdb_append_rows(clipdb_ctx *c, const float *rows, const int64_t *rowids, 
     if (c->n + m > c->cap) {
         int64_t cap = c->cap + c->cap / 2;
         if (cap < c->n + m) cap = c->n + m;
-        float *nr = nullptr;
         int64_t *ni = nullptr;
-        CU_TRY(c, cudaMalloc(reinterpret_cast<void **>(&nr), static_cast<size_t>(cap) * c->ld * sizeof(float)));
-        CU_TRY(c, cudaMemcpyAsync(nr, c->rows, static_cast<size_t>(c->n) * c->ld * sizeof(float),
-                                  cudaMemcpyDeviceToDevice, c->stream));
+        if (c->rows_host) {
+            // tiered store: the HBM tier keeps its size, the host tier grows
+            float *nh = nullptr, *nh_dev = nullptr;
+            CU_TRY(c, cudaHostAlloc(reinterpret_cast<void **>(&nh), static_cast<size_t>(cap - c->split) * c->ld * sizeof(float),
+                                    cudaHostAllocMapped | cudaHostAllocPortable));
+            CU_TRY(c, cudaHostGetDevicePointer(reinterpret_cast<void **>(&nh_dev), nh, 0));
+            CU_TRY(c, cudaStreamSynchronize(c->stream));
+            if (c->n > c->split) memcpy(nh, c->rows_host, static_cast<size_t>(c->n - c->split) * c->ld * sizeof(float));
+            cudaFreeHost(c->rows_host);
+            c->rows_host = nh;
+            c->rows_host_dev = nh_dev;
+        } else {
+            float *nr = nullptr;
+            CU_TRY(c, cudaMalloc(reinterpret_cast<void **>(&nr), static_cast<size_t>(cap) * c->ld * sizeof(float)));
+            CU_TRY(c, cudaMemcpyAsync(nr, c->rows, static_cast<size_t>(c->n) * c->ld * sizeof(float),
+                                      cudaMemcpyDeviceToDevice, c->stream));
+            CU_TRY(c, cudaStreamSynchronize(c->stream));
+            cudaFree(c->rows);
+            c->rows = nr;
+        }
         if (c->rowids) {
             CU_TRY(c, cudaMalloc(reinterpret_cast<void **>(&ni), static_cast<size_t>(cap) * sizeof(int64_t)));
             CU_TRY(c, cudaMemcpyAsync(ni, c->rowids, static_cast<size_t>(c->n) * sizeof(int64_t),
                                       cudaMemcpyDeviceToDevice, c->stream));
+            CU_TRY(c, cudaStreamSynchronize(c->stream));
+            cudaFree(c->rowids);
+            c->rowids = ni;
         }
-        CU_TRY(c, cudaStreamSynchronize(c->stream));
-        cudaFree(c->rows);
-        if (c->rowids) cudaFree(c->rowids);
-        c->rows = nr;
-        c->rowids = ni;
         c->cap = cap;
     }
     RC_TRY(copy_rows_in(c, rows, rowids, c->n, m));
+    const int64_t old_n = c->n;
     c->n += m;
-    if (m > 0) c->batch_dirty = true;   // the bf16 copy is rebuilt before the next batched search
+    if (m > 0 && c->batch_enabled && !c->batch_dirty) {
+        // keep the bf16 copy current: convert just the new rows (from the caller's buffer when the GPU can
+        // address it, else from where they landed in the store)
+        RC_TRY(batch_ensure_store(c, c->cap));
+        RC_TRY(batch_convert_rows(c, old_n, c->n, is_device_pointer(rows) ? rows : nullptr));
+    }
     if (c->mask) {  // a mask sized for the old row count no longer applies
         cudaFree(c->mask);
         c->mask = nullptr;
@@ -1181,10 +1304,15 @@ int clipdb_update_row(clipdb_ctx *c, int64_t position, const float *row) {
     if (!c->rows || !c->owns_rows) return fail(c, CLIPDB_ERR_STATE, "update_row: no owned store");
     if (position < 0 || position >= c->n || !row) return fail(c, CLIPDB_ERR_INVALID, "update_row: bad argument");
     DeviceGuard g(c->device);
-    CU_TRY(c, cudaMemcpyAsync(c->rows + position * c->ld, row, c->dim * sizeof(float), cudaMemcpyDefault,
+    CU_TRY(c, cudaMemcpyAsync(store_row_host_view(c, position), row, c->dim * sizeof(float), cudaMemcpyDefault,
                               c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
-    c->batch_dirty = true;
+    if (c->batch_enabled && !c->batch_dirty) {
+        // re-convert the one row; the store-wide count of zero-norm rows can only be kept exact that way
+        // while it is zero (a repaired bad row would stay counted), otherwise rebuild before the next use
+        if (c->batch_bad_rows == 0) RC_TRY(batch_convert_rows(c, position, position + 1, nullptr));
+        else c->batch_dirty = true;
+    }
     return CLIPDB_OK;
 }
 
@@ -1206,6 +1334,41 @@ int clipdb_attach_rows(clipdb_ctx *c, const float *d_rows, const int64_t *d_rowi
     c->n = c->cap = n;
     c->dim = c->ld = dim;
     c->rowid_base = rowid_base;
+    return CLIPDB_OK;
+}
+
+int clipdb_reserve_rows(clipdb_ctx *c, int64_t capacity, int32_t dim, int32_t explicit_rowids, int32_t placement) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (capacity < 0 || dim <= 0) return fail(c, CLIPDB_ERR_INVALID, "reserve_rows: bad argument");
+    if (placement != CLIPDB_PLACE_DEVICE && placement != CLIPDB_PLACE_HOST)
+        return fail(c, CLIPDB_ERR_INVALID, "reserve_rows: unknown placement %d", placement);
+    DeviceGuard g(c->device);
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    // option "host_tier_from_row": with CLIPDB_PLACE_HOST, rows below it still go to HBM (what is left of it)
+    const int64_t device_rows = placement == CLIPDB_PLACE_DEVICE ? -1 : c->host_tier_from_row;
+    const int rc = alloc_store(c, capacity, dim, explicit_rowids != 0, device_rows);
+    if (rc != CLIPDB_OK) release_store(c);
+    return rc;
+}
+
+int clipdb_stage_buffer(clipdb_ctx *c, int64_t bytes, void **out_host) {
+    if (!c || !out_host) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (bytes <= 0) return fail(c, CLIPDB_ERR_INVALID, "stage_buffer: bytes must be positive");
+    DeviceGuard g(c->device);
+    Buffer &b = c->stage;
+    if (!b.p || b.bytes < static_cast<size_t>(bytes)) {
+        if (b.p) {
+            CU_TRY(c, cudaStreamSynchronize(c->stream));
+            CU_TRY(c, cudaFreeHost(b.p));
+            b.p = nullptr;
+            b.bytes = 0;
+        }
+        CU_TRY(c, cudaMallocHost(&b.p, static_cast<size_t>(bytes)));
+        b.bytes = static_cast<size_t>(bytes);
+    }
+    *out_host = b.p;
     return CLIPDB_OK;
 }
 
@@ -1397,10 +1560,6 @@ int clipdb_search(clipdb_ctx *c, const float *queries, int32_t nq, int32_t k, in
     CU_TRY(c, cudaMemcpyAsync(c->d_query.p, c->pinned.p, qbytes, cudaMemcpyHostToDevice, c->stream));
     // the pinned buffer is reused for results: the H2D above is ordered before them on the stream
     const float *dq = static_cast<const float *>(c->d_query.p);
-    int64_t *o_ids = c->r_ids;
-    float *o_dist = c->r_dist;
-    int32_t *o_n = c->r_n;
-    int64_t *o_nan = c->r_nan;
     return run_and_fetch(c, dq, nq, k, metric, use_mask, out_rowids, out_dist, out_n, out_nan);
 }
 
@@ -1455,6 +1614,7 @@ int clipdb_enable_batch(clipdb_ctx *c, int32_t enable) {
     if (!enable) {
         CU_TRY(c, cudaStreamSynchronize(c->stream));
         c->batch_enabled = false;
+        c->bf16_built = c->bf16_cap_rows = 0;
         Buffer *bufs[] = {&c->bf16_rows, &c->bq_scores, &c->bq_cand, &c->bq_cand_u, &c->bq_surv};
         for (Buffer *b : bufs) free_buffer(*b);
         return CLIPDB_OK;
@@ -1648,6 +1808,9 @@ int clipdb_exchange_init(clipdb_ctx *c, int32_t world, int32_t rank, void *out_i
     c->xchg_batch_epoch = 0;
     c->xchg_peer[rank] = c->xchg_inbox;
     c->xchg_connected = world == 1;
+    CU_TRY(c, cudaHostAlloc(reinterpret_cast<void **>(&c->xchg_abort_host), sizeof(int), cudaHostAllocMapped));
+    *c->xchg_abort_host = 0;
+    CU_TRY(c, cudaHostGetDevicePointer(reinterpret_cast<void **>(&c->xchg_abort_dev), c->xchg_abort_host, 0));
     if (out_ipc_handle) {
         static_assert(sizeof(cudaIpcMemHandle_t) == CLIPDB_IPC_HANDLE_BYTES, "IPC handle size");
         cudaIpcMemHandle_t h;
@@ -1700,6 +1863,60 @@ int clipdb_exchange_connect_pointers(clipdb_ctx *c, void *const *inboxes, const 
     return CLIPDB_OK;
 }
 
+// The epoch after `cur`: never 0 ("slot never written"), and consecutive epochs always differ in parity (the
+// two inbox banks alternate), so 0xFFFFFFFF is followed by 2, not by 1.
+static uint32_t next_epoch(uint32_t cur) {
+    const uint32_t e = cur + 1;
+    return e == 0 ? 2 : e;
+}
+
+static void fill_exchange_args(const clipdb_ctx *c, ExchangeArgs &xa, int32_t k, uint32_t epoch, bool with_stats) {
+    for (int r = 0; r < c->xchg_world; r++) xa.inbox[r] = c->xchg_peer[r];
+    xa.world = c->xchg_world;
+    xa.rank = c->xchg_rank;
+    xa.k = k;
+    xa.epoch = epoch;
+    xa.timeout_ns = static_cast<unsigned long long>(c->xchg_timeout_ms) * 1000000ull;
+    xa.abort_flag = c->xchg_abort_dev;
+    xa.stats = with_stats && c->xchg_stats_on ? static_cast<unsigned long long *>(c->xchg_stats.p) : nullptr;
+}
+
+int clipdb_exchange_abort(clipdb_ctx *c, int32_t abort) {
+    // no lock: meant to be called while another thread sits in a stream synchronisation
+    if (!c || !c->xchg_abort_host) return CLIPDB_ERR_INVALID;
+    *static_cast<volatile int *>(c->xchg_abort_host) = abort != 0;
+    return CLIPDB_OK;
+}
+
+int clipdb_exchange_set_epoch(clipdb_ctx *c, uint32_t single_epoch, uint32_t batch_epoch) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->xchg_inbox) return fail(c, CLIPDB_ERR_STATE, "exchange_set_epoch: call exchange_init first");
+    DeviceGuard g(c->device);
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    c->xchg_epoch = single_epoch;
+    c->xchg_batch_epoch = batch_epoch;
+    return CLIPDB_OK;
+}
+
+int clipdb_exchange_stats(clipdb_ctx *c, int32_t enable, int32_t reset, double *out_ns, int64_t *out_launches) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    const bool fresh = c->xchg_stats.p == nullptr;
+    RC_TRY(ensure_device(c, c->xchg_stats, XCHG_STATS_WORDS * sizeof(unsigned long long)));
+    if (fresh) CU_TRY(c, cudaMemsetAsync(c->xchg_stats.p, 0, XCHG_STATS_WORDS * sizeof(unsigned long long), c->stream));
+    unsigned long long h[XCHG_STATS_WORDS] = {};
+    CU_TRY(c, cudaMemcpyAsync(h, c->xchg_stats.p, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    if (reset) CU_TRY(c, cudaMemsetAsync(c->xchg_stats.p, 0, sizeof h, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (out_ns)
+        for (int i = 0; i < XCHG_STATS_WORDS - 1; i++) out_ns[i] = static_cast<double>(h[i]);
+    if (out_launches) *out_launches = static_cast<int64_t>(h[XCHG_STATS_WORDS - 1]);
+    c->xchg_stats_on = enable != 0;
+    return CLIPDB_OK;
+}
+
 int clipdb_search_sharded_device(clipdb_ctx *c, const float *d_query, int32_t k, int32_t metric, int32_t use_mask,
                                  int64_t *d_out_rowids, float *d_out_dist, int32_t *d_out_n, int64_t *d_out_nan) {
     if (!c) return CLIPDB_ERR_INVALID;
@@ -1712,14 +1929,8 @@ int clipdb_search_sharded_device(clipdb_ctx *c, const float *d_query, int32_t k,
     if (use_mask && !c->mask) return fail(c, CLIPDB_ERR_STATE, "search: use_mask set but no mask installed");
     DeviceGuard g(c->device);
     ExchangeArgs xa{};
-    for (int r = 0; r < c->xchg_world; r++) xa.inbox[r] = c->xchg_peer[r];
-    xa.world = c->xchg_world;
-    xa.rank = c->xchg_rank;
-    xa.k = k;
-    uint32_t epoch = c->xchg_epoch + 1;
-    if (epoch == 0) epoch = 1;   // 0 means "never written"
-    xa.epoch = epoch;
-    xa.timeout_ns = static_cast<unsigned long long>(c->xchg_timeout_ms) * 1000000ull;
+    const uint32_t epoch = next_epoch(c->xchg_epoch);
+    fill_exchange_args(c, xa, k, epoch, true);
     if (xa.world == 1) return search_one(c, d_query, k, metric, use_mask != 0, d_out_rowids, d_out_dist, d_out_n, d_out_nan);
     RC_TRY(search_one(c, d_query, k, metric, use_mask != 0, d_out_rowids, d_out_dist, d_out_n, d_out_nan, &xa));
     c->xchg_epoch = epoch;   // only a launch that was enqueued consumes an epoch: the ranks stay in step
@@ -1737,14 +1948,8 @@ int clipdb_search_batch_sharded_device(clipdb_ctx *c, const float *d_queries, in
     if (c->xchg_world == 1)
         return batch_search_device_locked(c, d_queries, nq, k, use_mask, d_out_rowids, d_out_dist, d_out_n, d_out_nan, d_flags);
     ExchangeArgs xa{};
-    for (int r = 0; r < c->xchg_world; r++) xa.inbox[r] = c->xchg_peer[r];
-    xa.world = c->xchg_world;
-    xa.rank = c->xchg_rank;
-    xa.k = k;
-    uint32_t epoch = c->xchg_batch_epoch + 1;
-    if (epoch == 0) epoch = 1;
-    xa.epoch = epoch;
-    xa.timeout_ns = static_cast<unsigned long long>(c->xchg_timeout_ms) * 1000000ull;
+    const uint32_t epoch = next_epoch(c->xchg_batch_epoch);
+    fill_exchange_args(c, xa, k, epoch, false);
     RC_TRY(batch_search_device_locked(c, d_queries, nq, k, use_mask, d_out_rowids, d_out_dist, d_out_n, d_out_nan,
                                       d_flags, &xa));
     c->xchg_batch_epoch = epoch;

@@ -84,6 +84,7 @@ struct ScanSync {
     unsigned int tile_counter;        // dynamic tile scheduler
     unsigned int done_counter;        // CTAs finished
     unsigned long long nan_rows;      // admitted rows whose distance was NaN
+    unsigned long long t_start;       // %globaltimer of the first CTA to start (exchange statistics only)
 };
 
 // ---- fused shard exchange (multi-GPU) --------------------------------------------
@@ -126,7 +127,11 @@ struct ExchangeArgs {
     int k;                                 // requested (global) k
     uint32_t epoch;                        // same on every rank for the same query / batch, never 0
     unsigned long long timeout_ns;
+    const volatile int *abort_flag;        // nullable; mapped host memory: != 0 = stop waiting for the peers now
+    unsigned long long *stats;             // nullable; [0..4] summed segment durations (ns), [5] launches
 };
+
+constexpr int XCHG_STATS_WORDS = 6;
 
 __host__ __device__ inline size_t exchange_inbox_slots(int world) {
     return static_cast<size_t>(2) * world * (1 + XCHG_BATCH);
@@ -154,7 +159,8 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 template <int L>
 __device__ __forceinline__ int exchange_merge_decode(uint64_t *scratch, const DecodeArgs &dec, const ExchangeArgs &xa,
                                                      int slot0, int slot_stride, long long nan_local,
-                                                     int flags_local, int32_t *out_flags, int tid, int nthreads) {
+                                                     int flags_local, int32_t *out_flags, int tid, int nthreads,
+                                                     unsigned long long *stamps = nullptr) {
     const int k = xa.k, G = xa.world;
     int mine = 0;
     for (int base = 0; base < k; base += nthreads) {
@@ -182,23 +188,27 @@ __device__ __forceinline__ int exchange_merge_decode(uint64_t *scratch, const De
     __threadfence_system();
     __syncthreads();
     if (tid < G) st_release_sys(&(xa.inbox[tid] + slot0 + xa.rank * slot_stride)->epoch, xa.epoch);
+    if (stamps && tid == 0) stamps[0] = global_timer_ns();   // published
     // 3. wait for every shard's record in the own inbox
     const ExchangeSlot *own = xa.inbox[xa.rank] + slot0;
     bool late = false;
     if (tid < G) {
         const unsigned long long t0 = global_timer_ns();
+        unsigned spins = 0;
         while (ld_acquire_sys(&own[tid * slot_stride].epoch) != xa.epoch) {
-            if (global_timer_ns() - t0 > xa.timeout_ns) {
+            // the abort flag lives in host memory (a PCIe round trip): looked at every 32nd spin only
+            if (global_timer_ns() - t0 > xa.timeout_ns || ((++spins & 31u) == 0 && xa.abort_flag && *xa.abort_flag)) {
                 late = true;
                 break;
             }
             __nanosleep(200);
         }
     }
-    if (__syncthreads_count(late)) {   // a peer never delivered: reported by the host as an error
+    if (__syncthreads_count(late)) {   // a peer never delivered (or the host gave up): an error code, not a hang
         if (tid == 0) *dec.out_n = -1;
         return -1;
     }
+    if (stamps && tid == 0) stamps[1] = global_timer_ns();   // every record arrived
     // a peer that answered a different request (another k) would make the merge meaningless
     if (__syncthreads_count(tid < G && (__ldcg(&own[(tid < G ? tid : 0) * slot_stride].count) >> 16) != k)) {
         if (tid == 0) *dec.out_n = -2;
@@ -247,16 +257,32 @@ template <int L>
 __device__ __forceinline__ void merge_decode_reset(const uint64_t *lists, int n_lists, uint64_t *scratch,
                                                    const DecodeArgs &dec, const ExchangeArgs &xa, ScanSync *sync,
                                                    int tid, int nthreads) {
+    __shared__ unsigned long long s_t[4];   // exchange statistics: scanned | merged | published | received
+    const bool timing = xa.world > 1 && xa.stats != nullptr;
+    if (timing && tid == 0) s_t[0] = global_timer_ns();
     for (int i = tid; i < n_lists * L; i += nthreads) scratch[i] = __ldcg(lists + i);
     __syncthreads();
     merge_sorted_lists_tournament<L>(scratch, n_lists, tid, nthreads);
     if (xa.world > 1) {
         __shared__ long long s_nan;
-        if (tid == 0) s_nan = static_cast<long long>(atomicExch(&sync->nan_rows, 0ull));
-        __syncthreads();
-        exchange_merge_decode<L>(scratch, dec, xa, static_cast<int>(xa.epoch & 1u) * xa.world, 1, s_nan, 0, nullptr,
-                                 tid, nthreads);
         if (tid == 0) {
+            s_nan = static_cast<long long>(atomicExch(&sync->nan_rows, 0ull));
+            if (timing) s_t[1] = global_timer_ns();
+        }
+        __syncthreads();
+        const int rc = exchange_merge_decode<L>(scratch, dec, xa, static_cast<int>(xa.epoch & 1u) * xa.world, 1, s_nan,
+                                                0, nullptr, tid, nthreads, timing ? s_t + 2 : nullptr);
+        if (tid == 0) {
+            if (timing && rc >= 0) {   // one writer per launch, launches of a context are serialised on its stream
+                const unsigned long long t_end = global_timer_ns(), t0 = sync->t_start;
+                xa.stats[0] += s_t[0] - (t0 ? t0 : s_t[0]);
+                xa.stats[1] += s_t[1] - s_t[0];
+                xa.stats[2] += s_t[2] - s_t[1];
+                xa.stats[3] += s_t[3] - s_t[2];
+                xa.stats[4] += t_end - s_t[3];
+                xa.stats[5] += 1;
+            }
+            sync->t_start = 0;
             sync->tile_counter = 0;
             sync->done_counter = 0;
         }
@@ -273,6 +299,7 @@ __device__ __forceinline__ void merge_decode_reset(const uint64_t *lists, int n_
         *dec.out_n = found;
         const unsigned long long nan = atomicExch(&sync->nan_rows, 0ull);
         if (dec.out_nan) *dec.out_nan = static_cast<int64_t>(nan);
+        sync->t_start = 0;
         sync->tile_counter = 0;
         sync->done_counter = 0;
     }

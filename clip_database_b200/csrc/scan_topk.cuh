@@ -65,8 +65,18 @@ constexpr int SCAN_ASSIGN_DYNAMIC = 2;      // chunks of tiles claimed with atom
 constexpr int LDG_WARPS = 8;
 constexpr int LDG_THREADS = LDG_WARPS * 32;
 
+// A store may be TIERED (clipdb_reserve_rows): rows [0, split) in HBM at `rows`, rows [split, n) in pinned,
+// device-mapped host memory.  `rows_hi` is biased so that rows_hi + pos * ld addresses row pos >= split;
+// split is a multiple of 128, so no tile of any kernel straddles it.  All-HBM stores have split = LLONG_MAX.
+__device__ __forceinline__ const float *row_address(const float *rows, const float *rows_hi, long long split,
+                                                    long long pos, int ld) {
+    return (pos < split ? rows : rows_hi) + pos * ld;
+}
+
 struct ScanArgs {
     const float *rows;             // [n][ld] float32, scan order
+    const float *rows_hi;          // tiered store: biased base of the host-resident rows (see row_address)
+    long long split;               // first position that lives in host memory (LLONG_MAX: none)
     const float *query;            // [dim]
     const uint32_t *mask;          // nullable admission bitset
     uint64_t *cand;                // [gridDim.x][cand_stride], each ascending
@@ -246,6 +256,8 @@ __global__ void __launch_bounds__(CFG::THREADS, 1) scan_tma_kernel(const ScanArg
             mbar_init(&empty_bar[s], CFG::GROUP_WARPS);
         }
         mbar_fence_init();
+        // exchange statistics: the first CTA to get here stamps the launch's start
+        if (a.xchg.world > 1 && a.xchg.stats) atomicCAS(&a.sync->t_start, 0ull, global_timer_ns());
     }
     __syncthreads();
 
@@ -267,7 +279,7 @@ __global__ void __launch_bounds__(CFG::THREADS, 1) scan_tma_kernel(const ScanArg
                     const long long left = a.n - row0;
                     const uint32_t bytes = static_cast<uint32_t>((left < R ? left : R) * SCAN_ROW_BYTES);
                     mbar_arrive_expect_tx(&full_bar[s], bytes);
-                    const float *src = a.rows + row0 * SCAN_DIM;
+                    const float *src = row_address(a.rows, a.rows_hi, a.split, row0, SCAN_DIM);
                     if (a.evict_first)
                         bulk_copy_g2s_hint(ring + s * CFG::STAGE_BYTES, src, bytes, &full_bar[s], policy);
                     else
@@ -420,7 +432,7 @@ __global__ void __launch_bounds__(LDG_THREADS) scan_ldg_kernel(const ScanArgs a)
             if (WRITE_ALL && lane == 0) a.all_keys[pos] = KEY_EMPTY;
             continue;
         }
-        const float4 *src = reinterpret_cast<const float4 *>(a.rows + pos * ld);
+        const float4 *src = reinterpret_cast<const float4 *>(row_address(a.rows, a.rows_hi, a.split, pos, ld));
         RowSums sums;
         sums.clear();
         if (DIM_T > 0) {

@@ -163,7 +163,47 @@ class GpuIndex:
                                              n, dim))
         self._keepalive = []
 
+    def reserve(self, capacity: int, dim: int, explicit_rowids: bool = True, placement: str = "device",
+                device_rows: int = 0) -> None:
+        """Empty store with room for ``capacity`` rows, filled by ``append`` chunk by chunk (a streaming
+        loader never holds more than a chunk on the host).  ``placement="host"`` keeps the float32 rows
+        in pinned, device-mapped host memory — all of them, or those from position ``device_rows`` on
+        (rounded down to a multiple of 128; the rows before stay in HBM): combined with ``enable_batch``
+        and ``set_option("batch_min_nq", 1)`` that is a bf16-primary store (see clipdb_reserve_rows)."""
+        places = {"device": _lib.PLACE_DEVICE, "host": _lib.PLACE_HOST}
+        if placement not in places:
+            raise ValueError(f"placement must be one of {sorted(places)}")
+        if placement == "host":
+            self.set_option("host_tier_from_row", int(device_rows))
+        self._check(self._L.clipdb_reserve_rows(self._ctx, int(capacity), int(dim), int(bool(explicit_rowids)),
+                                                places[placement]))
+        self._keepalive = []
+        self.batch_enabled = False
+
+    def stage_buffer(self, rows: int, dim: int) -> np.ndarray:
+        """A float32 ``[rows, dim]`` numpy view of context-owned PINNED host memory: fill it, then
+        ``append(view[:m], ...)`` moves the rows with one DMA instead of a pageable-memory copy.  Valid
+        until the next call that asks for a larger buffer, or ``close``."""
+        ptr = ctypes.c_void_p()
+        nbytes = int(rows) * int(dim) * 4
+        self._check(self._L.clipdb_stage_buffer(self._ctx, nbytes, ctypes.byref(ptr)))
+        buf = (ctypes.c_float * (int(rows) * int(dim))).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=np.float32).reshape(int(rows), int(dim))
+
     def append(self, rows, rowids=None) -> None:
+        """Append rows (numpy, or a torch tensor on any device) in scan order."""
+        if _is_torch(rows):
+            rows_t = rows.detach().contiguous()
+            if rows_t.dtype.is_floating_point is False or rows_t.element_size() != 4 or rows_t.dim() != 2:
+                raise ValueError("rows must be a float32 [m, dim] tensor")
+            ids_t = None
+            if rowids is not None:
+                import torch
+                ids_t = torch.as_tensor(rowids, dtype=torch.int64).contiguous()
+            self._check(self._L.clipdb_append_rows(self._ctx, ctypes.c_void_p(rows_t.data_ptr()),
+                                                   ctypes.c_void_p(ids_t.data_ptr() if ids_t is not None else 0),
+                                                   rows_t.shape[0]))
+            return
         rows = np.ascontiguousarray(rows, dtype=np.float32)
         if rows.ndim != 2 or (self.dim and rows.shape[1] != self.dim):
             raise ValueError("rows must be [m, dim] with the store's dim")
@@ -486,6 +526,32 @@ class GpuIndex:
         ptrs = (ctypes.c_void_p * len(inboxes))(*[ctypes.c_void_p(int(p)) for p in inboxes])
         devs = (ctypes.c_int32 * len(inboxes))(*[int(d) for d in devices]) if devices is not None else None
         self._check(self._L.clipdb_exchange_connect_pointers(self._ctx, ptrs, devs))
+
+    def exchange_abort(self, abort: bool = True) -> None:
+        """Make every exchange of this context that is waiting for its peers give up now (out_n = -1)
+        instead of spinning until ``xchg_timeout_ms``; ``False`` re-arms.  Takes no lock: callable from
+        a watchdog thread while another thread waits on the stream."""
+        rc = self._L.clipdb_exchange_abort(self._ctx, int(bool(abort)))
+        if rc != _lib.OK:
+            raise _lib.ClipdbError(rc, "exchange_abort: exchange not initialised")
+
+    def exchange_set_epoch(self, single_epoch: int, batch_epoch: int = 0) -> None:
+        """Next single-query / batched exchange uses sequence number ``single_epoch + 1`` /
+        ``batch_epoch + 1``.  Every rank must be idle and pass the same values (resynchronisation
+        after a rank failed to enqueue a search)."""
+        self._check(self._L.clipdb_exchange_set_epoch(self._ctx, int(single_epoch) & 0xFFFFFFFF,
+                                                      int(batch_epoch) & 0xFFFFFFFF))
+
+    def exchange_stats(self, enable: bool = True, reset: bool = True):
+        """({"scan", "local_merge", "publish", "wait_peers", "final_merge"} -> mean microseconds per
+        launch, launches) of the fused sharded search since the last reset; ``enable`` switches the
+        in-kernel %globaltimer stamping on or off from the next launch."""
+        ns = (ctypes.c_double * 5)()
+        n = ctypes.c_int64(0)
+        self._check(self._L.clipdb_exchange_stats(self._ctx, int(bool(enable)), int(bool(reset)), ns, ctypes.byref(n)))
+        names = ("scan", "local_merge", "publish", "wait_peers", "final_merge")
+        m = max(int(n.value), 1)
+        return {k: ns[i] / m / 1e3 for i, k in enumerate(names)}, int(n.value)
 
     def search_sharded_device(self, d_query, k: int, out_rowids, out_dist, out_n, out_nan=None,
                               metric="cosine", use_mask: bool = False) -> None:

@@ -53,6 +53,10 @@ typedef struct clipdb_ctx clipdb_ctx;
 /* ABI version of this header (bumped on any signature change). */
 int clipdb_abi_version(void);
 
+/* Hex SHA-256 of the sources (csrc/ and this header) the library was compiled from, so a binding can
+ * refuse to run kernels older than the code next to it (the built library is not under version control). */
+const char *clipdb_source_hash(void);
+
 /* ---- context -------------------------------------------------------------
  * Replaces: sqlite3.connect + sqlite_vec.load(conn) per search (idb:1475-1484);
  * here the store is loaded once and stays resident in HBM. */
@@ -96,6 +100,27 @@ int clipdb_append_rows(clipdb_ctx *ctx, const float *rows, const int64_t *rowids
 int clipdb_update_row(clipdb_ctx *ctx, int64_t position, const float *row);
 int clipdb_attach_rows(clipdb_ctx *ctx, const float *d_rows, const int64_t *d_rowids,
                        int64_t n, int32_t dim, int64_t rowid_base);
+
+/* clipdb_reserve_rows creates an EMPTY owned store with room for `capacity` rows, to be filled with
+ * clipdb_append_rows chunk by chunk (a loader that streams a large SQLite file never holds more than one
+ * chunk on the host; appends beyond the capacity still grow it).  `explicit_rowids` != 0: every append
+ * must pass rowids.  `placement` says where the float32 rows live:
+ *   CLIPDB_PLACE_DEVICE  HBM (the default of clipdb_load_rows): 4 * dim bytes per row resident.
+ *   CLIPDB_PLACE_HOST    pinned, device-mapped HOST memory.  Meant to be combined with
+ *                        clipdb_enable_batch + option "batch_min_nq" = 1 (a "bf16-primary" store): the
+ *                        bf16 copy (2 * dim bytes per row) is the only thing resident in HBM and every
+ *                        search pre-selects on it with the tensor-core path, while the exact float32
+ *                        re-rank reads its few hundred candidate rows from host memory over PCIe
+ *                        (zero-copy).  Results are identical to the all-HBM store; a 50M-row shard
+ *                        (230 GB of float32) fits one B200 this way (115 GB of bf16).  The exact scan
+ *                        still works on such a store but streams the rows over PCIe.
+ * clipdb_stage_buffer returns a context-owned pinned host buffer of at least `bytes` bytes (valid until
+ * the next call asking for more, or destroy): rows written there reach HBM by one DMA per
+ * clipdb_append_rows call instead of a pageable-memory copy. */
+#define CLIPDB_PLACE_DEVICE 0
+#define CLIPDB_PLACE_HOST   1
+int clipdb_reserve_rows(clipdb_ctx *ctx, int64_t capacity, int32_t dim, int32_t explicit_rowids, int32_t placement);
+int clipdb_stage_buffer(clipdb_ctx *ctx, int64_t bytes, void **out_host);
 int64_t clipdb_num_rows(const clipdb_ctx *ctx);
 int32_t clipdb_dim(const clipdb_ctx *ctx);
 
@@ -292,6 +317,28 @@ int clipdb_search_sharded_device(clipdb_ctx *ctx, const float *d_query, int32_t 
 int clipdb_search_batch_sharded_device(clipdb_ctx *ctx, const float *d_queries, int32_t nq, int32_t k, int32_t use_mask,
                                        int64_t *d_out_rowids, float *d_out_dist, int32_t *d_out_n,
                                        int64_t *d_out_nan, int32_t *d_flags);
+
+/* Host-side control of the in-kernel exchange.
+ *   clipdb_exchange_abort      abort != 0: every exchange of this context that is (or will be) waiting for
+ *                              its peers gives up at once with *d_out_n = -1 instead of spinning until
+ *                              "xchg_timeout_ms" (a watchdog thread can call this while another thread
+ *                              waits on the stream: it takes no lock); abort == 0 re-arms.
+ *   clipdb_exchange_set_epoch  the sequence numbers the NEXT single-query / batched exchange will use are
+ *                              single_epoch + 1 / batch_epoch + 1.  All ranks must be idle and pass the same
+ *                              values, larger than any epoch used since clipdb_exchange_init: this is how
+ *                              ranks that fell out of step (one of them failed to enqueue a search) are
+ *                              brought back in step without re-creating the inboxes.
+ *   clipdb_exchange_stats      per-launch timeline of clipdb_search_sharded_device, summed on the device
+ *                              from %globaltimer stamps taken by the scan kernel's last CTA since the last
+ *                              reset: out_ns[0] first CTA started -> last CTA finished its rows (scan),
+ *                              [1] -> per-SM lists merged, [2] -> record stored into every peer's inbox and
+ *                              published, [3] -> every peer's record arrived (exchange wait: includes the
+ *                              time the other GPUs were still scanning), [4] -> merged and decoded.
+ *                              `enable` != 0 turns the stamping on (off by default), `reset` != 0 zeroes the
+ *                              sums after reading.  Synchronises the stream. */
+int clipdb_exchange_abort(clipdb_ctx *ctx, int32_t abort);
+int clipdb_exchange_set_epoch(clipdb_ctx *ctx, uint32_t single_epoch, uint32_t batch_epoch);
+int clipdb_exchange_stats(clipdb_ctx *ctx, int32_t enable, int32_t reset, double *out_ns, int64_t *out_launches);
 
 /* ---- measurement ------------------------------------------------------------
  * With profiling enabled every scan kernel (the dominant, HBM-bound launch) is
