@@ -34,4 +34,4 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
 def test_reference_arm_under_torchrun_only_rank0_prints():
     assert run("--gpus", "4", env={"RANK": "2", "WORLD_SIZE": "4", "LOCAL_RANK": "2"}).strip() == ""
     d = json.loads(run("--gpus", "4", env={"RANK": "0", "WORLD_SIZE": "4", "LOCAL_RANK": "0"}))
-    assert d["n_gpus"] == 4 and d["config"]["rows_per_gpu"] == 12_500_000
+    assert d["n_gpus"] == 4 and d["config"]["rows_per_gpu"] == 25_000_000 and d["config"]["rows_total"] == 100_000_000
