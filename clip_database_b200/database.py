@@ -7,15 +7,15 @@ loaded once from the SQLite database into resident HBM and every search is one
 blend + scan + top-k on the GPU instead of a per-row SQL function call.
 
 The SigLIP model is out of scope (no weights offline): ``search()`` takes text /
-image-path queries only when an ``embedder`` is supplied; ``search_embedding()``
-takes the float32[1152] vectors directly and is what ``search()`` calls after
-embedding.  There is no CPU search path.
+image-path queries when an ``embedder`` is supplied, and ``vector:<file.npy>`` queries
+(ready-made embeddings) always; ``search_embedding()`` takes the float32[1152] vectors
+directly and is what ``search()`` calls after embedding.  There is no CPU search path.
 """
 from __future__ import annotations
 
 import os
 import sqlite3
-from typing import Callable, Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -33,6 +33,33 @@ class Embedder:
 
     def image(self, path: str) -> Optional[np.ndarray]:       # image_database.py:443-463
         raise NotImplementedError
+
+
+VECTOR_PREFIX = "vector:"
+
+
+def load_vector(path: str, dim: int) -> np.ndarray:
+    """A ready-made query embedding from a ``.npy`` file (``vector:<path>`` in any query position of
+    ``search()`` and of the interactive session): float32[dim], e.g. saved from the reference's
+    ``_get_text_embedding`` / ``_get_image_embedding`` or from any SigLIP 2 SO400M pipeline."""
+    v = np.asarray(np.load(path, allow_pickle=False), dtype=np.float32).reshape(-1)
+    if v.shape[0] != dim:
+        raise ValueError(f"{path}: {v.shape[0]} values, expected {dim}")
+    return v
+
+
+def load_embedder(spec: str) -> Embedder:
+    """``module:Class`` or ``module:factory`` -> an object with ``text(str)`` and ``image(path)`` methods
+    returning float32[1152] (or None).  The class / factory is called without arguments."""
+    import importlib
+    module, _, name = spec.partition(":")
+    if not module or not name:
+        raise ValueError("embedder must be given as module:Class")
+    obj = getattr(importlib.import_module(module), name)()
+    for method in ("text", "image"):
+        if not callable(getattr(obj, method, None)):
+            raise TypeError(f"{spec}: the embedder needs a {method}() method")
+    return obj
 
 
 def like_prefix_mask(file_paths: Sequence[str], folders: Sequence[str],
@@ -127,7 +154,12 @@ class ImageDatabase:
         self._paths: List[str] = []
         self._lowered: Optional[List[bytes]] = None
         self._image_ids = np.zeros(0, dtype=np.int64)
-        self._rowid_to_pos: Dict[int, int] = {}
+        self._rowids = np.zeros(0, dtype=np.int64)
+        self._mtimes = np.zeros(0, dtype=np.float64)
+        self._alive: Optional[np.ndarray] = None      # False = the row's mapping is gone (refresh): masked out
+        self._watch = None
+        self._data_version = -1
+        self.load_seconds = 0.0
         self._binary_count = 0
         self._vec0_count = 0
         self._mask_key: Optional[Tuple[str, ...]] = None
@@ -138,82 +170,191 @@ class ImageDatabase:
         if self.verbose:
             print(*a, flush=True)
 
+    def _pos_of(self, rowids) -> np.ndarray:
+        """Scan positions of resident rowids (``self._rowids`` is ascending: the scan order)."""
+        return np.searchsorted(self._rowids, np.asarray(rowids, dtype=np.int64))
+
+    def _stream_into(self, conn, append, lo=None, hi=None, expect_dim=None) -> loader.HostStore:
+        """Read rowids in (lo, hi] chunk by chunk and hand every chunk to ``append(rows, rowids)`` through a
+        pinned staging buffer: host memory stays O(chunk) whatever the size of the database."""
+        stage = {"buf": None}
+        lead = self.index.shards[0] if hasattr(self.index, "shards") else self.index
+
+        def sink(chunk: loader.StoreChunk) -> None:
+            m, dim = chunk.rows.shape
+            if stage["buf"] is None or stage["buf"].shape[1] != dim:
+                stage["buf"] = lead.stage_buffer(loader.CHUNK_ROWS, dim)
+            for at in range(0, m, loader.CHUNK_ROWS):
+                part = chunk.rows[at:at + loader.CHUNK_ROWS]
+                buf = stage["buf"][:part.shape[0]]
+                buf[:] = part
+                append(buf, chunk.rowids[at:at + loader.CHUNK_ROWS])    # copies before it returns
+        return loader.stream_store(self.db_path, sink, expect_dim=expect_dim, min_rowid=lo, max_rowid=hi, conn=conn)
+
     def reload(self) -> None:
-        """(Re)read the whole database into HBM.  With several GPUs every shard's rowid range is read
-        and uploaded on its own, so the float32 matrix never has to fit host memory at once."""
+        """(Re)read the whole database into HBM, streamed: every chunk of rows goes from SQLite through a pinned
+        staging buffer straight into the resident store.  With several GPUs the shard boundaries are computed
+        once and every range is read through the same connection inside ONE read transaction, so a scan writing
+        concurrently cannot make two shards disagree about where one ends and the next begins."""
+        import time
+        t0 = time.perf_counter()
         multi = hasattr(self.index, "shards")
         world = self.index.world if multi else 1
-        sharded_load = multi
-        if multi:
-            n_joined = loader.shard_rowid_range(self.db_path, 0, world)[2]
-            if 0 < n_joined < world:
-                raise ValueError(f"{n_joined} rows cannot be sharded over {world} GPUs")
-            sharded_load = n_joined > 0              # a binary-only database has no float rows to shard
-        parts = []
-        for rank in range(world if sharded_load else 1):
-            if sharded_load:
-                lo, hi, _ = loader.shard_rowid_range(self.db_path, rank, world)
-                host = loader.read_store(self.db_path, min_rowid=lo, max_rowid=hi)
-                self.index.load_shard(rank, host.rows, host.rowids)
-                host.rows = None                     # uploaded: free the host copy before the next range
+        with loader.snapshot(self.db_path) as conn:
+            self._data_version = loader.data_version(self._watch_conn())
+            mapped = int(conn.execute("SELECT COUNT(*) FROM image_embeddings").fetchone()[0])
+            parts = []
+            if multi and mapped > 0:
+                ranges, n_mapped = loader.plan_shards(conn, world)
+                if 0 < n_mapped < world:
+                    raise ValueError(f"{n_mapped} rows cannot be sharded over {world} GPUs")
+                for rank, (lo, hi) in enumerate(ranges):
+                    shard = self.index.shards[rank]
+                    state = {"reserved": False}
+
+                    def append(rows, rowids, shard=shard, state=state):
+                        if not state["reserved"]:
+                            shard.reserve(max(n_mapped // world + 1, rows.shape[0]), rows.shape[1], explicit_rowids=True)
+                            state["reserved"] = True
+                        shard.append(rows, rowids)
+                        shard.synchronize()
+                    host = self._stream_into(conn, append, lo, hi)
+                    if host.rowids.shape[0] < 1:
+                        raise ValueError("every shard needs at least one row (too many vec0 rows are missing)")
+                    self.index.note_shard_loaded(rank, host.rowids.shape[0])
+                    parts.append(host)
+                self.index.finish_load()
             else:
-                host = loader.read_store(self.db_path)
-            parts.append(host)
-        if sharded_load:
-            self.index.finish_load()
+                single = self.index.shards[0] if multi else self.index
+                state = {"reserved": False}
+
+                def append(rows, rowids):
+                    if not state["reserved"]:
+                        single.reserve(max(mapped, rows.shape[0]), rows.shape[1], explicit_rowids=True)
+                        state["reserved"] = True
+                    single.append(rows, rowids)
+                    single.synchronize()
+                parts.append(self._stream_into(conn, append))
+            self._vec0_count = loader.count_vec0(conn)
         first = parts[0]
         self._binary_count = first.binary_count
-        self._vec0_count = sum(p.vec0_count for p in parts)
         self._paths = [fp for p in parts for fp in p.file_paths]
         self._lowered = None
         self._image_ids = np.concatenate([p.image_ids for p in parts])
+        self._mtimes = np.concatenate([p.mtimes for p in parts])
         self._rowids = np.concatenate([p.rowids for p in parts])
-        self._rowid_to_pos = {int(r): i for i, r in enumerate(self._rowids)}
+        self._alive = None
         self._mask_key = None
         self._codes = None
         self._code_mask_key = None
-        if not multi and first.rows.shape[0]:
-            self.index.load(first.rows, first.rowids)
-        if self.batch_store and self._rowids.shape[0] and self.index.dim == schema.EMBEDDING_DIM:
+        n = self._rowids.shape[0]
+        if self.batch_store and n and self.index.dim == schema.EMBEDDING_DIM:
             self.index.enable_batch()
             if not multi:
                 self.index.set_option("batch_min_nq", 1)
-        self._log(f"loaded {self._rowids.shape[0]} rows ({first.source}); "
+        self.load_seconds = time.perf_counter() - t0
+        self._log(f"loaded {n} rows ({first.source}) in {self.load_seconds:.2f} s "
+                  f"({n / max(self.load_seconds, 1e-9):.0f} rows/s); "
                   f"{sum(p.dropped for p in parts)} vec0 rows without a mapping were skipped")
 
-    def refresh(self) -> int:
-        """Append rows the scanner added since the last load (new vec0 rowids are always
-        larger: INSERT INTO vec0 auto-assigns, image_database.py:1171-1175).  Returns
-        the number of rows appended.  In-place UPDATEs of old rows need ``reload()``."""
-        last = int(self._rowids[-1]) if len(self._paths) else None
-        host = loader.read_store(self.db_path, expect_dim=self.index.dim or None, min_rowid=last)
-        if host.binary_count != self._binary_count:
-            self._codes = None            # sign codes were added: the fallback store is re-read on next use
-            self._code_mask_key = None
-        self._binary_count = host.binary_count
-        self._vec0_count = self._vec0_count + host.vec0_count if last is not None else host.vec0_count
-        m = host.rows.shape[0]
-        if m == 0:
+    def _watch_conn(self):
+        """A connection kept open only to read ``PRAGMA data_version``: it changes iff someone else committed."""
+        if self._watch is None:
+            self._watch = loader.connect(self.db_path)
+        return self._watch
+
+    def refresh(self, force: bool = False) -> int:
+        """Bring the resident store in line with what a fresh connection would see now — what the reference does
+        implicitly by reopening SQLite for every search (image_database.py:1475).  Free when nothing was
+        committed since the last look (``PRAGMA data_version``).  Otherwise one pass over the integer mapping
+        (``image_embeddings JOIN images``: no blobs) finds
+          * rows the scanner appended (new vec0 rowids are always larger: ``INSERT INTO vec0`` auto-assigns,
+            :1171-1175)                                           -> streamed in and appended;
+          * rows whose mapping disappeared — a modified file is re-keyed by ``INSERT OR REPLACE INTO images``
+            (:1137-1148), which orphans its old vec0 row; the reference's INNER JOINs then drop it
+            (:1569-1570)                                          -> masked out of every search;
+          * rows whose image row changed (``last_modified`` / ``image_id``), the trace of an in-place
+            ``UPDATE vec0`` (:1165-1167)                            -> blob re-read, ``clipdb_update_row``;
+          * anything else (a mapping that appeared for an old rowid)  -> full ``reload()``.
+        Returns the number of rows appended + updated + retired."""
+        dv = loader.data_version(self._watch_conn())
+        if not force and dv == self._data_version:
             return 0
-        if not self._paths:
-            self.index.load(host.rows, host.rowids)
-        else:
-            self.index.append(host.rows, host.rowids)
-        base = len(self._paths)
-        self._paths.extend(host.file_paths)
-        self._lowered = None
-        self._image_ids = np.concatenate([self._image_ids, host.image_ids])
-        self._rowids = np.concatenate([self._rowids, host.rowids]) if base else host.rowids
-        for i, r in enumerate(host.rowids):
-            self._rowid_to_pos[int(r)] = base + i
-        self._mask_key = None
-        return m
+        multi = hasattr(self.index, "shards")
+        touched = 0
+        with loader.snapshot(self.db_path) as conn:
+            self._data_version = dv
+            mp = loader.read_mapping(conn)
+            old = self._rowids
+            n_old = old.shape[0]
+            last = int(old[-1]) if n_old else None
+            at = np.searchsorted(mp.rowids, old)
+            at[at >= max(len(mp.rowids), 1)] = max(len(mp.rowids) - 1, 0)
+            present = (mp.rowids[at] == old) if len(mp.rowids) else np.zeros(n_old, dtype=bool)
+            n_present_old = int(present.sum())
+            n_old_in_map = int(np.searchsorted(mp.rowids, last, side="right")) if last is not None else 0
+            if n_old == 0 or n_old_in_map != n_present_old:
+                # a store that was empty, or a mapping that appeared for a rowid we skipped at load time
+                conn.execute("ROLLBACK")
+                self.reload()
+                return self._rowids.shape[0]
+            # retired rows (and rows whose mapping came back)
+            alive_before = self._alive if self._alive is not None else np.ones(n_old, dtype=bool)
+            flipped = alive_before != present
+            if flipped.any():
+                self._alive = None if present.all() else present.copy()
+                self._mask_key = None
+                touched += int(flipped.sum())
+            # in-place re-embeddings
+            changed = present & ((mp.image_ids[at] != self._image_ids) | (mp.mtimes[at] != self._mtimes))
+            if changed.any():
+                for chunk in loader.read_rows_by_rowid(conn, old[changed].tolist()):
+                    pos = self._pos_of(chunk.rowids)
+                    for j, p in enumerate(pos.tolist()):
+                        self.index.update_row(p, chunk.rows[j])
+                        self._paths[p] = chunk.file_paths[j]
+                    self._image_ids[pos] = chunk.image_ids
+                    self._mtimes[pos] = chunk.mtimes
+                    touched += len(pos)
+                self._lowered = None
+                self._mask_key = None
+            # appended rows
+            if len(mp.rowids) > n_old_in_map:
+                target = self.index
+
+                def append(rows, rowids):
+                    target.append(rows, rowids)
+                    (target.shards[-1] if multi else target).synchronize()     # the staging buffer is reused
+                host = self._stream_into(conn, append, lo=last, expect_dim=self.index.dim or None)
+                m = host.rowids.shape[0]
+                if m:
+                    self._paths.extend(host.file_paths)
+                    self._lowered = None
+                    self._image_ids = np.concatenate([self._image_ids, host.image_ids])
+                    self._mtimes = np.concatenate([self._mtimes, host.mtimes])
+                    self._rowids = np.concatenate([self._rowids, host.rowids])
+                    if self._alive is not None:
+                        self._alive = np.concatenate([self._alive, np.ones(m, dtype=bool)])
+                    self._mask_key = None
+                    touched += m
+            binary_count = loader.count_binary(conn)
+            if binary_count != self._binary_count or touched:
+                self._codes = None            # the sign-code fallback store is re-read on next use
+                self._code_mask_key = None
+            self._binary_count = binary_count
+            self._vec0_count = loader.count_vec0(conn)
+        return touched
 
     def close(self) -> None:
+        if self._watch is not None:
+            self._watch.close()
+            self._watch = None
         self.index.close()
 
     # ---- search -----------------------------------------------------------------------
     def _embed(self, query: str, is_image: bool, what: str) -> Optional[np.ndarray]:
+        if isinstance(query, str) and query.lower().startswith(VECTOR_PREFIX):
+            return load_vector(query[len(VECTOR_PREFIX):].strip(), self.embedding_dim)
         if self.embedder is None:
             raise RuntimeError("no embedder configured: pass embedder=... or call search_embedding() "
                                "with float32 vectors (the SigLIP model is outside this package)")
@@ -301,17 +442,24 @@ class ImageDatabase:
             if nan > 0 and self.nan_policy == "reference" and k > 0:
                 out.append([])            # the reference's search() returns [] (see search_embedding)
                 continue
-            out.append([(self._paths[self._rowid_to_pos[int(r)]], 1.0 - float(d)) for r, d in zip(rowids, dist)])
+            out.append([(self._paths[p], 1.0 - float(d)) for p, d in zip(self._pos_of(rowids).tolist(), dist)])
         return out
 
     def _install_mask(self, filter_folders: Optional[Sequence[str]]) -> bool:
-        if not filter_folders:
+        """Admission bitset = the folder WHERE clause AND the rows whose mapping still exists."""
+        retired = self._alive is not None and not self._alive.all()
+        if not filter_folders and not retired:
             return False
-        key = tuple(filter_folders)
+        key = (tuple(filter_folders or ()), retired)
         if key != self._mask_key:
-            if self._lowered is None:
-                self._lowered = [p.encode("utf-8").lower() for p in self._paths]
-            self.index.set_mask(like_prefix_mask(self._paths, filter_folders, self._lowered))
+            admitted = np.ones(len(self._paths), dtype=bool)
+            if filter_folders:
+                if self._lowered is None:
+                    self._lowered = [p.encode("utf-8").lower() for p in self._paths]
+                admitted = like_prefix_mask(self._paths, filter_folders, self._lowered)
+            if retired:
+                admitted = admitted & self._alive
+            self.index.set_mask(admitted)
             self._mask_key = key
         return True
 
@@ -351,7 +499,7 @@ class ImageDatabase:
                 # SQLite stores a NaN distance as NULL, NULLs sort first, and the reference's
                 # `1.0 - distance` then raises inside its try block (:1588, :1637-1640)
                 raise TypeError("unsupported operand type(s) for -: 'float' and 'NoneType'")
-            positions = [self._rowid_to_pos[int(r)] for r in rowids]
+            positions = self._pos_of(rowids).tolist()
             top = [(self._paths[p], 1.0 - float(d)) for p, d in zip(positions, dist)]
             timings["db_query"] = time.time() - t0
             results = [(p, float(s)) for p, s in top]

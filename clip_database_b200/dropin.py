@@ -11,9 +11,12 @@ reference's own code, now answered from HBM.  The embeddings still come from the
     db = image_database.ImageDatabase("images.db")                    # the reference, unchanged
     db.search("a red car", k=20, negative_query="people")              # scan + top-k on the GPU
 
-The resident store is built on the first search of each instance and picks up rows the scanner
-appended (new ``vec0`` rowids) before every search; after an in-place re-embedding of existing
-files call ``db._b200.reload()``.  ``uninstall`` restores the original method.
+The resident store is built on the first search of each instance.  Before every later search
+``ImageDatabase.refresh()`` checks SQLite's change counter (O(1)) and, when something was committed,
+reconciles the store with the mapping tables: appended rows are streamed in, rows orphaned by a
+re-scan of a modified file (``INSERT OR REPLACE INTO images`` re-keys it) are retired, re-embedded
+rows are re-read — what the reference sees by reopening the database for every search.
+``uninstall`` restores the original method.
 """
 from __future__ import annotations
 

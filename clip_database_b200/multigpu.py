@@ -50,6 +50,8 @@ class MultiGpuIndex:
         self.num_rows = 0
         self._connected = False
         self._k = None
+        self._masked = False          # every shard holds an admission mask
+        self._issued = 0              # upper bound on the exchange sequence numbers used so far
 
     # ---- store ------------------------------------------------------------------------
     def load(self, rows: np.ndarray, rowids: Optional[np.ndarray] = None) -> None:
@@ -73,6 +75,21 @@ class MultiGpuIndex:
         self.shards[rank].load(rows, np.ascontiguousarray(rowids, dtype=np.int64))
         self._shard_rows = getattr(self, "_shard_rows", {})
         self._shard_rows[rank] = rows.shape[0]
+
+    def note_shard_loaded(self, rank: int, n_rows: int) -> None:
+        """Shard ``rank`` was filled directly (``shards[rank].reserve`` + ``append``, the streaming loader)."""
+        if n_rows < 1:
+            raise ValueError("every shard needs at least one row")
+        self._shard_rows = getattr(self, "_shard_rows", {})
+        self._shard_rows[rank] = int(n_rows)
+
+    def update_row(self, position: int, row) -> None:
+        """Overwrite the row at global scan position ``position`` (in-place re-embedding)."""
+        for (lo, hi), idx in zip(self.bounds, self.shards):
+            if lo <= position < hi:
+                idx.update_row(position - lo, row)
+                return
+        raise IndexError("position out of range")
 
     def finish_load(self) -> None:
         counts = [self._shard_rows[r] for r in range(self.world)]
@@ -99,6 +116,8 @@ class MultiGpuIndex:
         self.shards[-1].append(rows, ids if ids is not None else np.arange(hi, hi + rows.shape[0], dtype=np.int64))
         self.bounds[-1] = (lo, hi + rows.shape[0])
         self.num_rows += rows.shape[0]
+        if self._masked:               # the last shard dropped its mask (sized for the old row count): so do the others
+            self.clear_mask()
 
     def set_mask(self, admitted) -> None:
         bits = np.asarray(admitted).astype(bool)
@@ -106,10 +125,28 @@ class MultiGpuIndex:
             raise ValueError("mask must have one entry per row")
         for (lo, hi), idx in zip(self.bounds, self.shards):
             idx.set_mask(bits[lo:hi])
+        self._masked = True
 
     def clear_mask(self) -> None:
         for idx in self.shards:
             idx.clear_mask()
+        self._masked = False
+
+    def resync(self) -> None:
+        """Bring the shards' exchanges back in step after a launch failed on some of them or a wait timed out:
+        shards that did launch are released from their in-kernel wait (abort flag), every stream is drained, and
+        all shards restart from one common sequence number above anything used so far (stale inbox records
+        carry older numbers and are ignored)."""
+        if not self._connected:
+            return
+        for idx in self.shards:
+            idx.exchange_abort(True)
+        for s in self._streams:
+            s.synchronize()
+        self._issued += 16
+        for idx in self.shards:
+            idx.exchange_abort(False)
+            idx.exchange_set_epoch(self._issued, self._issued)
 
     @property
     def dim(self) -> int:
@@ -147,24 +184,37 @@ class MultiGpuIndex:
     def search(self, query: np.ndarray, k: int, use_mask: bool = False) -> Tuple[np.ndarray, np.ndarray, int]:
         """(rowids, distances, NaN rows over all shards) for one query; synchronous.  One kernel
         launch per GPU; every GPU ends up with the merged answer, GPU 0's is fetched."""
+        # everything that can be refused is refused BEFORE the first launch: a shard that launched while another
+        # did not would wait in-kernel for a record that never comes, and the sequence numbers would drift apart
         if not 1 <= k <= self.FUSED_K_MAX:
             raise ValueError(f"k must be 1..{self.FUSED_K_MAX} on the multi-GPU path")
+        if use_mask and not self._masked:
+            raise ValueError("use_mask set but no mask installed (set_mask after the last append)")
+        q_host = np.ascontiguousarray(query, dtype=np.float32).ravel()
+        if q_host.shape[0] != self.dim:
+            raise ValueError(f"query must be [{self.dim}]")
         t = self.torch
         self._prepare(k)
-        self._h_q.numpy()[:] = np.ascontiguousarray(query, dtype=np.float32).ravel()
-        for r, (d, idx) in enumerate(zip(self.devices, self.shards)):
-            with t.cuda.device(d), t.cuda.stream(self._streams[r]):
-                self._q[r].copy_(self._h_q, non_blocking=True)
-                ids, dist, n, nan = self._views[r]
-                idx.search_sharded_device(self._q[r], k, ids, dist, n, nan, use_mask=use_mask)
-        with t.cuda.device(self.devices[0]), t.cuda.stream(self._streams[0]):
-            self._h_out.copy_(self._out[0], non_blocking=True)
-        for s in self._streams:                         # results of GPU 0; every H2D of the pinned query done
-            s.synchronize()
+        self._h_q.numpy()[:] = q_host
+        self._issued += 1
+        try:
+            for r, (d, idx) in enumerate(zip(self.devices, self.shards)):
+                with t.cuda.device(d), t.cuda.stream(self._streams[r]):
+                    self._q[r].copy_(self._h_q, non_blocking=True)
+                    ids, dist, n, nan = self._views[r]
+                    idx.search_sharded_device(self._q[r], k, ids, dist, n, nan, use_mask=use_mask)
+            with t.cuda.device(self.devices[0]), t.cuda.stream(self._streams[0]):
+                self._h_out.copy_(self._out[0], non_blocking=True)
+            for s in self._streams:                     # results of GPU 0; every H2D of the pinned query done
+                s.synchronize()
+        except Exception:
+            self.resync()
+            raise
         lay = self._lay
         h = self._h_out.numpy()
         m = int(h[lay.off_count:lay.off_count + 4].view(np.int32)[0])
         if m < 0:
+            self.resync()
             raise RuntimeError("multi-GPU search: a shard did not deliver its candidates in time"
                                if m == -1 else "multi-GPU search: the shards were asked different questions")
         ids = h[lay.off_rowids:lay.off_rowids + 8 * m].view(np.int64).copy()
@@ -191,25 +241,35 @@ class MultiGpuIndex:
         if not 1 <= k <= self.FUSED_K_MAX:
             raise ValueError(f"k must be 1..{self.FUSED_K_MAX} on the multi-GPU path")
         q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"queries must be [nq, {self.dim}]")
+        if k > min(hi - lo for lo, hi in self.bounds):
+            raise ValueError("k exceeds the smallest shard: use search() per query")
         nq = q.shape[0]
         h_q = t.from_numpy(q).pin_memory()
         outs = []
-        for r, (d, idx) in enumerate(zip(self.devices, self.shards)):
-            with t.cuda.device(d), t.cuda.stream(self._streams[r]):
-                dev = t.device("cuda", d)
-                dq = h_q.to(dev, non_blocking=True)
-                o = (t.empty((nq, k), dtype=t.int64, device=dev), t.empty((nq, k), dtype=t.float32, device=dev),
-                     t.zeros(nq, dtype=t.int32, device=dev), t.zeros(nq, dtype=t.int64, device=dev),
-                     t.zeros(nq, dtype=t.int32, device=dev))
-                for q0 in range(0, nq, 256):
-                    q1 = min(q0 + 256, nq)
-                    idx.search_batch_sharded_device(dq[q0:q1], k, o[0][q0:q1], o[1][q0:q1], o[2][q0:q1], o[3][q0:q1],
-                                                    o[4][q0:q1])
-                outs.append((dq, o))
-        for s in self._streams:
-            s.synchronize()
+        self._issued += (nq + 255) // 256
+        try:
+            for r, (d, idx) in enumerate(zip(self.devices, self.shards)):
+                with t.cuda.device(d), t.cuda.stream(self._streams[r]):
+                    dev = t.device("cuda", d)
+                    dq = h_q.to(dev, non_blocking=True)
+                    o = (t.empty((nq, k), dtype=t.int64, device=dev), t.empty((nq, k), dtype=t.float32, device=dev),
+                         t.zeros(nq, dtype=t.int32, device=dev), t.zeros(nq, dtype=t.int64, device=dev),
+                         t.zeros(nq, dtype=t.int32, device=dev))
+                    for q0 in range(0, nq, 256):
+                        q1 = min(q0 + 256, nq)
+                        idx.search_batch_sharded_device(dq[q0:q1], k, o[0][q0:q1], o[1][q0:q1], o[2][q0:q1],
+                                                        o[3][q0:q1], o[4][q0:q1])
+                    outs.append((dq, o))
+            for s in self._streams:
+                s.synchronize()
+        except Exception:
+            self.resync()
+            raise
         ids, dist, n, nan, flags = (x.cpu().numpy() for x in outs[0][1])
         if (n < 0).any():
+            self.resync()
             raise RuntimeError("multi-GPU batch search: a shard did not deliver in time")
         res = SearchResult(ids.copy(), dist.copy(), n.copy(), nan.copy())
         for qi in np.flatnonzero(flags).tolist():

@@ -13,6 +13,12 @@ the reference's ``"{rank}. {similarity:.4f}: {path}"`` form.
   <q> - <neg> [- <neg2> ...]        negatives, split on ' - '                (:2157-2190)
   <q1> + <q2>                       combined query, split on the first '+'   (:2193-2213)
   image:<path>                      an image query in any of the positions   (:2167, 2200, 2208, 2227)
+  vector:<file.npy>                 (this package) a ready-made float32[1152] embedding in any of the
+                                    positions; needs no model: ``vector:q.npy + vector:style.npy - vector:neg.npy``
+
+``python -m clip_database_b200.session --db images.db --embedder mymodule:MyEmbedder`` runs the loop with a
+model behind text / image queries (an object with ``text(str)`` and ``image(path)``, see
+``database.Embedder``); without ``--embedder`` the session answers ``vector:`` queries only.
 """
 from __future__ import annotations
 
@@ -162,22 +168,36 @@ def run_session(db, state: Optional[SessionState] = None, read: Callable[[str], 
             write(f"Error: {e}")
 
 
-def main(argv: Optional[List[str]] = None) -> int:
-    """``python -m clip_database_b200.session --db images.db``: search an existing database.
-    Text / image queries need an embedder plugged in by the caller; without one the session
-    still accepts ``vector:<path.npy>`` style use through ``ImageDatabase.search_embedding``."""
+def main(argv: Optional[List[str]] = None, read: Callable[[str], str] = input,
+         write: Callable[[str], None] = print) -> int:
+    """``python -m clip_database_b200.session --db images.db [--embedder module:Class]``: search an existing
+    database interactively (the reference's ``interactive`` command, image_database.py:2035-2047)."""
     import argparse
 
-    from .database import ImageDatabase
+    from .database import ImageDatabase, load_embedder
     ap = argparse.ArgumentParser(description="Interactive KNN search over a CLIP-database SQLite file (GPU path)")
     ap.add_argument("--db", required=True)
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--devices", default=None, help="comma-separated GPUs to row-shard the store over")
     ap.add_argument("-k", type=int, default=10)
     ap.add_argument("--show-duplicates", action="store_true")
+    ap.add_argument("--profile", action="store_true")
+    ap.add_argument("--batch-store", action="store_true", help="keep the bf16 copy: tensor-core pre-selection")
+    ap.add_argument("--embedder", default=None,
+                    help="module:Class of an embedder (text(str) / image(path) -> float32[1152]); without it only "
+                         "vector:<file.npy> queries can be answered")
     args = ap.parse_args(argv)
-    db = ImageDatabase(args.db, device=args.device, verbose=True)
+    embedder = load_embedder(args.embedder) if args.embedder else None
+    devices = [int(d) for d in args.devices.split(",")] if args.devices else None
+    db = ImageDatabase(args.db, device=args.device, embedder=embedder, verbose=True, batch_store=args.batch_store,
+                       devices=devices)
+    write("Interactive search: text, image:<path>, vector:<file.npy>; 'q1 + q2', 'q - negative'; k:<n>, "
+          "folder:<path>, duplicates:show|hide, quit" if embedder is not None else
+          "Interactive search (no embedder: vector:<file.npy> queries only); 'v1 + v2', 'v - negative'; k:<n>, "
+          "folder:<path>, duplicates:show|hide, quit")
     try:
-        run_session(db, SessionState(k=args.k, show_duplicates=args.show_duplicates))
+        run_session(db, SessionState(k=args.k, show_duplicates=args.show_duplicates, profile=args.profile),
+                    read=read, write=write)
     finally:
         db.close()
     return 0

@@ -246,6 +246,24 @@ class ShardedIndex:
             dist.all_gather_object(flags, ok, group=group)
             self.fused = all(flags)
 
+    def resync(self) -> None:
+        """COLLECTIVE: after a rank failed to enqueue a search, or an exchange timed out, every rank calls this
+        to restart the fused exchange from one common sequence number (agreed with an all-reduce MAX) — stale
+        inbox records carry older numbers and are ignored.  Ranks still spinning in a kernel are released first."""
+        if not (self.fused and self.world > 1):
+            return
+        index = self.backend.index
+        index.exchange_abort(True)
+        index.synchronize()
+        t = self.backend.torch
+        self._issued = getattr(self, "_issued", 0) + 16
+        top = t.tensor([self._issued], dtype=t.int64, device=self.backend.device)
+        self.dist.all_reduce(top, op=self.dist.ReduceOp.MAX, group=self.group)
+        self._issued = int(top[0])
+        index.exchange_abort(False)
+        index.exchange_set_epoch(self._issued, self._issued)
+        self.dist.barrier(group=self.group)
+
     def _prepare(self, k: int) -> None:
         if self._k == k:
             return
@@ -261,6 +279,7 @@ class ShardedIndex:
         every rank holds the same merged answer."""
         self._prepare(k)
         if self.fused and 1 <= k <= self.FUSED_K_MAX:
+            self._issued = getattr(self, "_issued", 0) + 1
             self.backend.fused_search(d_query, k, self.out_dist, self.out_rowids, self.out_n, self.backend.out_nan,
                                       use_mask)
             return self.out_dist, self.out_rowids, self.out_n
@@ -289,6 +308,7 @@ class ShardedIndex:
                 self._bflags = t.zeros(nq, dtype=t.int32, device=self.backend.device)
                 self._bkey = fkey
             out_dist, out_rowids, out_n = self._bout
+            self._issued = getattr(self, "_issued", 0) + max(nq, 1)
             if getattr(self.backend, "batch_enabled", False):
                 self.backend.fused_search_batch(d_queries, k, out_dist, out_rowids, out_n, self._bnan, self._bflags)
             else:

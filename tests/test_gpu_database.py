@@ -1,0 +1,227 @@
+"""``ImageDatabase`` as a long-lived process next to a scanner that keeps writing: ``refresh()`` must leave the
+resident store answering exactly what the reference answers by reopening SQLite for every search
+(image_database.py:1475) — checked against the reference's own SQL statement executed by the real SQLite on
+the same file (oracle/sql_harness.py).  Also the streaming loader at 1M rows and the interactive session."""
+import os
+import resource
+import sqlite3
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from clip_database_b200 import synth
+from oracle import sql_harness
+
+from conftest import ROOT, have_gpu, tol
+
+pytestmark = pytest.mark.gpu
+DIM = 1152
+
+
+def reference_answer(db_path, q, k, folders=None):
+    return sql_harness.reference_search(db_path, q, k, folders)
+
+
+def assert_same_answer(got, want):
+    assert [p for p, _ in got] == [p for p, _ in want]
+    g, w = np.array([s for _, s in got]), np.array([s for _, s in want])
+    assert np.all(np.abs(g - w) <= tol(1.0 - w))
+
+
+def rescan_modified_file(conn, file_path, new_embedding, mtime):
+    """What ``_commit_batch`` does for a file whose content changed (image_database.py:1137-1198): the image row
+    is re-keyed by INSERT OR REPLACE, a NEW vec0 row is inserted and linked; the old vec0 row stays, orphaned."""
+    cur = conn.cursor()
+    cur.execute("INSERT OR REPLACE INTO images (file_path, last_modified, file_hash) VALUES (?, ?, ?)",
+                (file_path, mtime, "changed"))
+    image_id = cur.lastrowid
+    assert cur.execute("SELECT rowid FROM image_embeddings WHERE image_id = ?", (image_id,)).fetchone() is None
+    cur.execute("INSERT INTO vec0 (embedding) VALUES (?)", (np.asarray(new_embedding, dtype=np.float32).tobytes(),))
+    vec_rowid = cur.lastrowid
+    cur.execute("INSERT INTO image_embeddings (rowid, image_id) VALUES (?, ?)", (vec_rowid, image_id))
+    cur.execute("INSERT INTO binary_embeddings (image_id, embedding) VALUES (?, ?)",
+                (image_id, (np.asarray(new_embedding) >= 0).astype(np.uint8).tobytes()))
+    conn.commit()
+    return image_id, vec_rowid
+
+
+@pytest.mark.parametrize("devices,batch_store", [(None, False), (None, True), ([0, 0], False)],
+                         ids=["one-gpu", "one-gpu-bf16", "two-shards"])
+def test_refresh_tracks_a_scanner_writing_next_to_it(tmp_path, devices, batch_store):
+    assert have_gpu(), "GPU tests selected but no CUDA device is visible"
+    from clip_database_b200 import ImageDatabase
+    n, k = 3000, 12
+    rows = synth.unit_rows(n, DIM, 31)
+    paths = synth.default_paths(n)
+    db_path = str(tmp_path / "live.db")
+    synth.write_reference_db(db_path, rows, paths, drop_mapping_for=[17])
+    q = synth.unit_rows(1, DIM, 32)[0]
+    db = ImageDatabase(db_path, device=0, devices=devices, batch_store=batch_store)
+    writer = sqlite3.connect(db_path)
+    try:
+        first = db.search_embedding(q, k=k, show_duplicates=True)
+        assert_same_answer(first, reference_answer(db_path, q, k))
+        assert db.refresh() == 0                                      # nothing was committed: O(1)
+
+        # 1. a modified file is re-scanned: its old row must disappear, its new embedding must be found
+        top_path = first[0][0]
+        new_vec = synth.unit_rows(1, DIM, 33)[0]
+        rescan_modified_file(writer, top_path, new_vec, 1.8e9)
+        assert db.refresh() == 2                                      # one row retired, one appended
+        after = db.search_embedding(q, k=k, show_duplicates=True)
+        assert_same_answer(after, reference_answer(db_path, q, k))
+        assert top_path not in [p for p, _ in after]                  # (its new embedding is unrelated to q)
+        near_new = db.search_embedding(new_vec, k=3, show_duplicates=True)
+        assert near_new[0][0] == top_path and abs(near_new[0][1] - 1.0) < 1e-5
+        assert_same_answer(near_new, reference_answer(db_path, new_vec, 3))
+
+        # 2. plain appends (new files)
+        more = synth.unit_rows(40, DIM, 34)
+        more[5] = q                                                   # one of them is the query itself
+        cur = writer.cursor()
+        for j in range(40):
+            cur.execute("INSERT INTO images (file_path, last_modified, file_hash) VALUES (?, ?, ?)",
+                        (f"/data/new/img_{j:04d}.jpg", 1.9e9 + j, "x"))
+            image_id = cur.lastrowid
+            cur.execute("INSERT INTO vec0 (embedding) VALUES (?)", (more[j].tobytes(),))
+            cur.execute("INSERT INTO image_embeddings (rowid, image_id) VALUES (?, ?)", (cur.lastrowid, image_id))
+        writer.commit()
+        assert db.refresh() == 40
+        got = db.search_embedding(q, k=k, show_duplicates=True)
+        assert got[0][0] == "/data/new/img_0005.jpg"
+        assert_same_answer(got, reference_answer(db_path, q, k))
+
+        # 3. an in-place re-embedding (UPDATE vec0 ... WHERE rowid, :1165-1167) with the image row touched
+        victim_path = got[1][0]
+        image_id, vec_rowid = writer.execute(
+            "SELECT i.id, ie.rowid FROM images i JOIN image_embeddings ie ON ie.image_id = i.id WHERE i.file_path = ?",
+            (victim_path,)).fetchone()
+        writer.execute("UPDATE vec0 SET embedding = ? WHERE rowid = ?", (synth.unit_rows(1, DIM, 35)[0].tobytes(), vec_rowid))
+        writer.execute("UPDATE images SET last_modified = ? WHERE id = ?", (2.0e9, image_id))
+        writer.commit()
+        assert db.refresh() == 1
+        got = db.search_embedding(q, k=k, show_duplicates=True)
+        assert victim_path not in [p for p, _ in got]
+        assert_same_answer(got, reference_answer(db_path, q, k))
+
+        # 4. a folder filter on top of retired rows
+        folders = ["/data/photos/a", "/data/new"]
+        assert_same_answer(db.search_embedding(q, k=k, filter_folders=folders, show_duplicates=True),
+                           reference_answer(db_path, q, k, folders))
+
+        # 5. a mapping appears for a vec0 row that had none at load time: a full reload
+        writer.execute("INSERT INTO image_embeddings (rowid, image_id) VALUES (?, ?)", (18, 18))
+        writer.commit()
+        assert db.refresh() > 40
+        assert_same_answer(db.search_embedding(rows[17], k=3, show_duplicates=True), reference_answer(db_path, rows[17], 3))
+        assert db.refresh() == 0
+    finally:
+        writer.close()
+        db.close()
+
+
+def test_session_answers_vector_queries_and_uses_the_embedder_hook(tmp_path):
+    assert have_gpu()
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from clip_database_b200 import ImageDatabase, session
+    from fake_embedder import HashEmbedder
+    n = 2000
+    rows = synth.unit_rows(n, DIM, 41)
+    db_path = str(tmp_path / "s.db")
+    synth.write_reference_db(db_path, rows)
+    emb = HashEmbedder()
+    vq, vs, vn = synth.unit_rows(3, DIM, 42)
+    for name, v in (("q", vq), ("s", vs), ("n", vn)):
+        np.save(tmp_path / f"{name}.npy", v)
+    img = str(tmp_path / "y.jpg")
+    open(img, "w").close()
+    with _closing(ImageDatabase(db_path, device=0)) as db:
+        want_vec = db.search_embedding(vq, k=5, embedding2=vs, negative_embeddings=[vn], negative_weights=[0.5])
+        want_txt = db.search_embedding(emb.text("a red car"), k=5, embedding2=emb.image(img))
+        want_mix = db.search_embedding(emb.text("boats"), k=5, negative_embeddings=[vn], negative_weights=[0.5])
+
+    def scripted(lines):
+        it = iter(lines)
+        out = []
+
+        def read(_prompt):
+            try:
+                return next(it)
+            except StopIteration:
+                raise EOFError
+        return read, out.append, out
+
+    def listed(out):
+        return [ln.split(": ", 1)[1] for ln in out if ln.startswith("  ") and ". " in ln and ": " in ln and "/" in ln]
+
+    # no embedder: vector queries only
+    read, write, out = scripted(["k:5", f"vector:{tmp_path}/q.npy + vector:{tmp_path}/s.npy - vector:{tmp_path}/n.npy",
+                                 "a red car", "quit"])
+    assert session.main(["--db", db_path], read=read, write=write) == 0
+    assert listed(out) == [p for p, _ in want_vec]
+    assert any("no embedder configured" in ln for ln in out)          # the text query is refused, the session goes on
+    # with the embedder hook: text, image: and vector: in one session
+    read, write, out = scripted(["k:5", f"a red car + image:{img}", "quit"])
+    assert session.main(["--db", db_path, "--embedder", "fake_embedder:HashEmbedder"], read=read, write=write) == 0
+    assert listed(out) == [p for p, _ in want_txt]
+    read, write, out = scripted(["k:5", f"boats - vector:{tmp_path}/n.npy", "quit"])
+    assert session.main(["--db", db_path, "--embedder", "fake_embedder:HashEmbedder"], read=read, write=write) == 0
+    assert listed(out) == [p for p, _ in want_mix]
+
+
+class _closing:
+    def __init__(self, db):
+        self.db = db
+
+    def __enter__(self):
+        return self.db
+
+    def __exit__(self, *exc):
+        self.db.close()
+
+
+MAKE_BIG_DB = r"""
+import sys
+sys.path.insert(0, {root!r})
+from clip_database_b200 import synth
+from oracle import ref
+rows = ref.fill_unit_rows({n}, 1152, 1234)
+synth.write_reference_db({path!r}, rows, binary_codes=False)
+import sqlite3
+c = sqlite3.connect({path!r})
+c.execute("INSERT INTO binary_embeddings (image_id, embedding) VALUES (1, zeroblob(1152))")   # the guard at :1488-1500
+c.commit()
+"""
+
+
+def test_loader_streams_a_million_rows(tmp_path):
+    """SURVEY §8d config 1 says "loaded to HBM through the loader"; VERDICT r1 weak #6: the loader must survive a
+    real database.  1M rows (4.6 GB of blobs) written by a child process, streamed into HBM here: host memory
+    grows by far less than the store, rows/s is reported, and the answers equal the reference statement's."""
+    assert have_gpu()
+    import shutil
+    import time
+    from clip_database_b200 import ImageDatabase
+    n = 1_000_000
+    if shutil.disk_usage(str(tmp_path)).free < 12e9:
+        pytest.skip("needs ~6 GB of scratch disk")
+    db_path = str(tmp_path / "big.db")
+    subprocess.run([sys.executable, "-c", MAKE_BIG_DB.format(root=ROOT, n=n, path=db_path)], check=True, timeout=900)
+    rss0 = resource.getrusage(resource.RUSAGE_SELF).ru_maxrss          # KiB
+    t0 = time.perf_counter()
+    db = ImageDatabase(db_path, device=0, verbose=True)
+    secs = time.perf_counter() - t0
+    rss1 = resource.getrusage(resource.RUSAGE_SELF).ru_maxrss
+    try:
+        assert db.index.num_rows == n
+        grown = (rss1 - rss0) * 1024
+        print(f"loader: {n / secs:.0f} rows/s ({n * 4608 / 1e6 / secs:.0f} MB/s), host RSS grew by {grown / 1e6:.0f} MB "
+              f"for a {n * 4608 / 1e6:.0f} MB store")
+        assert grown < 1.5e9, "the loader must not hold the store in host memory"
+        for seed in (7, 8):
+            q = synth.unit_rows(1, DIM, seed)[0]
+            assert_same_answer(db.search_embedding(q, k=20, show_duplicates=True), reference_answer(db_path, q, 20))
+    finally:
+        db.close()

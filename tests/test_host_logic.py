@@ -167,3 +167,52 @@ def test_sharded_loading_covers_the_store_exactly_once(tmp_path, layout):
         assert np.array_equal(np.concatenate([p.rowids for p in parts]), whole.rowids)
         assert np.array_equal(np.concatenate([p.rows for p in parts]), whole.rows)
         assert sum((p.file_paths for p in parts), []) == whole.file_paths
+
+
+def test_streamed_reading_is_chunked_and_consistent(tmp_path):
+    """iter_store yields the same rows as read_store, chunk by chunk, skipping orphans inside and across chunks;
+    plan_shards tiles the rowid axis from one snapshot."""
+    n = 700
+    rows = synth.unit_rows(n, 32, 5)
+    db = str(tmp_path / "s.db")
+    drop_m, drop_i = [0, 99, 100, 101, 699], [350]
+    synth.write_reference_db(db, rows, drop_mapping_for=drop_m, drop_image_for=drop_i, rowid_start=10)
+    whole = loader.read_store(db)
+    keep = [i for i in range(n) if i not in drop_m + drop_i]
+    assert whole.rowids.tolist() == [10 + i for i in keep] and np.array_equal(whole.rows, rows[keep])
+    assert whole.vec0_count == n and whole.dropped == len(drop_m) + len(drop_i)
+    assert whole.mtimes.shape == (len(keep),) and whole.mtimes[0] == 1.7e9 + keep[0]
+    with loader.snapshot(db) as conn:
+        st = loader.StoreStats()
+        chunks = list(loader.iter_store(conn, chunk_rows=64, stats=st))
+        assert all(len(c.rowids) <= 64 for c in chunks) and len(chunks) >= n // 64
+        assert np.array_equal(np.concatenate([c.rowids for c in chunks]), whole.rowids)
+        assert np.array_equal(np.concatenate([c.rows for c in chunks]), whole.rows)
+        assert [p for c in chunks for p in c.file_paths] == whole.file_paths
+        assert st.vec0_rows == n and st.joined_rows == len(keep) and st.dim == 32
+        ranges, mapped = loader.plan_shards(conn, 3)
+        assert mapped == len(keep) and ranges[0][0] is None and ranges[-1][1] is None
+        got = [loader.stream_store(db, lambda c: None, min_rowid=lo, max_rowid=hi, conn=conn) for lo, hi in ranges]
+        assert np.array_equal(np.concatenate([g.rowids for g in got]), whole.rowids)
+        sizes = [len(g.rowids) for g in got]
+        assert max(sizes) - min(sizes) <= 1
+        some = [whole.rowids[3], whole.rowids[400], whole.rowids[401], 10 + 99]      # the last one is an orphan
+        picked = list(loader.read_rows_by_rowid(conn, some))
+        assert np.concatenate([c.rowids for c in picked]).tolist() == sorted(some[:3])
+        mp = loader.read_mapping(conn)
+        assert np.array_equal(mp.rowids, whole.rowids) and np.array_equal(mp.image_ids, whole.image_ids)
+
+
+def test_data_version_moves_only_when_someone_else_commits(tmp_path):
+    import sqlite3
+    db = str(tmp_path / "v.db")
+    synth.write_reference_db(db, synth.unit_rows(10, 16, 1))
+    watch = loader.connect(db)
+    v0 = loader.data_version(watch)
+    assert loader.data_version(watch) == v0
+    w = sqlite3.connect(db)
+    w.execute("UPDATE images SET last_modified = last_modified + 1 WHERE id = 3")
+    w.commit()
+    w.close()
+    assert loader.data_version(watch) != v0
+    watch.close()

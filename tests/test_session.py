@@ -66,3 +66,30 @@ def test_session_loop_calls_search_with_reference_kwargs():
     assert kw["negative_query"] == "dog" and kw["weights"] == (0.7, 0.3) and kw["show_duplicates"]
     assert kw["filter_folders"] is None
     assert any("0.9123: /p/a.jpg" in o for o in out) and "No results found." in out
+
+
+def test_vector_queries_pass_through_the_grammar_unchanged():
+    """``vector:<file.npy>`` needs no parser support: it travels as the query text and ImageDatabase resolves it."""
+    st = SessionState()
+    r = parse_line("vector:/tmp/q.npy + vector:/tmp/s.npy - vector:/tmp/n.npy", st)
+    assert (r.query, r.is_image_path, r.query2, r.is_image_path2) == ("vector:/tmp/q.npy", False, "vector:/tmp/s.npy", False)
+    assert r.negative_query == "vector:/tmp/n.npy" and not r.negative_is_image
+
+
+def test_load_vector_and_embedder_hook(tmp_path):
+    import numpy as np
+    import pytest
+    from clip_database_b200.database import load_embedder, load_vector
+    v = np.arange(1152, dtype=np.float64)
+    np.save(tmp_path / "q.npy", v)
+    got = load_vector(str(tmp_path / "q.npy"), 1152)
+    assert got.dtype == np.float32 and np.array_equal(got, v.astype(np.float32))
+    np.save(tmp_path / "short.npy", v[:10])
+    with pytest.raises(ValueError):
+        load_vector(str(tmp_path / "short.npy"), 1152)
+    emb = load_embedder("fake_embedder:HashEmbedder")
+    assert emb.text("a red car").shape == (1152,) and not np.array_equal(emb.text("a"), emb.image("a"))
+    with pytest.raises(TypeError):
+        load_embedder("fake_embedder:NotAnEmbedder")
+    with pytest.raises(ValueError):
+        load_embedder("no_colon")
