@@ -613,6 +613,7 @@ def measure_batch(args, torch, idx, rows_per_gpu, device, local_rank, host_q, st
     torch.cuda.synchronize()
     ms_step = ev0.elapsed_time(ev1) / steps
     gemm_ms, gemm_n = idx.profile_read()
+    kernel_mhz, _ = idx.profile_clock()
     idx.profile(False)
     launches = idx.launch_count - launches0
     flagged = int((flags != 0).sum())
@@ -658,13 +659,20 @@ def measure_batch(args, torch, idx, rows_per_gpu, device, local_rank, host_q, st
                 "flops_per_launch": flops, "avg_launch_ms": gemm_avg, "launches_timed": int(gemm_n),
                 "hbm_GBps_bf16_store": store_gbps, "hbm_frac_bf16_store": store_gbps / hbm_peak,
                 "live_cublas_tflops": live, "frac_of_live_cublas": (tflops / live) if live else None,
+                # the clock the launches really ran at (%clock64 / %globaltimer inside the kernel): the board holds
+                # its power cap by lowering it, and the tensor pipe's ceiling moves with it (nominal dense bf16 =
+                # 2250 TFLOP/s at 1965 MHz)
+                "sm_mhz_in_kernel": kernel_mhz,
+                "nominal_peak_at_that_clock": (2250.0 * kernel_mhz / 1965.0) if kernel_mhz else None,
+                "frac_of_peak_at_that_clock": (tflops / (2250.0 * kernel_mhz / 1965.0)) if kernel_mhz else None,
                 "traffic": traffic, "traffic_source": traffic_src}
     else:           # 64 / 128 queries per pass: the contraction streams the bf16 store -> HBM-bound
         roof = {"bound": "hbm", "kernel": "batch_gemm_pair_kernel<FILTER, %d>" % (64 if B <= 64 else 128),
                 "achieved": store_gbps, "peak": hbm_peak, "unit": "GB/s", "frac": store_gbps / hbm_peak,
                 "frac_of_nominal_8000": store_gbps / 8000.0, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)",
                 "algorithmic_bytes_per_launch": rows_per_gpu * BF16_ROW_BYTES, "avg_launch_ms": gemm_avg,
-                "launches_timed": int(gemm_n), "tensor_TFLOPs": tflops, "traffic": None, "traffic_source": None}
+                "launches_timed": int(gemm_n), "tensor_TFLOPs": tflops, "sm_mhz_in_kernel": kernel_mhz,
+                "traffic": None, "traffic_source": None}
     return {
         "metric": "knn_batched_queries_per_s", "value": B * 1e3 / ms_step, "unit": "queries/s", "n_gpus": 1,
         "steps": steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True,

@@ -91,6 +91,7 @@ SIGNATURES = [
     ("clipdb_merge_batch_device", c_int, [_CTX, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p,
                                           c_int64, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     ("clipdb_profile", c_int, [_CTX, c_int32]),
+    ("clipdb_profile_clock", c_int, [_CTX, _D, _D, _I64]),
     ("clipdb_profile_read", c_int, [_CTX, _D, _I64]),
 ]
 

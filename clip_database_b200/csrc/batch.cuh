@@ -255,6 +255,8 @@ struct BatchGemmArgs {
     int cand_cap;
     unsigned int *tile_counter; // CTA-pair kernel: dynamic tile scheduler, zeroed before the launch
     int static_tiles;           // CTA-pair kernel: 1 = static interleave (pair p takes tiles p, p + pairs, ...)
+    unsigned long long *clock;  // nullable (profiling): [0] += SM cycles, [1] += nanoseconds, [2] += 1 per launch,
+                                // taken by CTA 0 around its whole run: cycles / ns = the SM clock the launch ran at
 };
 
 // ---- filter epilogue ---------------------------------------------------------------------------
@@ -617,6 +619,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
+    long long clk0 = 0;
+    unsigned long long ns0 = 0;
+    if (a.clock && blockIdx.x == 0 && tid == 0) {
+        clk0 = clock64();
+        ns0 = global_timer_ns();
+    }
     const int total_pair_tiles = (a.total_tiles + 1) / 2;                       // 256 rows each
     const int eff_tiles = (total_pair_tiles + a.tile_stride - 1) / a.tile_stride;
 
@@ -779,6 +787,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
     __syncthreads();
     cluster_sync_all();    // no CTA leaves (or frees TMEM) while its peer may still touch it
     if (warp == 1) tmem_dealloc_pair(tmem_base, CFG::TMEM_COLS);
+    if (a.clock && blockIdx.x == 0 && tid == 0) {
+        atomicAdd(a.clock, static_cast<unsigned long long>(clock64() - clk0));
+        atomicAdd(a.clock + 1, global_timer_ns() - ns0);
+        atomicAdd(a.clock + 2, 1ull);
+    }
 }
 
 // ---- per-query selection in two levels ----------------------------------------------------

@@ -110,6 +110,7 @@ struct clipdb_ctx {
     unsigned long long batch_bad_rows = 0;  // zero-norm / non-finite rows found when the copy was built
     Buffer bf16_rows, bad_rows, bq_queries, bq_qnorm, bq_scores, bq_thr, bq_flags, bq_count, bq_cand, bq_parts, bq_qerr, row_err;
     Buffer bq_cand_u, bq_margin, bq_surv, bq_surv_count, bq_tilectr;
+    Buffer bq_clock;                     // 3 x uint64: SM cycles, ns, launches of the profiled contraction launches
     CUtensorMap map_rows, map_q, map_qhalf[3];   // query-half boxes for 64 / 128 / 256 queries per pass
     int64_t bq_sample_groups_used = 0;  // groups the last pass A wrote
     int64_t batch_min_nq = 2;       // clipdb_search switches to the batched path from this nq (one batch
@@ -972,6 +973,12 @@ int batch_search_device_locked(clipdb_ctx *c, const float *d_queries, int32_t nq
     CU_TRY(c, cudaMemsetAsync(c->bq_count.p, 0, BQ_N * sizeof(unsigned int), c->stream));
     g.tile_stride = 1;
     g.tile_counter = static_cast<unsigned int *>(c->bq_tilectr.p) + 1;
+    if (c->profiling) {
+        const bool fresh = c->bq_clock.p == nullptr;
+        RC_TRY(ensure_device(c, c->bq_clock, 3 * sizeof(unsigned long long)));
+        if (fresh) CU_TRY(c, cudaMemsetAsync(c->bq_clock.p, 0, 3 * sizeof(unsigned long long), c->stream));
+        g.clock = static_cast<unsigned long long *>(c->bq_clock.p);
+    }
     RC_TRY(profile_mark(c, true));
     if (pair) {
         const int ptiles = (tiles + 1) / 2;
@@ -1131,7 +1138,7 @@ void clipdb_destroy(clipdb_ctx *c) {
                           &c->cub_tmp, &c->d_query, &c->d_results, &c->d_blend_in, &c->d_blend_flags, &c->bf16_rows,
                           &c->bad_rows, &c->bq_queries, &c->bq_qnorm, &c->bq_scores, &c->bq_thr, &c->bq_flags,
                           &c->bq_count, &c->bq_cand, &c->bq_parts, &c->bq_qerr, &c->row_err, &c->bq_cand_u, &c->bq_margin,
-                          &c->bq_surv, &c->bq_surv_count, &c->bq_tilectr, &c->xchg_stats};
+                          &c->bq_surv, &c->bq_surv_count, &c->bq_tilectr, &c->xchg_stats, &c->bq_clock};
         for (Buffer *b : bufs) free_buffer(*b);
         if (c->pinned.p) cudaFreeHost(c->pinned.p);
         if (c->stage.p) cudaFreeHost(c->stage.p);
@@ -2037,6 +2044,22 @@ int clipdb_profile_read(clipdb_ctx *c, double *scan_ms_total, int64_t *scans) {
     RC_TRY(profile_fold(c));
     *scan_ms_total = c->prof_ms;
     *scans = c->prof_scans;
+    return CLIPDB_OK;
+}
+
+int clipdb_profile_clock(clipdb_ctx *c, double *sm_cycles, double *nanoseconds, int64_t *launches) {
+    if (!c) return CLIPDB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    unsigned long long h[3] = {0, 0, 0};
+    if (c->bq_clock.p) {
+        CU_TRY(c, cudaMemcpyAsync(h, c->bq_clock.p, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(c, cudaMemsetAsync(c->bq_clock.p, 0, sizeof h, c->stream));
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+    if (sm_cycles) *sm_cycles = static_cast<double>(h[0]);
+    if (nanoseconds) *nanoseconds = static_cast<double>(h[1]);
+    if (launches) *launches = static_cast<int64_t>(h[2]);
     return CLIPDB_OK;
 }
 

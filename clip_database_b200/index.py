@@ -134,6 +134,13 @@ class GpuIndex:
         self._check(self._L.clipdb_profile_read(self._ctx, ctypes.byref(ms), ctypes.byref(n)))
         return float(ms.value), int(n.value)
 
+    def profile_clock(self) -> Tuple[Optional[float], int]:
+        """(SM clock in MHz the profiled contraction launches of the batched path ran at — %clock64 over
+        %globaltimer inside the kernel —, launches) since the last call."""
+        cyc, ns, n = ctypes.c_double(0.0), ctypes.c_double(0.0), ctypes.c_int64(0)
+        self._check(self._L.clipdb_profile_clock(self._ctx, ctypes.byref(cyc), ctypes.byref(ns), ctypes.byref(n)))
+        return (cyc.value / ns.value * 1e3 if ns.value > 0 else None), int(n.value)
+
     # ---- row store ------------------------------------------------------------------
     def load(self, rows, rowids=None) -> None:
         """Copy ``rows`` (numpy ``[n, dim]`` float32, or a torch tensor on any device)

@@ -347,6 +347,11 @@ int clipdb_exchange_stats(clipdb_ctx *ctx, int32_t enable, int32_t reset, double
  * since profiling was (re)enabled.  bench.py derives roofline.achieved from it. */
 int clipdb_profile(clipdb_ctx *ctx, int32_t enable);
 int clipdb_profile_read(clipdb_ctx *ctx, double *scan_ms_total, int64_t *scans);
+/* The SM clock the batched path's contraction actually ran at: while profiling is enabled, CTA 0 of every
+ * filter-pass launch (batch_gemm_pair_kernel<FILTER>) reads %clock64 and %globaltimer at entry and exit.  Returns
+ * the sums since the last call (and clears them): sm_cycles / nanoseconds = GHz.  The tensor pipe's peak scales
+ * with that clock, and under the board's power cap it sits far below the 1965 MHz the datasheet peak assumes. */
+int clipdb_profile_clock(clipdb_ctx *ctx, double *sm_cycles, double *nanoseconds, int64_t *launches);
 
 #ifdef __cplusplus
 }
