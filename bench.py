@@ -1108,6 +1108,7 @@ def run_single_gpu(args, torch, device, local_rank):
         rec["single_query_through_bf16_preselect"] = {
             "ms_per_step": one["ms_per_step"], "queries_per_s": one["value"], "k": k,
             "hbm_GBps_bf16_store": one["roofline"]["achieved"], "frac_of_hbm_peak": one["roofline"]["frac"],
+            "sm_mhz_in_kernel": one["roofline"].get("sm_mhz_in_kernel"),
             "e2e_ms_per_step": one["e2e"]["ms_per_step"], "gpu_launches": one["gpu_launches"]}
         idx.set_option("batch_min_nq", 2)
         line["configs2"] = rec
