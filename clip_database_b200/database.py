@@ -521,7 +521,10 @@ class ImageDatabase:
                                 " WHERE (i.file_path LIKE ? ESCAPE '\\')", ("x%",)).fetchall()
         finally:
             conn.close()
-        return bool(plan) and str(plan[0][-1]).startswith("SCAN i")
+        # "SCAN i USING [COVERING] INDEX sqlite_autoindex_images_1" = file_path order; a bare "SCAN i" would be a
+        # table scan in id order, "SCAN be" the unfiltered statement's binary_embeddings rowid order
+        first = str(plan[0][-1]) if plan else ""
+        return first.startswith("SCAN i") and "INDEX" in first and "autoindex_images" in first
 
     def _binary_fallback(self, embedding1, k, embedding2, weights, negative_embeddings, negative_weights,
                          filter_folders, timings) -> Result:
