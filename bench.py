@@ -1318,6 +1318,7 @@ def run_sharded(args, torch, dist, device, rank, local_rank, world):
     barrier()
     ms_step = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
     scan_ms, scans = idx.profile_read()
+    kernel_mhz = idx.profile_clock()[0] if bf16_primary else None
     idx.profile(False)
     launches = idx.launch_count - launches0
     reranked = float(idx.batch_stats()[1][0]) if bf16_primary else 0.0
@@ -1365,7 +1366,8 @@ def run_sharded(args, torch, dist, device, rank, local_rank, world):
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "frac_of_nominal_8000": achieved / 8000.0, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": n * row_bytes, "avg_launch_ms": scan_avg,
-                         "launches_timed": int(scans), "traffic": None, "traffic_source": None},
+                         "launches_timed": int(scans), "sm_mhz_in_kernel": kernel_mhz,
+                         "traffic": None, "traffic_source": None},
             "clocks": sampler.summary() if sampler else None,
         }
         if parity is not None:
