@@ -1191,8 +1191,32 @@ def run_sharded(args, torch, dist, device, rank, local_rank, world):
         idx.attach(rows, rowid_base=first_rowid)
     else:
         rows = None
-        idx.reserve(n, DIM, explicit_rowids=True, placement="host", device_rows=plan["hbm_fp32_rows"])
-        idx.enable_batch()                      # every append converts its rows into the bf16 copy
+        # the tiers are sized from what the box reports; if it then refuses the allocation anyway (a cgroup limit,
+        # locked-memory limits, fragmentation) every rank falls back to a smaller shard together, and says so
+        while True:
+            try:
+                idx.reserve(n, DIM, explicit_rowids=True, placement="host", device_rows=plan["hbm_fp32_rows"])
+                idx.enable_batch()              # every append converts its rows into the bf16 copy
+                ok = True
+            except Exception as e:              # noqa: BLE001
+                ok = False
+                why = str(e)
+            if all(gather_objects(ok)):
+                break
+            idx.close()
+            idx = GpuIndex(local_rank)
+            torch.cuda.empty_cache()
+            if n <= 4 * CHUNK_ROWS:
+                return fail("store allocation", {"rank": rank, "error": why if not ok else "another rank failed"})
+            n = max(4 * CHUNK_ROWS, int(n * 0.8) // CHUNK_ROWS * CHUNK_ROWS)
+            shrink = plan["rows_per_gpu"] - n
+            plan = dict(plan, rows_per_gpu=n, rows_total=n * world,
+                        host_fp32_rows=max(0, plan["host_fp32_rows"] - shrink),
+                        note="the box refused the planned allocation: shard reduced to %d rows per GPU" % n)
+            plan["hbm_fp32_rows"] = (n - plan["host_fp32_rows"]) & ~127
+            plan["host_fp32_rows"] = n - plan["hbm_fp32_rows"]
+            first_rowid = 1 + rank * n
+            plants = (7, n // 2, n - 1) if subs else ()
 
         def commit(chunk, pos):
             ids = torch.arange(first_rowid + pos, first_rowid + pos + chunk.shape[0], dtype=torch.int64, device=device)
