@@ -69,20 +69,34 @@ def is_stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Build ``libclipdb_b200.so`` if missing or compiled from other sources than the ones here."""
+    """Build ``libclipdb_b200.so`` if missing or compiled from other sources than the ones here.  Safe when
+    several processes get here together (one rank per GPU importing the package at the same moment): the build
+    is serialised by a file lock, whoever waited re-checks staleness, and the library appears atomically."""
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-DCLIPDB_SOURCE_HASH=\"%s\"" % source_hash(), "-I", INCLUDE, "-o", LIB_PATH]
-    cmd += [os.path.join(CSRC, s) for s in SOURCES]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd), flush=True)
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if proc.returncode != 0:
-        sys.stderr.write(proc.stdout + proc.stderr)
-        raise RuntimeError("nvcc failed building " + LIB_NAME)
-    if verbose:
-        sys.stderr.write(proc.stderr)
+    import fcntl
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():      # another process built it while this one waited
+                return LIB_PATH
+            tmp = LIB_PATH + ".%d.tmp" % os.getpid()
+            cmd = [_nvcc()] + NVCC_FLAGS + ["-DCLIPDB_SOURCE_HASH=\"%s\"" % source_hash(), "-I", INCLUDE, "-o", tmp]
+            cmd += [os.path.join(CSRC, s) for s in SOURCES]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+                print(" ".join(cmd), flush=True)
+            proc = subprocess.run(cmd, capture_output=True, text=True)
+            if proc.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                sys.stderr.write(proc.stdout + proc.stderr)
+                raise RuntimeError("nvcc failed building " + LIB_NAME)
+            os.replace(tmp, LIB_PATH)
+            if verbose:
+                sys.stderr.write(proc.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 

@@ -495,14 +495,21 @@ constexpr int BP_SMEM_LIMIT = 232448;                      // 227 KB per CTA
 template <int NQ>
 struct PairCfg {
     static_assert(NQ == 64 || NQ == 128 || NQ == 256, "queries per pass");
-    static constexpr int B_BYTES = (NQ / 2) * BQ_BLOCK_K * 2;   // this CTA's NQ/2 queries
-    static constexpr int STAGE_BYTES = BP_A_BYTES + B_BYTES;
-    static constexpr int FIT = (BP_SMEM_LIMIT - 64 - BQ_HEADER - 1024 - BQ_QUEUE_SMEM) / STAGE_BYTES;
-    static constexpr int STAGES = FIT > 10 ? 10 : FIT;          // 6 / 8 / 10 for NQ = 256 / 128 / 64
-    static constexpr int SMEM_BYTES = BQ_HEADER + STAGES * STAGE_BYTES + 1024 + BQ_QUEUE_SMEM;
+    static constexpr int B_BYTES = (NQ / 2) * BQ_BLOCK_K * 2;   // this CTA's NQ/2 queries, one k-block
+    // NQ = 64: this CTA's 32 queries are 73,728 B over all 18 k-blocks — they stay RESIDENT in shared memory for the
+    // whole launch (loaded once) and the ring carries rows only.  The pass is an HBM stream of the bf16 store; with
+    // the query block re-read per tile it pushed 25 % more bytes through L2 than it read from DRAM (28.8 vs 23.0 GB
+    // per launch, profiles/r02_batch_gemm_nq64_ncu.md) and twice the TMA operations.
+    static constexpr bool Q_RESIDENT = NQ == 64;
+    static constexpr int Q_BYTES = Q_RESIDENT ? BQ_K_BLOCKS * B_BYTES : 0;
+    static constexpr int STAGE_BYTES = BP_A_BYTES + (Q_RESIDENT ? 0 : B_BYTES);
+    static constexpr int FIT = (BP_SMEM_LIMIT - 64 - BQ_HEADER - 1024 - BQ_QUEUE_SMEM - Q_BYTES) / STAGE_BYTES;
+    static constexpr int STAGES = FIT > 10 ? 10 : FIT;          // 6 / 8 / 8 for NQ = 256 / 128 / 64
+    static constexpr int SMEM_BYTES = BQ_HEADER + Q_BYTES + STAGES * STAGE_BYTES + 1024 + BQ_QUEUE_SMEM;
     static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((NQ >> 3) << 17) | ((256u >> 4) << 24);
     static constexpr int TMEM_COLS = 2 * NQ;                    // two accumulator buffers
-    static_assert(STAGES * 16 + 32 + 8 <= 1024, "barriers must fit below the thresholds");
+    static_assert(STAGES * 16 + 32 + 8 <= 448, "barriers must fit below the query barrier");
+    static_assert(Q_BYTES % 1024 == 0, "the ring must stay 1024-byte aligned behind the resident queries");
 };
 constexpr uint32_t BP_PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> CTA 0
 
@@ -609,12 +616,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
     // the producer cannot run ahead of iteration it-1's MMAs (the operand ring is shorter than a
     // tile), those waited for the accumulator freed at the END of epilogue it-3.
     constexpr int BP_TQ = 4;
+    uint64_t *q_bar = reinterpret_cast<uint64_t *>(bq_smem_raw + 448);   // resident queries landed (leader's copy counts)
     uint64_t *tq_full = reinterpret_cast<uint64_t *>(bq_smem_raw + 512);
     volatile int *tile_ring = reinterpret_cast<volatile int *>(bq_smem_raw + 512 + BP_TQ * 8);
     float *thr_s = reinterpret_cast<float *>(bq_smem_raw + 1024);
     const uint32_t raw_addr = smem_u32(bq_smem_raw);
-    const uint32_t tiles_addr = (raw_addr + BQ_HEADER + 1023u) & ~1023u;
-    uint8_t *tiles = bq_smem_raw + (tiles_addr - raw_addr);
+    const uint32_t q_addr = (raw_addr + BQ_HEADER + 1023u) & ~1023u;     // resident query block (Q_RESIDENT), then the ring
+    const uint32_t tiles_addr = q_addr + CFG::Q_BYTES;
+    uint8_t *q_tiles = bq_smem_raw + (q_addr - raw_addr);
+    uint8_t *tiles = q_tiles + CFG::Q_BYTES;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
@@ -638,6 +648,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
             mbar_init(&tmem_empty[b], 8);   // 4 epilogue warps in each of the two CTAs
         }
         for (int i = 0; i < BP_TQ; i++) mbar_init(&tq_full[i], 1);
+        mbar_init(q_bar, 1);
         mbar_fence_init();
     }
     if (!DUMP)
@@ -664,6 +675,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
                 }
                 return t < static_cast<unsigned>(eff_tiles) ? static_cast<int>(t) : -1;
             };
+            if (CFG::Q_RESIDENT) {
+                // this CTA's half of the query block, all 18 k-blocks, once; both CTAs' bytes are credited to the
+                // leader's barrier, which the MMA issuer waits on before its first instruction (and always waits
+                // on, so no CTA can leave while a copy into its shared memory is still in flight)
+                if (leader) mbar_arrive_expect_tx(q_bar, 2 * CFG::Q_BYTES);
+                for (int kb = 0; kb < BQ_K_BLOCKS; kb++)
+                    tma_load_2d_pair(q_tiles + kb * CFG::B_BYTES, &map_qhalf, kb * BQ_BLOCK_K,
+                                     static_cast<int>(rank) * (NQ / 2), q_bar);
+            }
             int s = 0;
             uint32_t phase = 0;
             int next = leader ? claim() : 0;
@@ -689,8 +709,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
                     uint8_t *stage = tiles + s * BP_STAGE_BYTES;
                     tma_load_2d_pair_hint(stage, &map_rows, 0, (tile128 * BQ_K_BLOCKS + kb) * BQ_M, &full_bar[s],
                                           stream_policy);
-                    tma_load_2d_pair(stage + BP_A_BYTES, &map_qhalf, kb * BQ_BLOCK_K, static_cast<int>(rank) * (NQ / 2),
-                                     &full_bar[s]);
+                    if (!CFG::Q_RESIDENT)
+                        tma_load_2d_pair(stage + BP_A_BYTES, &map_qhalf, kb * BQ_BLOCK_K,
+                                         static_cast<int>(rank) * (NQ / 2), &full_bar[s]);
                     if (++s == BP_STAGES) {
                         s = 0;
                         phase ^= 1u;
@@ -703,6 +724,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
         if (leader && lane == 0) {
             int s = 0;
             uint32_t phase = 0;
+            if (CFG::Q_RESIDENT) {
+                mbar_wait_cluster(q_bar, 0);
+                tc_fence_after();
+            }
             for (int it = 0;; it++) {
                 mbar_wait(&tq_full[it & (BP_TQ - 1)], static_cast<uint32_t>(it / BP_TQ) & 1u);
                 if (tile_ring[it & (BP_TQ - 1)] < 0) break;
@@ -714,7 +739,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
                     mbar_wait_cluster(&full_bar[s], phase);
                     tc_fence_after();
                     const uint32_t a_addr = tiles_addr + s * BP_STAGE_BYTES;
-                    const uint32_t b_addr = a_addr + BP_A_BYTES;
+                    const uint32_t b_addr = CFG::Q_RESIDENT ? q_addr + kb * CFG::B_BYTES : a_addr + BP_A_BYTES;
 #pragma unroll
                     for (int k = 0; k < BQ_BLOCK_K / BQ_UMMA_K; k++) {
                         umma_bf16_pair(tmem_d, umma_desc_sw128(a_addr + k * BQ_UMMA_K * 2),
