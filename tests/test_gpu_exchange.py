@@ -195,3 +195,49 @@ def test_single_process_multi_gpu_batch():
     assert np.array_equal(got.rowids, want.rowids)
     assert np.array_equal(got.distances.view(np.uint32), want.distances.view(np.uint32))
     assert got.rowids[12, :2].tolist() == [21, n - 2]
+
+
+def test_multi_gpu_index_recovers_when_one_shard_fails_to_launch():
+    """a host-side failure on shard r after shards < r have launched used to leave the shards'
+    sequence numbers apart for good.  Now refusable requests are refused before the first launch, and a failure
+    in the middle resynchronises the exchange: the next search works."""
+    assert have_gpu()
+    import torch
+    from clip_database_b200 import GpuIndex
+    from clip_database_b200.multigpu import MultiGpuIndex
+    n_dev = torch.cuda.device_count()
+    devices = list(range(min(n_dev, 4))) if n_dev > 1 else [0, 0, 0]
+    n = 30_000
+    rows = synth.unit_rows(n, DIM, 515)
+    queries = synth.unit_rows(3, DIM, 516)
+    with GpuIndex(0) as whole:
+        whole.load(rows, np.arange(1, n + 1))
+        want = whole.search(queries, 10)
+    with MultiGpuIndex(devices, scan_ctas=None if n_dev > 1 else 24, timeout_ms=3000) as multi:
+        multi.load(rows, np.arange(1, n + 1))
+        ids, dist, _ = multi.search(queries[0], 10)
+        assert np.array_equal(ids, want.rowids[0])
+        # refused up front: nothing was launched, nothing to repair
+        before = multi.launch_count
+        with pytest.raises(ValueError):
+            multi.search(queries[1], 10, use_mask=True)                  # no mask installed
+        with pytest.raises(ValueError):
+            multi.search(queries[1][:100], 10)                          # wrong dimension
+        assert multi.launch_count == before
+        # a failure in the middle: shard 0 launches, the last shard raises
+        victim = multi.shards[-1]
+        real = victim.search_sharded_device
+        calls = {"n": 0}
+
+        def flaky(*a, **kw):
+            calls["n"] += 1
+            raise RuntimeError("injected launch failure")
+        victim.search_sharded_device = flaky
+        with pytest.raises(RuntimeError, match="injected"):
+            multi.search(queries[1], 10)
+        victim.search_sharded_device = real
+        assert calls["n"] == 1
+        for qi in range(3):                                              # back in step
+            ids, dist, _ = multi.search(queries[qi], 10)
+            assert np.array_equal(ids, want.rowids[qi])
+            assert np.array_equal(dist.view(np.uint32), want.distances[qi].view(np.uint32))
