@@ -181,14 +181,12 @@ class ImageDatabase:
         lead = self.index.shards[0] if hasattr(self.index, "shards") else self.index
 
         def sink(chunk: loader.StoreChunk) -> None:
-            m, dim = chunk.rows.shape
-            if stage["buf"] is None or stage["buf"].shape[1] != dim:
-                stage["buf"] = lead.stage_buffer(loader.CHUNK_ROWS, dim)
-            for at in range(0, m, loader.CHUNK_ROWS):
-                part = chunk.rows[at:at + loader.CHUNK_ROWS]
-                buf = stage["buf"][:part.shape[0]]
-                buf[:] = part
-                append(buf, chunk.rowids[at:at + loader.CHUNK_ROWS])    # copies before it returns
+            m, dim = len(chunk), chunk.dim
+            if stage["buf"] is None or stage["buf"].shape[1] != dim or stage["buf"].shape[0] < m:
+                stage["buf"] = lead.stage_buffer(max(loader.CHUNK_ROWS, m), dim)
+            buf = stage["buf"][:m]
+            chunk.write_rows(buf)                      # blobs -> pinned memory, one memcpy per row
+            append(buf, chunk.rowids)                  # copies before it returns
         return loader.stream_store(self.db_path, sink, expect_dim=expect_dim, min_rowid=lo, max_rowid=hi, conn=conn)
 
     def reload(self) -> None:

@@ -33,14 +33,45 @@ _MIN_ROWID = -(1 << 63)
 _MAX_ROWID = (1 << 63) - 1
 
 
-@dataclass
 class StoreChunk:
-    """Consecutive joined rows in scan order."""
-    rowids: np.ndarray        # int64 [m], ascending
-    image_ids: np.ndarray     # int64 [m]
-    mtimes: np.ndarray        # float64 [m]  images.last_modified (refresh compares it)
-    file_paths: List[str]     # [m]
-    rows: np.ndarray          # float32 [m, dim] (read-only view of the fetched blobs)
+    """Consecutive joined rows in scan order.  The vectors are held as the blobs SQLite returned; ``write_rows``
+    copies them straight into a caller buffer (the pinned staging buffer of the GPU load: no intermediate joined
+    copy), ``rows`` materialises a float32 matrix for host-side users."""
+    __slots__ = ("rowids", "image_ids", "mtimes", "file_paths", "blobs", "dim", "_rows")
+
+    def __init__(self, rowids, image_ids, mtimes, file_paths, blobs=None, dim=0, rows=None):
+        self.rowids = rowids          # int64 [m], ascending
+        self.image_ids = image_ids    # int64 [m]
+        self.mtimes = mtimes          # float64 [m]  images.last_modified (refresh compares it)
+        self.file_paths = file_paths  # [m]
+        self.blobs = blobs            # m little-endian float32 blobs of dim * 4 bytes (or None when built from rows)
+        self.dim = int(dim if rows is None else rows.shape[1])
+        self._rows = rows
+
+    def __len__(self) -> int:
+        return len(self.rowids)
+
+    @property
+    def rows(self) -> np.ndarray:
+        """float32 [m, dim] (read-only view of one joined copy of the blobs)."""
+        if self._rows is None:
+            self._rows = np.frombuffer(b"".join(self.blobs), dtype="<f4").reshape(len(self.blobs), self.dim)
+        return self._rows
+
+    def write_rows(self, out: np.ndarray) -> None:
+        """Copy the vectors into ``out`` (C-contiguous float32 ``[m, dim]``), one memcpy per row."""
+        m = len(self.rowids)
+        if out.shape != (m, self.dim) or out.dtype != np.float32 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float32 [m, dim] array")
+        if self._rows is not None or self.blobs is None:
+            out[:] = self.rows
+            return
+        dst = memoryview(out).cast("B")
+        step = self.dim * 4
+        at = 0
+        for blob in self.blobs:
+            dst[at:at + step] = blob
+            at += step
 
 
 @dataclass
@@ -296,11 +327,10 @@ def iter_store(conn: sqlite3.Connection, min_rowid: Optional[int] = None, max_ro
                     raise ValueError(f"vec0 rowid {rowid}: blob length {len(blob)} is not float32[]")
                 if len(blob) != st.dim * 4:
                     raise ValueError(f"vec0 rowid {rowid}: {len(blob) // 4} floats, expected {st.dim}")
-        rows = np.frombuffer(b"".join(blobs), dtype="<f4").reshape(len(blobs), st.dim)
         st.joined_rows += len(ids)
         whole = len(at) == len(m_ids)
         yield StoreChunk(ids, m_image if whole else m_image[at], m_mtime if whole else m_mtime[at],
-                         m_paths if whole else [m_paths[i] for i in at.tolist()], rows)
+                         m_paths if whole else [m_paths[i] for i in at.tolist()], blobs=blobs, dim=st.dim)
 
 
 def read_mapping(conn: sqlite3.Connection, min_rowid: Optional[int] = None, max_rowid: Optional[int] = None
@@ -371,15 +401,15 @@ def read_rows_by_rowid(conn: sqlite3.Connection, rowids: Sequence[int]) -> Itera
             if keep.any():
                 idx = np.flatnonzero(keep)
                 yield StoreChunk(chunk.rowids[idx], chunk.image_ids[idx], chunk.mtimes[idx],
-                                 [chunk.file_paths[t] for t in idx.tolist()], chunk.rows[idx])
+                                 [chunk.file_paths[t] for t in idx.tolist()], rows=chunk.rows[idx])
         i = j + 1
 
 
 def stream_store(db_path: str, sink, expect_dim: Optional[int] = None, min_rowid: Optional[int] = None,
                  max_rowid: Optional[int] = None, chunk_rows: int = CHUNK_ROWS,
                  conn: Optional[sqlite3.Connection] = None) -> HostStore:
-    """Feed every chunk to ``sink(chunk)`` (which copies what it needs: ``chunk.rows`` dies with the next
-    fetch) and return the store's metadata with ``rows=None``."""
+    """Feed every chunk to ``sink(chunk)`` (which copies what it needs, e.g. ``chunk.write_rows(buffer)``) and
+    return the store's metadata with ``rows=None``."""
     if conn is None:
         with snapshot(db_path) as own:
             return stream_store(db_path, sink, expect_dim, min_rowid, max_rowid, chunk_rows, own)
@@ -411,9 +441,9 @@ def read_store(db_path: str, expect_dim: Optional[int] = None, min_rowid: Option
 
         def sink(chunk: StoreChunk) -> None:
             if box["rows"] is None:
-                box["rows"] = np.empty((bound, chunk.rows.shape[1]), dtype=np.float32)
-            m = chunk.rows.shape[0]
-            box["rows"][box["n"]:box["n"] + m] = chunk.rows
+                box["rows"] = np.empty((bound, chunk.dim), dtype=np.float32)
+            m = len(chunk)
+            chunk.write_rows(box["rows"][box["n"]:box["n"] + m])
             box["n"] += m
         host = stream_store(db_path, sink, expect_dim, min_rowid, max_rowid, CHUNK_ROWS, conn)
     rows = box["rows"]
