@@ -169,7 +169,10 @@ def plan_store(args, n_gpus):
     if kind == "bf16-primary":
         # bf16 copy resident (2304 B/row); the float32 rows (4608 B/row, read only by the re-rank) fill what
         # is left of HBM and continue in pinned host memory
-        host_budget = int((host_mem_available_bytes() or 200_000_000_000) * 0.80) // n_gpus
+        # MemAvailable moves by a few hundred MB between two looks; rounding it down to whole 8 GB keeps the plan
+        # (and with it `config`) identical for the two arms of a run
+        avail = (host_mem_available_bytes() or 200_000_000_000) // 8_000_000_000 * 8_000_000_000
+        host_budget = int(avail * 0.80) // n_gpus
 
         def split(r):
             in_hbm = max(0, min(r, (budget - r * BF16_ROW_BYTES) // ROW_BYTES)) & ~127
