@@ -1378,6 +1378,11 @@ def run_sharded(args, torch, dist, device, rank, local_rank, world):
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16 pre-select + f32 re-rank" if bf16_primary else "f32",
             "data": "synthetic" if args.data == "uniform" else "synthetic, clustered (1024 clusters, queries near stored rows)",
             "config": workload_config(args, plan, world),
+            "scaling_note": ("value is a RATE (bytes scanned per second), so v_N / (N * v_1) compares per-GPU scan rates; "
+                             "the store is BASELINE configs[4] at its stated size (%d rows in total at every N > 1: per-GPU "
+                             "rows shrink as N grows), while N = 1 is configs[1] (10M rows: 100M do not fit one GPU); "
+                             "fixed-size strong scaling of the 10M-row store is the `strong` sub-record"
+                             % plan["rows_total"]),
             "queries_per_s": 1e3 / ms_step,
             "algorithmic_bytes_per_query": bytes_per_query,
             "equivalent_fp32_scan_GBps": plan["rows_total"] * ROW_BYTES / 1e9 / (ms_step / 1e3),
