@@ -1226,6 +1226,14 @@ int clipdb_get_option(clipdb_ctx *c, const char *name, int64_t *value) {
         *value = c->sm_count;
         return CLIPDB_OK;
     }
+    if (name && (!strcmp(name, "device_free_bytes") || !strcmp(name, "device_total_bytes"))) {
+        // read-only: what a loader needs to decide between an all-HBM store and a tiered one
+        DeviceGuard g(c->device);
+        size_t free_b = 0, total_b = 0;
+        CU_TRY(c, cudaMemGetInfo(&free_b, &total_b));
+        *value = static_cast<int64_t>(name[7] == 'f' ? free_b : total_b);
+        return CLIPDB_OK;
+    }
     int64_t *slot = option_slot(c, name);
     if (!slot) return fail(c, CLIPDB_ERR_INVALID, "unknown option '%s'", name ? name : "(null)");
     *value = *slot;

@@ -126,13 +126,18 @@ class ImageDatabase:
     def __init__(self, db_path: str, device: int = 0, embedder: Optional[Embedder] = None,
                  nan_policy: str = "reference", verbose: bool = False,
                  binary_score_mode: str = "reference", batch_store: bool = False,
-                 devices: Optional[Sequence[int]] = None):
+                 devices: Optional[Sequence[int]] = None, hbm_budget_bytes: Optional[int] = None):
         """``batch_store=True`` also keeps the bf16 copy of the store (half its size again) and sends
         every search — single queries included — through the tensor-core pre-selection + exact
         re-rank: same results, about half the latency per query, and ``search_embeddings`` answers
         many sessions' queries in one pass.  ``devices=[0, 1, ...]`` row-shards the store over
         several GPUs of the box from this one process (``multigpu.MultiGpuIndex``: one launch per
-        GPU per query, candidates exchanged over NVLink inside the scan kernel)."""
+        GPU per query, candidates exchanged over NVLink inside the scan kernel).
+        A store whose float32 rows do not fit the GPU next to the bf16 copy is loaded TIERED when
+        ``batch_store=True``: the bf16 copy and as many float32 rows as fit stay in HBM, the rest of the float32
+        rows go to pinned host memory and are only touched by the exact re-rank (a few hundred rows per query) —
+        same answers, about 35M images per B200 become 70M.  ``hbm_budget_bytes`` overrides the free-memory
+        reading that decision is based on (tests)."""
         if nan_policy not in ("reference", "exclude"):
             raise ValueError("nan_policy must be 'reference' or 'exclude'")
         if binary_score_mode not in ("reference", "popcount"):
@@ -140,6 +145,8 @@ class ImageDatabase:
                              "computes it) or 'popcount'")
         self.binary_score_mode = binary_score_mode
         self.batch_store = bool(batch_store)
+        self.hbm_budget_bytes = hbm_budget_bytes
+        self.placement = "device"          # or "tiered" (see reload)
         self._codes = None                 # loader.HostCodes once the sign-code fallback is needed
         self._code_mask_key: Optional[Tuple[str, ...]] = None
         self.db_path = db_path
@@ -189,6 +196,27 @@ class ImageDatabase:
             append(buf, chunk.rowids)                  # copies before it returns
         return loader.stream_store(self.db_path, sink, expect_dim=expect_dim, min_rowid=lo, max_rowid=hi, conn=conn)
 
+    def _reserve(self, index, rows_hint: int, dim: int) -> str:
+        """Reserve room for ``rows_hint`` rows on ``index``: all in HBM when they fit (next to the bf16 copy if one
+        is wanted), else — with ``batch_store`` — tiered.  Returns "device" or "tiered"."""
+        need32 = rows_hint * dim * 4
+        need16 = rows_hint * dim * 2 if (self.batch_store and dim == schema.EMBEDDING_DIM) else 0
+        free = self.hbm_budget_bytes if self.hbm_budget_bytes is not None else index.get_option("device_free_bytes")
+        slack = min(2 << 30, free // 8)            # workspaces, candidate lists, fragmentation
+        if need32 + need16 + slack <= free:
+            index.reserve(rows_hint, dim, explicit_rowids=True)
+            return "device"
+        if need16 and need16 + slack < free:
+            device_rows = max(0, (free - need16 - slack) // (dim * 4))
+            index.reserve(rows_hint, dim, explicit_rowids=True, placement="host", device_rows=device_rows)
+            index.enable_batch()                   # every append converts its rows: one pass builds both copies
+            index.set_option("batch_min_nq", 1)    # every search pre-selects on the resident bf16 copy
+            return "tiered"
+        raise MemoryError(
+            f"{rows_hint} rows x {dim} float32 = {need32 / 1e9:.1f} GB do not fit the GPU ({free / 1e9:.1f} GB free)"
+            + ("" if need16 else "; batch_store=True keeps only a bf16 copy resident (half the bytes) and tiers the "
+                                 "float32 rows into host memory") + "; or shard over more GPUs with devices=[...]")
+
     def reload(self) -> None:
         """(Re)read the whole database into HBM, streamed: every chunk of rows goes from SQLite through a pinned
         staging buffer straight into the resident store.  With several GPUs the shard boundaries are computed
@@ -202,6 +230,7 @@ class ImageDatabase:
             self._data_version = loader.data_version(self._watch_conn())
             mapped = int(conn.execute("SELECT COUNT(*) FROM image_embeddings").fetchone()[0])
             parts = []
+            placed: List[str] = []
             if multi and mapped > 0:
                 ranges, n_mapped = loader.plan_shards(conn, world)
                 if 0 < n_mapped < world:
@@ -212,7 +241,7 @@ class ImageDatabase:
 
                     def append(rows, rowids, shard=shard, state=state):
                         if not state["reserved"]:
-                            shard.reserve(max(n_mapped // world + 1, rows.shape[0]), rows.shape[1], explicit_rowids=True)
+                            placed.append(self._reserve(shard, max(n_mapped // world + 1, rows.shape[0]), rows.shape[1]))
                             state["reserved"] = True
                         shard.append(rows, rowids)
                         shard.synchronize()
@@ -228,7 +257,7 @@ class ImageDatabase:
 
                 def append(rows, rowids):
                     if not state["reserved"]:
-                        single.reserve(max(mapped, rows.shape[0]), rows.shape[1], explicit_rowids=True)
+                        placed.append(self._reserve(single, max(mapped, rows.shape[0]), rows.shape[1]))
                         state["reserved"] = True
                     single.append(rows, rowids)
                     single.synchronize()
@@ -246,12 +275,15 @@ class ImageDatabase:
         self._codes = None
         self._code_mask_key = None
         n = self._rowids.shape[0]
+        self.placement = "tiered" if "tiered" in placed else "device"
         if self.batch_store and n and self.index.dim == schema.EMBEDDING_DIM:
             self.index.enable_batch()
             if not multi:
                 self.index.set_option("batch_min_nq", 1)
+            else:
+                self.index.prefer_batch = self.placement == "tiered"
         self.load_seconds = time.perf_counter() - t0
-        self._log(f"loaded {n} rows ({first.source}) in {self.load_seconds:.2f} s "
+        self._log(f"loaded {n} rows ({first.source}, {self.placement} store) in {self.load_seconds:.2f} s "
                   f"({n / max(self.load_seconds, 1e-9):.0f} rows/s); "
                   f"{sum(p.dropped for p in parts)} vec0 rows without a mapping were skipped")
 

@@ -306,6 +306,11 @@ class MultiGpuIndex:
                      metric="cosine", use_mask: bool = False) -> SearchResult:
         """Blend / negatives on GPU 0 (K3), then the sharded scan."""
         query, _flags = self.shards[0].blend(e1, e2, weights, negatives, negative_weights)
+        if getattr(self, "prefer_batch", False) and getattr(self, "batch_enabled", False) and not use_mask \
+                and 1 <= int(k) <= min(self.FUSED_K_MAX, min(hi - lo for lo, hi in self.bounds)):
+            # tiered shards: the exact scan would stream the host tier over PCIe; the bf16 pre-selection + exact
+            # re-rank gives the same answer from the resident copy
+            return self.search_batch(query[None, :], int(k))
         ids, dist, nan = self.search_any_k(query, int(k), use_mask)
         kc = max(int(k), 0)
         res = SearchResult(np.full((1, kc), -1, dtype=np.int64), np.full((1, kc), np.nan, dtype=np.float32),

@@ -73,7 +73,10 @@ int clipdb_use_own_stream(clipdb_ctx *ctx);
 int clipdb_synchronize(clipdb_ctx *ctx);
 
 /* Tuning knobs for experiments ("scan_variant", "scan_ctas", ...).  Unknown
- * names fail with CLIPDB_ERR_INVALID. */
+ * names fail with CLIPDB_ERR_INVALID.  Read-only names for clipdb_get_option:
+ * "sm_count", "device_free_bytes", "device_total_bytes" (cudaMemGetInfo of the
+ * context's device: what a loader needs to choose between an all-HBM and a
+ * tiered store, see clipdb_reserve_rows). */
 int clipdb_set_option(clipdb_ctx *ctx, const char *name, int64_t value);
 int clipdb_get_option(clipdb_ctx *ctx, const char *name, int64_t *value);
 

@@ -47,9 +47,10 @@ def rescan_modified_file(conn, file_path, new_embedding, mtime):
     return image_id, vec_rowid
 
 
-@pytest.mark.parametrize("devices,batch_store", [(None, False), (None, True), ([0, 0], False)],
-                         ids=["one-gpu", "one-gpu-bf16", "two-shards"])
-def test_refresh_tracks_a_scanner_writing_next_to_it(tmp_path, devices, batch_store):
+@pytest.mark.parametrize("devices,batch_store,budget", [(None, False, None), (None, True, None), ([0, 0], False, None),
+                                                        (None, True, 12_000_000)],
+                         ids=["one-gpu", "one-gpu-bf16", "two-shards", "one-gpu-tiered"])
+def test_refresh_tracks_a_scanner_writing_next_to_it(tmp_path, devices, batch_store, budget):
     assert have_gpu(), "GPU tests selected but no CUDA device is visible"
     from clip_database_b200 import ImageDatabase
     n, k = 3000, 12
@@ -58,7 +59,10 @@ def test_refresh_tracks_a_scanner_writing_next_to_it(tmp_path, devices, batch_st
     db_path = str(tmp_path / "live.db")
     synth.write_reference_db(db_path, rows, paths, drop_mapping_for=[17])
     q = synth.unit_rows(1, DIM, 32)[0]
-    db = ImageDatabase(db_path, device=0, devices=devices, batch_store=batch_store)
+    db = ImageDatabase(db_path, device=0, devices=devices, batch_store=batch_store, hbm_budget_bytes=budget)
+    # a 12 MB "GPU": 13.8 MB of float32 + 6.9 MB of bf16 do not fit -> bf16 copy + 768 float32 rows resident, the
+    # other float32 rows in pinned host memory, every search through the pre-selection + exact re-rank
+    assert db.placement == ("tiered" if budget else "device")
     writer = sqlite3.connect(db_path)
     try:
         first = db.search_embedding(q, k=k, show_duplicates=True)
@@ -225,3 +229,14 @@ def test_loader_streams_a_million_rows(tmp_path):
             assert_same_answer(db.search_embedding(q, k=20, show_duplicates=True), reference_answer(db_path, q, 20))
     finally:
         db.close()
+
+
+def test_a_store_too_large_for_the_gpu_says_what_to_do(tmp_path):
+    assert have_gpu()
+    from clip_database_b200 import ImageDatabase
+    db_path = str(tmp_path / "big.db")
+    synth.write_reference_db(db_path, synth.unit_rows(3000, DIM, 61))
+    with pytest.raises(MemoryError, match="batch_store=True"):
+        ImageDatabase(db_path, device=0, hbm_budget_bytes=12_000_000)
+    with pytest.raises(MemoryError, match="devices="):
+        ImageDatabase(db_path, device=0, batch_store=True, hbm_budget_bytes=5_000_000)
