@@ -166,7 +166,9 @@ class ImageDatabase:
         self._alive: Optional[np.ndarray] = None      # False = the row's mapping is gone (refresh): masked out
         self._watch = None
         self._data_version = -1
+        self._dangling = 0            # mapped rowids (<= the last resident one) that have no vec0 row: see refresh()
         self.load_seconds = 0.0
+        self.reloads = 0
         self._binary_count = 0
         self._vec0_count = 0
         self._mask_key: Optional[Tuple[str, ...]] = None
@@ -275,6 +277,7 @@ class ImageDatabase:
         self._codes = None
         self._code_mask_key = None
         n = self._rowids.shape[0]
+        self._dangling = 0
         self.placement = "tiered" if "tiered" in placed else "device"
         if self.batch_store and n and self.index.dim == schema.EMBEDDING_DIM:
             self.index.enable_batch()
@@ -283,9 +286,23 @@ class ImageDatabase:
             else:
                 self.index.prefer_batch = self.placement == "tiered"
         self.load_seconds = time.perf_counter() - t0
+        self.reloads += 1
         self._log(f"loaded {n} rows ({first.source}, {self.placement} store) in {self.load_seconds:.2f} s "
                   f"({n / max(self.load_seconds, 1e-9):.0f} rows/s); "
                   f"{sum(p.dropped for p in parts)} vec0 rows without a mapping were skipped")
+
+    def _match_mapping(self, mp: "loader.Mapping"):
+        """(index of every resident rowid in the mapping, which resident rowids are still mapped, how many mapped
+        rowids up to the last resident one are NOT resident)."""
+        old = self._rowids
+        n_old = old.shape[0]
+        if n_old == 0 or len(mp.rowids) == 0:
+            return np.zeros(n_old, dtype=np.int64), np.zeros(n_old, dtype=bool), 0
+        at = np.searchsorted(mp.rowids, old)
+        at[at >= len(mp.rowids)] = len(mp.rowids) - 1
+        present = mp.rowids[at] == old
+        mapped_up_to_last = int(np.searchsorted(mp.rowids, int(old[-1]), side="right"))
+        return at, present, mapped_up_to_last - int(present.sum())
 
     def _watch_conn(self):
         """A connection kept open only to read ``PRAGMA data_version``: it changes iff someone else committed."""
@@ -318,15 +335,15 @@ class ImageDatabase:
             old = self._rowids
             n_old = old.shape[0]
             last = int(old[-1]) if n_old else None
-            at = np.searchsorted(mp.rowids, old)
-            at[at >= max(len(mp.rowids), 1)] = max(len(mp.rowids) - 1, 0)
-            present = (mp.rowids[at] == old) if len(mp.rowids) else np.zeros(n_old, dtype=bool)
-            n_present_old = int(present.sum())
+            at, present, dangling = self._match_mapping(mp)
             n_old_in_map = int(np.searchsorted(mp.rowids, last, side="right")) if last is not None else 0
-            if n_old == 0 or n_old_in_map != n_present_old:
-                # a store that was empty, or a mapping that appeared for a rowid we skipped at load time
+            if n_old == 0 or dangling != self._dangling:
+                # a store that was empty, or a mapping that appeared for a rowid we skipped at load time.  Mapped
+                # rowids that still have no vec0 row after a fresh load are permanent: remembered, so that they do
+                # not trigger a reload on every later change of the database
                 conn.execute("ROLLBACK")
                 self.reload()
+                self._dangling = self._match_mapping(mp)[2]
                 return self._rowids.shape[0]
             # retired rows (and rows whose mapping came back)
             alive_before = self._alive if self._alive is not None else np.ones(n_old, dtype=bool)

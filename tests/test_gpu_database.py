@@ -240,3 +240,26 @@ def test_a_store_too_large_for_the_gpu_says_what_to_do(tmp_path):
         ImageDatabase(db_path, device=0, hbm_budget_bytes=12_000_000)
     with pytest.raises(MemoryError, match="devices="):
         ImageDatabase(db_path, device=0, batch_store=True, hbm_budget_bytes=5_000_000)
+
+
+def test_a_mapping_without_a_vector_does_not_cause_reload_after_reload(tmp_path):
+    """A dangling image_embeddings row (its vec0 row is missing) can never be loaded; refresh() must notice once
+    and then leave the store alone."""
+    assert have_gpu()
+    from clip_database_b200 import ImageDatabase
+    rows = synth.unit_rows(500, DIM, 71)
+    db_path = str(tmp_path / "d.db")
+    synth.write_reference_db(db_path, rows)
+    w = sqlite3.connect(db_path)
+    w.execute("DELETE FROM vec0 WHERE rowid = 100")
+    w.commit()
+    with _closing(ImageDatabase(db_path, device=0)) as db:
+        assert db.index.num_rows == 499 and db.reloads == 1
+        for step in range(3):
+            w.execute("UPDATE images SET file_hash = ? WHERE id = 7", (f"h{step}",))     # unrelated commits
+            w.commit()
+            db.refresh()
+            assert db.reloads == 2, "one reload to learn that rowid 100 is permanently unloadable, then none"
+        q = rows[99]                                                                      # the row that is missing
+        assert_same_answer(db.search_embedding(q, k=5, show_duplicates=True), reference_answer(db_path, q, 5))
+    w.close()
