@@ -20,6 +20,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=3000)
     ap.add_argument("--rows", type=int, default=120_000)
+    ap.add_argument("--wrap", action="store_true",
+                    help="start both sequence counters just below 2^32 so the run crosses the uint32 wrap")
+    ap.add_argument("--batch-every", type=int, default=7, help="every n-th iteration is a 48-query batched search")
     args = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(rank)
@@ -28,14 +31,25 @@ def main():
     lo, hi = shard_bounds(args.rows, world)[rank]
     idx = GpuIndex(rank)
     idx.load(rows[lo:hi], np.arange(lo + 1, hi + 1))
+    idx.enable_batch()
     fused = ShardedIndex(CudaShardBackend(idx), fused=True)
     nccl = ShardedIndex(CudaShardBackend(idx), fused=False)
+    if args.wrap:
+        idx.exchange_set_epoch(0xFFFFFF00, 0xFFFFFFF0)      # single-query counter wraps after 255 searches, batched after 15
     queries = synth.unit_rows(64, 1152, 99)
     rng = np.random.default_rng(7)                       # same sequence on every rank
     ks = rng.choice([1, 5, 20, 33, 100, 128], size=args.iters)
     bad = 0
     for it in range(args.iters):
         q, k = queries[it % 64], int(ks[it])
+        if args.batch_every and it % args.batch_every == 0:
+            qs = queries[(it % 16):(it % 16) + 48]
+            a = fused.search_batch(qs, min(k, 100))
+            if it % (10 * args.batch_every) == 0:
+                b = nccl.search_batch(qs, min(k, 100))
+                if not (np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))):
+                    bad += 1
+            continue
         a_ids, a_d = fused.search(q, k)
         if it % 10 == 0:                                 # the reference answer every 10th iteration
             b_ids, b_d = nccl.search(q, k)
