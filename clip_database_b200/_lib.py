@@ -21,7 +21,7 @@ SCORE_POPCOUNT = 1
 IPC_HANDLE_BYTES = 64
 BLEND_POSITIVE_ZERO_NORM = 1
 BLEND_NEGATIVE_ZERO_NORM = 2
-ABI_VERSION = 4
+ABI_VERSION = 5
 PLACE_DEVICE = 0
 PLACE_HOST = 1
 
@@ -32,6 +32,11 @@ _I32 = POINTER(c_int32)
 _U32 = POINTER(c_uint32)
 _D = POINTER(c_double)
 _CTX = c_void_p
+
+# clipdb_sqlite_chunk_fn: (user, n, rowids, image_ids, last_modified, paths, paths_bytes) -> int
+SQLITE_CHUNK_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_int64, POINTER(c_int64), POINTER(c_int64), POINTER(c_double),
+                                   POINTER(ctypes.c_char), c_int64)
+ERR_UNSUPPORTED = 5
 
 SIGNATURES = [
     ("clipdb_abi_version", c_int, []),
@@ -51,6 +56,7 @@ SIGNATURES = [
     ("clipdb_attach_rows", c_int, [_CTX, c_void_p, c_void_p, c_int64, c_int32, c_int64]),
     ("clipdb_reserve_rows", c_int, [_CTX, c_int64, c_int32, c_int32, c_int32]),
     ("clipdb_stage_buffer", c_int, [_CTX, c_int64, POINTER(c_void_p)]),
+    ("clipdb_append_sqlite", c_int, [_CTX, c_char_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, _I64, _I64]),
     ("clipdb_num_rows", c_int64, [_CTX]),
     ("clipdb_dim", c_int32, [_CTX]),
     ("clipdb_set_mask", c_int, [_CTX, c_void_p, c_int64]),

@@ -14,6 +14,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -24,12 +25,13 @@
 #include "blend.cuh"
 #include "merge.cuh"
 #include "scan_topk.cuh"
+#include "sqlite_reader.cuh"
 
 using namespace clipdb;
 
 namespace {
 
-constexpr int ABI_VERSION = 4;
+constexpr int ABI_VERSION = 5;
 #ifndef CLIPDB_SOURCE_HASH
 #define CLIPDB_SOURCE_HASH "unknown"
 #endif
@@ -99,6 +101,8 @@ struct clipdb_ctx {
     Buffer d_blend_in, d_blend_flags;
     Buffer pinned;      // host staging (inputs, then results)
     Buffer stage;       // pinned host buffer lent to the caller (clipdb_stage_buffer)
+    Buffer sql_stage[2];           // pinned double buffer of the native SQLite loader (clipdb_append_sqlite)
+    cudaEvent_t sql_done[2] = {nullptr, nullptr};   // the copy out of sql_stage[i] has completed
     Buffer pinned_aux;  // host staging for the blended query read-back
     Buffer pinned_flags; // host staging for the batched path's per-query flags
 
@@ -1142,6 +1146,10 @@ void clipdb_destroy(clipdb_ctx *c) {
         for (Buffer *b : bufs) free_buffer(*b);
         if (c->pinned.p) cudaFreeHost(c->pinned.p);
         if (c->stage.p) cudaFreeHost(c->stage.p);
+        for (int i = 0; i < 2; i++) {
+            if (c->sql_stage[i].p) cudaFreeHost(c->sql_stage[i].p);
+            if (c->sql_done[i]) cudaEventDestroy(c->sql_done[i]);
+        }
         if (c->pinned_aux.p) cudaFreeHost(c->pinned_aux.p);
         if (c->pinned_flags.p) cudaFreeHost(c->pinned_flags.p);
         for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -1254,9 +1262,15 @@ int clipdb_load_rows(clipdb_ctx *c, const float *rows, const int64_t *rowids, in
     return CLIPDB_OK;
 }
 
+static int append_rows_locked(clipdb_ctx *c, const float *rows, const int64_t *rowids, int64_t m);
+
 int clipdb_append_rows(clipdb_ctx *c, const float *rows, const int64_t *rowids, int64_t m) {
     if (!c) return CLIPDB_ERR_INVALID;
     std::lock_guard<std::mutex> lk(c->mu);
+    return append_rows_locked(c, rows, rowids, m);
+}
+
+static int append_rows_locked(clipdb_ctx *c, const float *rows, const int64_t *rowids, int64_t m) {
     if (!c->rows || !c->owns_rows) return fail(c, CLIPDB_ERR_STATE, "append_rows: no owned store (load first)");
     if (m < 0 || (m > 0 && !rows)) return fail(c, CLIPDB_ERR_INVALID, "append_rows: bad argument");
     if ((c->rowids != nullptr) != (rowids != nullptr) && m > 0)
@@ -1385,6 +1399,166 @@ int clipdb_stage_buffer(clipdb_ctx *c, int64_t bytes, void **out_host) {
     }
     *out_host = b.p;
     return CLIPDB_OK;
+}
+
+// The statement of the native loader: the row set and order of the reference's search statement
+// (image_database.py:1564-1571) — vec0 scanned in rowid order, INNER JOINed to image_embeddings and images — with the
+// join order pinned by CROSS JOIN (SQLite keeps the written nesting), so rows arrive in rowid order without a sorter.
+static const char *const SQL_LOAD_ROWS =
+    "SELECT v.rowid, ie.image_id, i.last_modified, i.file_path, v.embedding "
+    "FROM vec0 AS v CROSS JOIN image_embeddings AS ie ON ie.rowid = v.rowid "
+    "CROSS JOIN images AS i ON i.id = ie.image_id "
+    "WHERE v.rowid > ?1 AND v.rowid <= ?2 ORDER BY v.rowid";
+
+int clipdb_append_sqlite(clipdb_ctx *c, const char *db_path, int64_t min_rowid, int64_t max_rowid, int64_t chunk_rows,
+                         clipdb_sqlite_chunk_fn on_chunk, void *user, int64_t *out_vec0_rows, int64_t *out_joined_rows) {
+    if (!c || !db_path) return CLIPDB_ERR_INVALID;
+    const SqliteApi *sq = sqlite_api();
+    if (!sq) {
+        std::lock_guard<std::mutex> lk(c->mu);
+        return fail(c, CLIPDB_ERR_UNSUPPORTED, "append_sqlite: libsqlite3.so.0 is not available to the native loader");
+    }
+    int32_t dim = 0;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        if (!c->rows || !c->owns_rows || c->dim <= 0)
+            return fail(c, CLIPDB_ERR_STATE, "append_sqlite: reserve (or load) an owned store first");
+        if (!c->rowids && c->n > 0)
+            return fail(c, CLIPDB_ERR_STATE, "append_sqlite: the store must carry explicit rowids");
+        dim = c->dim;
+        if (chunk_rows <= 0) chunk_rows = 8192;
+        DeviceGuard g(c->device);
+        const size_t bytes = static_cast<size_t>(chunk_rows) * dim * sizeof(float);
+        for (int i = 0; i < 2; i++) {
+            if (!c->sql_stage[i].p || c->sql_stage[i].bytes < bytes) {
+                if (c->sql_stage[i].p) {
+                    CU_TRY(c, cudaStreamSynchronize(c->stream));
+                    cudaFreeHost(c->sql_stage[i].p);
+                    c->sql_stage[i].p = nullptr;
+                }
+                CU_TRY(c, cudaMallocHost(&c->sql_stage[i].p, bytes));
+                c->sql_stage[i].bytes = bytes;
+            }
+            if (!c->sql_done[i]) CU_TRY(c, cudaEventCreateWithFlags(&c->sql_done[i], cudaEventDisableTiming));
+        }
+    }
+    auto report = [&](int code, const char *what, void *db) {
+        std::lock_guard<std::mutex> lk(c->mu);
+        return fail(c, code, "append_sqlite: %s%s%s", what, db ? ": " : "", db ? sq->errmsg(db) : "");
+    };
+    void *db = nullptr;
+    const std::string uri = std::string("file:") + db_path + "?mode=ro";
+    if (sq->open_v2(uri.c_str(), &db, SQLITE_OPEN_READONLY_ | SQLITE_OPEN_URI_, nullptr) != SQLITE_OK_) {
+        const int rc = report(CLIPDB_ERR_INVALID, "cannot open the database", db);
+        if (db) sq->close_v2(db);
+        return rc;
+    }
+    sq->busy_timeout(db, 30000);
+    void *st_kind = nullptr, *st_count = nullptr, *st_rows = nullptr;
+    int rc = CLIPDB_OK;
+    int64_t vec0_rows = 0, joined = 0;
+    std::vector<int64_t> ids(chunk_rows), image_ids(chunk_rows);
+    std::vector<double> mtimes(chunk_rows);
+    std::string paths;
+    bool in_txn = false;
+    do {
+        // only a plain table named vec0 is read here; the virtual table / its shadow tables go through the Python reader
+        if (sq->prepare_v2(db, "SELECT type, sql FROM sqlite_master WHERE name = 'vec0'", -1, &st_kind, nullptr) != SQLITE_OK_) {
+            rc = report(CLIPDB_ERR_INVALID, "cannot read the schema", db);
+            break;
+        }
+        bool plain = false;
+        if (sq->step(st_kind) == SQLITE_ROW_) {
+            const char *type = reinterpret_cast<const char *>(sq->column_text(st_kind, 0));
+            const char *sql = reinterpret_cast<const char *>(sq->column_text(st_kind, 1));
+            plain = type && !strcmp(type, "table") && !(sql && (strstr(sql, "VIRTUAL") || strstr(sql, "virtual")));
+        }
+        if (!plain) {
+            rc = report(CLIPDB_ERR_UNSUPPORTED, "vec0 is not a plain table (use the Python reader)", nullptr);
+            break;
+        }
+        if (sq->exec(db, "BEGIN", nullptr, nullptr, nullptr) != SQLITE_OK_) {
+            rc = report(CLIPDB_ERR_INVALID, "BEGIN failed", db);
+            break;
+        }
+        in_txn = true;
+        if (sq->prepare_v2(db, "SELECT COUNT(*) FROM vec0 WHERE rowid > ?1 AND rowid <= ?2", -1, &st_count, nullptr) != SQLITE_OK_ ||
+            sq->prepare_v2(db, SQL_LOAD_ROWS, -1, &st_rows, nullptr) != SQLITE_OK_) {
+            rc = report(CLIPDB_ERR_INVALID, "cannot prepare the statements", db);
+            break;
+        }
+        sq->bind_int64(st_count, 1, min_rowid);
+        sq->bind_int64(st_count, 2, max_rowid);
+        if (sq->step(st_count) == SQLITE_ROW_) vec0_rows = sq->column_int64(st_count, 0);
+        sq->bind_int64(st_rows, 1, min_rowid);
+        sq->bind_int64(st_rows, 2, max_rowid);
+
+        const size_t row_bytes = static_cast<size_t>(dim) * sizeof(float);
+        int buf = 0;
+        int64_t fill = 0;
+        bool used[2] = {false, false};
+        auto flush = [&]() -> int {
+            if (fill == 0) return CLIPDB_OK;
+            {
+                std::lock_guard<std::mutex> lk(c->mu);
+                DeviceGuard g(c->device);
+                RC_TRY(append_rows_locked(c, static_cast<const float *>(c->sql_stage[buf].p), ids.data(), fill));
+                CU_TRY(c, cudaEventRecord(c->sql_done[buf], c->stream));
+                used[buf] = true;
+            }
+            if (on_chunk && on_chunk(user, fill, ids.data(), image_ids.data(), mtimes.data(), paths.data(),
+                                     static_cast<int64_t>(paths.size())) != 0)
+                return report(CLIPDB_ERR_INVALID, "the chunk callback asked to stop", nullptr);
+            joined += fill;
+            fill = 0;
+            paths.clear();
+            buf ^= 1;
+            if (used[buf]) {   // the copy that last read this buffer must be done before it is refilled
+                DeviceGuard g(c->device);
+                if (cudaEventSynchronize(c->sql_done[buf]) != cudaSuccess)
+                    return report(CLIPDB_ERR_CUDA, "waiting for the staging copy failed", nullptr);
+            }
+            return CLIPDB_OK;
+        };
+        int step_rc;
+        while ((step_rc = sq->step(st_rows)) == SQLITE_ROW_) {
+            const int nbytes = sq->column_bytes(st_rows, 4);
+            const void *blob = sq->column_blob(st_rows, 4);
+            if (static_cast<size_t>(nbytes) != row_bytes || !blob) {
+                std::lock_guard<std::mutex> lk(c->mu);
+                rc = fail(c, CLIPDB_ERR_INVALID, "append_sqlite: vec0 rowid %lld: %d bytes, expected float32[%d]",
+                          sq->column_int64(st_rows, 0), nbytes, dim);
+                break;
+            }
+            memcpy(static_cast<uint8_t *>(c->sql_stage[buf].p) + static_cast<size_t>(fill) * row_bytes, blob, row_bytes);
+            ids[fill] = sq->column_int64(st_rows, 0);
+            image_ids[fill] = sq->column_int64(st_rows, 1);
+            mtimes[fill] = sq->column_double(st_rows, 2);
+            const unsigned char *path = sq->column_text(st_rows, 3);
+            if (path) paths.append(reinterpret_cast<const char *>(path));
+            paths.push_back('\0');
+            if (++fill == chunk_rows && (rc = flush()) != CLIPDB_OK) break;
+        }
+        if (rc != CLIPDB_OK) break;
+        if (step_rc != SQLITE_DONE_) {
+            rc = report(CLIPDB_ERR_INVALID, "reading vec0 failed", db);
+            break;
+        }
+        rc = flush();
+    } while (false);
+    if (st_kind) sq->finalize(st_kind);
+    if (st_count) sq->finalize(st_count);
+    if (st_rows) sq->finalize(st_rows);
+    if (in_txn) sq->exec(db, "ROLLBACK", nullptr, nullptr, nullptr);
+    sq->close_v2(db);
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        DeviceGuard g(c->device);
+        cudaStreamSynchronize(c->stream);
+    }
+    if (out_vec0_rows) *out_vec0_rows = vec0_rows;
+    if (out_joined_rows) *out_joined_rows = joined;
+    return rc;
 }
 
 int64_t clipdb_num_rows(const clipdb_ctx *c) { return c ? c->n : 0; }

@@ -19,7 +19,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from . import loader, schema
+from . import _lib, loader, schema
 from .index import GpuIndex
 
 Result = List[Tuple[str, float]]
@@ -126,7 +126,8 @@ class ImageDatabase:
     def __init__(self, db_path: str, device: int = 0, embedder: Optional[Embedder] = None,
                  nan_policy: str = "reference", verbose: bool = False,
                  binary_score_mode: str = "reference", batch_store: bool = False,
-                 devices: Optional[Sequence[int]] = None, hbm_budget_bytes: Optional[int] = None):
+                 devices: Optional[Sequence[int]] = None, hbm_budget_bytes: Optional[int] = None,
+                 native_loader: bool = True):
         """``batch_store=True`` also keeps the bf16 copy of the store (half its size again) and sends
         every search — single queries included — through the tensor-core pre-selection + exact
         re-rank: same results, about half the latency per query, and ``search_embeddings`` answers
@@ -146,6 +147,8 @@ class ImageDatabase:
         self.binary_score_mode = binary_score_mode
         self.batch_store = bool(batch_store)
         self.hbm_budget_bytes = hbm_budget_bytes
+        self.native_loader = bool(native_loader)   # False: always the Python reader (tests compare the two)
+        self._placed: List[str] = []
         self.placement = "device"          # or "tiered" (see reload)
         self._codes = None                 # loader.HostCodes once the sign-code fallback is needed
         self._code_mask_key: Optional[Tuple[str, ...]] = None
@@ -168,6 +171,7 @@ class ImageDatabase:
         self._data_version = -1
         self._dangling = 0            # mapped rowids (<= the last resident one) that have no vec0 row: see refresh()
         self.load_seconds = 0.0
+        self.load_source = ""
         self.reloads = 0
         self._binary_count = 0
         self._vec0_count = 0
@@ -183,20 +187,55 @@ class ImageDatabase:
         """Scan positions of resident rowids (``self._rowids`` is ascending: the scan order)."""
         return np.searchsorted(self._rowids, np.asarray(rowids, dtype=np.int64))
 
-    def _stream_into(self, conn, append, lo=None, hi=None, expect_dim=None) -> loader.HostStore:
-        """Read rowids in (lo, hi] chunk by chunk and hand every chunk to ``append(rows, rowids)`` through a
-        pinned staging buffer: host memory stays O(chunk) whatever the size of the database."""
+    def _load_range(self, conn, index, lo=None, hi=None, rows_hint: Optional[int] = None) -> loader.HostStore:
+        """Append the joined vec0 rows with rowid in (lo, hi] to ``index`` (a ``GpuIndex``) and return their
+        metadata (``rows=None``).  ``rows_hint`` = reserve a fresh store for about that many rows first (a load);
+        None = append to the store that is there (a refresh).  Host memory stays O(chunk) either way:
+          * native reader (``clipdb_append_sqlite``) when vec0 is a plain table: SQLite's C library copies every
+            blob once, into a pinned double buffer, and the DMA of a chunk overlaps the reading of the next;
+          * otherwise (sqlite-vec's virtual table or its shadow tables) the Python reader: ``fetchmany`` chunks
+            copied into the context's pinned staging buffer."""
+        state = {"reserved": rows_hint is None}
+
+        def reserve(dim: int, at_least: int) -> None:
+            if not state["reserved"]:
+                self._placed.append(self._reserve(index, max(rows_hint, at_least, 1), dim))
+                state["reserved"] = True
+
+        if self.native_loader and loader.vec0_source(conn) == "plain-table":
+            dim = loader.peek_dim(conn, lo, hi)
+            if dim is not None:
+                reserve(dim, 1)
+                ids, images, mtimes, paths = [], [], [], []
+
+                def on_chunk(c_ids, c_images, c_mtimes, c_paths):
+                    ids.append(c_ids)
+                    images.append(c_images)
+                    mtimes.append(c_mtimes)
+                    paths.extend(c_paths)
+                try:
+                    vec0_rows, joined = index.append_sqlite(self.db_path, lo, hi, on_chunk, loader.CHUNK_ROWS)
+                except _lib.ClipdbError as e:
+                    if e.code != _lib.ERR_UNSUPPORTED:
+                        raise
+                else:
+                    cat = lambda parts, dt: np.concatenate(parts) if parts else np.zeros(0, dtype=dt)   # noqa: E731
+                    return loader.HostStore(cat(ids, np.int64), None, cat(images, np.int64), paths,
+                                            loader.count_binary(conn), vec0_rows, "plain-table (native reader)",
+                                            vec0_rows - joined, cat(mtimes, np.float64), dim)
         stage = {"buf": None}
-        lead = self.index.shards[0] if hasattr(self.index, "shards") else self.index
 
         def sink(chunk: loader.StoreChunk) -> None:
             m, dim = len(chunk), chunk.dim
+            reserve(dim, m)
             if stage["buf"] is None or stage["buf"].shape[1] != dim or stage["buf"].shape[0] < m:
-                stage["buf"] = lead.stage_buffer(max(loader.CHUNK_ROWS, m), dim)
+                stage["buf"] = index.stage_buffer(max(loader.CHUNK_ROWS, m), dim)
             buf = stage["buf"][:m]
             chunk.write_rows(buf)                      # blobs -> pinned memory, one memcpy per row
-            append(buf, chunk.rowids)                  # copies before it returns
-        return loader.stream_store(self.db_path, sink, expect_dim=expect_dim, min_rowid=lo, max_rowid=hi, conn=conn)
+            index.append(buf, chunk.rowids)
+            index.synchronize()                        # the staging buffer is reused by the next chunk
+        return loader.stream_store(self.db_path, sink, expect_dim=(index.dim or None) if rows_hint is None else None,
+                                   min_rowid=lo, max_rowid=hi, conn=conn)
 
     def _reserve(self, index, rows_hint: int, dim: int) -> str:
         """Reserve room for ``rows_hint`` rows on ``index``: all in HBM when they fit (next to the bf16 copy if one
@@ -232,22 +271,13 @@ class ImageDatabase:
             self._data_version = loader.data_version(self._watch_conn())
             mapped = int(conn.execute("SELECT COUNT(*) FROM image_embeddings").fetchone()[0])
             parts = []
-            placed: List[str] = []
+            self._placed = []
             if multi and mapped > 0:
                 ranges, n_mapped = loader.plan_shards(conn, world)
                 if 0 < n_mapped < world:
                     raise ValueError(f"{n_mapped} rows cannot be sharded over {world} GPUs")
                 for rank, (lo, hi) in enumerate(ranges):
-                    shard = self.index.shards[rank]
-                    state = {"reserved": False}
-
-                    def append(rows, rowids, shard=shard, state=state):
-                        if not state["reserved"]:
-                            placed.append(self._reserve(shard, max(n_mapped // world + 1, rows.shape[0]), rows.shape[1]))
-                            state["reserved"] = True
-                        shard.append(rows, rowids)
-                        shard.synchronize()
-                    host = self._stream_into(conn, append, lo, hi)
+                    host = self._load_range(conn, self.index.shards[rank], lo, hi, rows_hint=n_mapped // world + 1)
                     if host.rowids.shape[0] < 1:
                         raise ValueError("every shard needs at least one row (too many vec0 rows are missing)")
                     self.index.note_shard_loaded(rank, host.rowids.shape[0])
@@ -255,17 +285,10 @@ class ImageDatabase:
                 self.index.finish_load()
             else:
                 single = self.index.shards[0] if multi else self.index
-                state = {"reserved": False}
-
-                def append(rows, rowids):
-                    if not state["reserved"]:
-                        placed.append(self._reserve(single, max(mapped, rows.shape[0]), rows.shape[1]))
-                        state["reserved"] = True
-                    single.append(rows, rowids)
-                    single.synchronize()
-                parts.append(self._stream_into(conn, append))
+                parts.append(self._load_range(conn, single, rows_hint=mapped))
             self._vec0_count = loader.count_vec0(conn)
         first = parts[0]
+        self.load_source = first.source
         self._binary_count = first.binary_count
         self._paths = [fp for p in parts for fp in p.file_paths]
         self._lowered = None
@@ -278,7 +301,7 @@ class ImageDatabase:
         self._code_mask_key = None
         n = self._rowids.shape[0]
         self._dangling = 0
-        self.placement = "tiered" if "tiered" in placed else "device"
+        self.placement = "tiered" if "tiered" in self._placed else "device"
         if self.batch_store and n and self.index.dim == schema.EMBEDDING_DIM:
             self.index.enable_batch()
             if not multi:
@@ -287,6 +310,10 @@ class ImageDatabase:
                 self.index.prefer_batch = self.placement == "tiered"
         self.load_seconds = time.perf_counter() - t0
         self.reloads += 1
+        if loader.data_version(self._watch_conn()) != self._data_version:
+            # someone committed while the load ran (the native reader and this connection hold separate snapshots):
+            # reconcile with what a fresh connection sees now
+            self.refresh()
         self._log(f"loaded {n} rows ({first.source}, {self.placement} store) in {self.load_seconds:.2f} s "
                   f"({n / max(self.load_seconds, 1e-9):.0f} rows/s); "
                   f"{sum(p.dropped for p in parts)} vec0 rows without a mapping were skipped")
@@ -367,14 +394,12 @@ class ImageDatabase:
                 self._mask_key = None
             # appended rows
             if len(mp.rowids) > n_old_in_map:
-                target = self.index
-
-                def append(rows, rowids):
-                    target.append(rows, rowids)
-                    (target.shards[-1] if multi else target).synchronize()     # the staging buffer is reused
-                host = self._stream_into(conn, append, lo=last, expect_dim=self.index.dim or None)
+                target = self.index.shards[-1] if multi else self.index
+                host = self._load_range(conn, target, lo=last)
                 m = host.rowids.shape[0]
                 if m:
+                    if multi:
+                        self.index.note_appended(m)
                     self._paths.extend(host.file_paths)
                     self._lowered = None
                     self._image_ids = np.concatenate([self._image_ids, host.image_ids])

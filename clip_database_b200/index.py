@@ -9,6 +9,7 @@ and do not synchronise.
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple
 
@@ -196,6 +197,41 @@ class GpuIndex:
         self._check(self._L.clipdb_stage_buffer(self._ctx, nbytes, ctypes.byref(ptr)))
         buf = (ctypes.c_float * (int(rows) * int(dim))).from_address(ptr.value)
         return np.frombuffer(buf, dtype=np.float32).reshape(int(rows), int(dim))
+
+    def append_sqlite(self, db_path: str, min_rowid: Optional[int] = None, max_rowid: Optional[int] = None,
+                      on_chunk=None, chunk_rows: int = 8192) -> Tuple[int, int]:
+        """Native loader (clipdb_append_sqlite): append the joined vec0 rows with rowid in (min_rowid, max_rowid] of
+        a reference-schema SQLite file to the reserved store, read by SQLite's C library straight into pinned
+        memory.  ``on_chunk(rowids, image_ids, last_modified, file_paths)`` receives numpy copies and the list of
+        paths per chunk.  Returns (vec0 rows in the range before the joins, rows appended).  Raises ``ClipdbError``
+        with ``code == _lib.ERR_UNSUPPORTED`` when vec0 is not a plain table or libsqlite3 is unavailable."""
+        errors = []
+
+        def trampoline(_user, n, p_ids, p_images, p_mtimes, p_paths, paths_bytes):
+            try:
+                n = int(n)
+                ids = np.ctypeslib.as_array(p_ids, shape=(n,)).copy()
+                images = np.ctypeslib.as_array(p_images, shape=(n,)).copy()
+                mtimes = np.ctypeslib.as_array(p_mtimes, shape=(n,)).copy()
+                blob = ctypes.string_at(p_paths, int(paths_bytes))
+                paths = blob.decode("utf-8").split("\0")[:n]
+                if on_chunk is not None:
+                    on_chunk(ids, images, mtimes, paths)
+                return 0
+            except BaseException as e:      # noqa: BLE001 — an exception must not unwind through the C frames
+                errors.append(e)
+                return 1
+        cb = _lib.SQLITE_CHUNK_FN(trampoline)
+        vec0_rows, joined = ctypes.c_int64(0), ctypes.c_int64(0)
+        lo = -(1 << 63) if min_rowid is None else int(min_rowid)
+        hi = (1 << 63) - 1 if max_rowid is None else int(max_rowid)
+        rc = self._L.clipdb_append_sqlite(self._ctx, os.fsencode(db_path), lo, hi, int(chunk_rows),
+                                          ctypes.cast(cb, ctypes.c_void_p), None, ctypes.byref(vec0_rows),
+                                          ctypes.byref(joined))
+        if errors:
+            raise errors[0]
+        self._check(rc)
+        return int(vec0_rows.value), int(joined.value)
 
     def append(self, rows, rowids=None) -> None:
         """Append rows (numpy, or a torch tensor on any device) in scan order."""

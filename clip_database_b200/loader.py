@@ -218,6 +218,26 @@ def _vec0_source(conn: sqlite3.Connection) -> str:
     raise RuntimeError("database has no vec0 table")
 
 
+def vec0_source(conn: sqlite3.Connection) -> str:
+    """"plain-table", "sqlite-vec" or "shadow-tables" (raises when the database has no vec0 at all)."""
+    return _vec0_source(conn)
+
+
+def peek_dim(conn: sqlite3.Connection, min_rowid: Optional[int] = None, max_rowid: Optional[int] = None
+             ) -> Optional[int]:
+    """Dimension of the first vec0 blob with rowid in (min_rowid, max_rowid] of a plain-table vec0, or None when
+    the range is empty."""
+    lo = _MIN_ROWID if min_rowid is None else min_rowid
+    hi = _MAX_ROWID if max_rowid is None else max_rowid
+    row = conn.execute("SELECT rowid, length(embedding) FROM vec0 WHERE rowid > ? AND rowid <= ? ORDER BY rowid LIMIT 1",
+                       (lo, hi)).fetchone()
+    if row is None:
+        return None
+    if row[1] is None or row[1] % 4:
+        raise ValueError(f"vec0 rowid {row[0]}: blob length {row[1]} is not float32[]")
+    return int(row[1]) // 4
+
+
 def count_vec0(conn: sqlite3.Connection) -> int:
     """``SELECT COUNT(*) FROM vec0`` (the reference's guard, image_database.py:1532-1540)."""
     source = _vec0_source(conn)

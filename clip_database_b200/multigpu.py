@@ -119,6 +119,14 @@ class MultiGpuIndex:
         if self._masked:               # the last shard dropped its mask (sized for the old row count): so do the others
             self.clear_mask()
 
+    def note_appended(self, m: int) -> None:
+        """``m`` rows were appended to the LAST shard directly (``shards[-1].append_sqlite``)."""
+        lo, hi = self.bounds[-1]
+        self.bounds[-1] = (lo, hi + int(m))
+        self.num_rows += int(m)
+        if self._masked:
+            self.clear_mask()
+
     def set_mask(self, admitted) -> None:
         bits = np.asarray(admitted).astype(bool)
         if bits.shape != (self.num_rows,):

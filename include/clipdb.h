@@ -124,6 +124,22 @@ int clipdb_attach_rows(clipdb_ctx *ctx, const float *d_rows, const int64_t *d_ro
 #define CLIPDB_PLACE_HOST   1
 int clipdb_reserve_rows(clipdb_ctx *ctx, int64_t capacity, int32_t dim, int32_t explicit_rowids, int32_t placement);
 int clipdb_stage_buffer(clipdb_ctx *ctx, int64_t bytes, void **out_host);
+/* Native loader: append to the (reserved) store the rows the reference's search statement scans — `vec0` in rowid
+ * order, INNER JOINed to `image_embeddings` (vec0.rowid = ie.rowid) and `images` (ie.image_id = i.id), idb:1564-1571
+ * — for vec0 rowids in (min_rowid, max_rowid], read from the SQLite file with SQLite's own C library (libsqlite3.so.0,
+ * resolved with dlopen) inside one read transaction.  Every float32 blob is copied once, from SQLite's page buffer
+ * into a pinned double buffer, and leaves for the GPU by DMA while the next chunk is being read; vec0 rows without
+ * both partners are dropped, as the INNER JOINs drop them (idb:1569-1570).  After every chunk of up to `chunk_rows`
+ * rows `on_chunk` (nullable) receives what the host keeps per row: the rowids, image ids, `images.last_modified`
+ * and the file paths (`n` NUL-terminated UTF-8 strings back to back, `paths_bytes` in total); a non-zero return
+ * stops the load.  Only a plain table named vec0 is read here (CLIPDB_ERR_UNSUPPORTED otherwise, and when
+ * libsqlite3 is not available): sqlite-vec's virtual table is read by the binding's own reader.
+ * out_vec0_rows = COUNT(*) of vec0 in the range before the joins (the reference's guard, idb:1532-1540). */
+typedef int (*clipdb_sqlite_chunk_fn)(void *user, int64_t n, const int64_t *rowids, const int64_t *image_ids,
+                                      const double *last_modified, const char *paths, int64_t paths_bytes);
+int clipdb_append_sqlite(clipdb_ctx *ctx, const char *db_path, int64_t min_rowid, int64_t max_rowid,
+                         int64_t chunk_rows, clipdb_sqlite_chunk_fn on_chunk, void *user,
+                         int64_t *out_vec0_rows, int64_t *out_joined_rows);
 int64_t clipdb_num_rows(const clipdb_ctx *ctx);
 int32_t clipdb_dim(const clipdb_ctx *ctx);
 

@@ -263,3 +263,52 @@ def test_a_mapping_without_a_vector_does_not_cause_reload_after_reload(tmp_path)
         q = rows[99]                                                                      # the row that is missing
         assert_same_answer(db.search_embedding(q, k=5, show_duplicates=True), reference_answer(db_path, q, 5))
     w.close()
+
+
+def test_native_and_python_readers_load_the_same_store(tmp_path):
+    """clipdb_append_sqlite (SQLite's C library -> pinned double buffer -> DMA) against the Python reader: same rows
+    in the same order, same metadata (orphans dropped, unicode paths, ranges), same answers; sqlite-vec style
+    shadow tables fall back to the Python reader."""
+    assert have_gpu()
+    from clip_database_b200 import GpuIndex, ImageDatabase, loader
+    n = 20_000                                                     # more than two 8192-row chunks
+    rows = synth.unit_rows(n, DIM, 81)
+    paths = synth.default_paths(n)
+    paths[3] = "/data/photos/a/naïve – café ☕.jpg"
+    paths[19_999] = "/data/scans/日本語 ファイル.png"
+    db_path = str(tmp_path / "n.db")
+    synth.write_reference_db(db_path, rows, paths, rowid_start=5, drop_mapping_for=[0, 8191, 8192, 12_345],
+                             drop_image_for=[77, 19_998])
+    q = synth.unit_rows(3, DIM, 82)
+    with _closing(ImageDatabase(db_path, device=0, native_loader=False)) as py, \
+            _closing(ImageDatabase(db_path, device=0)) as nat:
+        assert py.load_source == "plain-table" and nat.load_source == "plain-table (native reader)"
+        assert nat.index.num_rows == py.index.num_rows == n - 6
+        assert np.array_equal(nat._rowids, py._rowids) and np.array_equal(nat._image_ids, py._image_ids)
+        assert np.array_equal(nat._mtimes, py._mtimes) and nat._paths == py._paths
+        assert nat._vec0_count == py._vec0_count == n
+        for v in q:
+            assert nat.search_embedding(v, k=15, show_duplicates=True) == py.search_embedding(v, k=15, show_duplicates=True)
+            assert_same_answer(nat.search_embedding(v, k=15, show_duplicates=True), reference_answer(db_path, v, 15))
+        hit = nat.search_embedding(rows[3], k=1, show_duplicates=True)
+        assert hit[0][0] == paths[3]
+    # a rowid range through the raw entry point, with the metadata callback
+    with GpuIndex(0) as idx:
+        idx.reserve(100, DIM, explicit_rowids=True)
+        seen = []
+        vec0_rows, joined = idx.append_sqlite(db_path, 5 + 8000, 5 + 8400, lambda *a: seen.append(a), chunk_rows=128)
+        assert vec0_rows == 400 and joined == 398 and idx.num_rows == 398          # positions 8191, 8192 are orphans
+        assert sum(len(a[0]) for a in seen) == 398 and len(seen) == 4
+        assert seen[0][0][0] == 5 + 8001 and seen[0][3][0] == paths[8001]
+        res = idx.search(rows[8100], 1)
+        assert res.rowids[0, 0] == 5 + 8100
+        with pytest.raises(Exception, match="float32"):                            # a store of another dimension
+            with GpuIndex(0) as other:
+                other.reserve(10, 64, explicit_rowids=True)
+                other.append_sqlite(db_path)
+    # shadow tables: not a plain table -> the Python reader
+    shadow = str(tmp_path / "s.db")
+    synth.write_reference_db(shadow, rows[:3000], vec0_layout="shadow")
+    with _closing(ImageDatabase(shadow, device=0)) as db:
+        assert db.load_source == "shadow-tables" and db.index.num_rows == 3000
+        assert db.search_embedding(rows[10], k=1, show_duplicates=True)[0][0] == synth.default_paths(3000)[10]
