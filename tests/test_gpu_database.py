@@ -312,3 +312,32 @@ def test_native_and_python_readers_load_the_same_store(tmp_path):
     with _closing(ImageDatabase(shadow, device=0)) as db:
         assert db.load_source == "shadow-tables" and db.index.num_rows == 3000
         assert db.search_embedding(rows[10], k=1, show_duplicates=True)[0][0] == synth.default_paths(3000)[10]
+
+
+def test_tiered_shards_on_several_gpus(tmp_path):
+    """ImageDatabase(devices=[0, 1], batch_store=True) with shards that do not fit their GPU: both shards are loaded
+    tiered and every search goes through the bf16 pre-selection + exact re-rank with the candidates exchanged by the
+    batched path's last kernel.  Needs one GPU per shard."""
+    assert have_gpu()
+    import torch
+    from clip_database_b200 import ImageDatabase
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n, k = 6000, 10
+    rows = synth.unit_rows(n, DIM, 91)
+    db_path = str(tmp_path / "t.db")
+    synth.write_reference_db(db_path, rows, drop_mapping_for=[5, 4000])
+    # per shard: 3000 rows = 13.8 MB float32 + 6.9 MB bf16 against a 12 MB budget -> tiered
+    with _closing(ImageDatabase(db_path, devices=[0, 1], batch_store=True, hbm_budget_bytes=12_000_000)) as db:
+        assert db.placement == "tiered" and db.index.prefer_batch
+        for seed in (92, 93, 94):
+            q = synth.unit_rows(1, DIM, seed)[0]
+            before = db.index.launch_count
+            got = db.search_embedding(q, k=k, show_duplicates=True)
+            assert db.index.launch_count - before <= 2 * 8, "the batched path was not taken"
+            assert_same_answer(got, reference_answer(db_path, q, k))
+        folders = ["/data/photos/a"]                              # a mask: the exact (fused) path over the tiers
+        assert_same_answer(db.search_embedding(rows[9], k=k, filter_folders=folders, show_duplicates=True),
+                           reference_answer(db_path, rows[9], k, folders))
+        many = db.search_embeddings(rows[100:140], k=5)
+        assert [r[0][0] for r in many] == [synth.default_paths(n)[i] for i in range(100, 140)]
