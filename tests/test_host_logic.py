@@ -216,3 +216,26 @@ def test_data_version_moves_only_when_someone_else_commits(tmp_path):
     w.close()
     assert loader.data_version(watch) != v0
     watch.close()
+
+
+def test_native_readers_statement_needs_no_sorter(tmp_path):
+    """The native loader's statement (csrc/clipdb.cu: SQL_LOAD_ROWS) must walk vec0 in rowid order with two primary-key
+    probes per row — the reference statement's own plan — and no temp b-tree (which would hold every blob)."""
+    import os
+    import re
+    import sqlite3
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "clip_database_b200", "csrc",
+                            "clipdb.cu")).read()
+    body = re.search(r"SQL_LOAD_ROWS =\s*((?:\s*\"[^\"]*\"\s*)+);", src).group(1)
+    sql = "".join(re.findall(r"\"([^\"]*)\"", body))
+    assert "CROSS JOIN image_embeddings" in sql and "ORDER BY v.rowid" in sql
+    db = str(tmp_path / "p.db")
+    synth.write_reference_db(db, synth.unit_rows(50, 16, 2), drop_mapping_for=[3])
+    conn = sqlite3.connect(db)
+    plan = [r[-1] for r in conn.execute("EXPLAIN QUERY PLAN " + sql.replace("?1", "?").replace("?2", "?"), (0, 1 << 40))]
+    assert plan[0].startswith("SEARCH v USING INTEGER PRIMARY KEY") and len(plan) == 3, plan
+    assert not any("TEMP B-TREE" in p for p in plan), plan
+    got = conn.execute(sql.replace("?1", "?").replace("?2", "?"), (0, 1 << 40)).fetchall()
+    want = loader.read_store(db)
+    assert [r[0] for r in got] == want.rowids.tolist() and [r[3] for r in got] == want.file_paths
+    conn.close()
