@@ -11,9 +11,12 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -101,8 +104,8 @@ struct clipdb_ctx {
     Buffer d_blend_in, d_blend_flags;
     Buffer pinned;      // host staging (inputs, then results)
     Buffer stage;       // pinned host buffer lent to the caller (clipdb_stage_buffer)
-    Buffer sql_stage[2];           // pinned double buffer of the native SQLite loader (clipdb_append_sqlite)
-    cudaEvent_t sql_done[2] = {nullptr, nullptr};   // the copy out of sql_stage[i] has completed
+    std::vector<void *> sql_slots;     // pinned staging slots of the native SQLite loader (clipdb_append_sqlite)
+    size_t sql_slot_bytes = 0;
     Buffer pinned_aux;  // host staging for the blended query read-back
     Buffer pinned_flags; // host staging for the batched path's per-query flags
 
@@ -143,6 +146,7 @@ struct clipdb_ctx {
     int64_t scan_chunk = 4;    // tiles per atomicAdd (dynamic assignment)
     int64_t fuse_tail = 1;     // 1: the scan's last CTA merges and decodes (one launch per query); 0: merge-tree kernels
     int64_t host_tier_from_row = 0;  // clipdb_reserve_rows(CLIPDB_PLACE_HOST): rows below this position stay in HBM
+    int64_t sqlite_readers = 4;      // clipdb_append_sqlite: connections reading rowid stripes in parallel
 };
 
 namespace {
@@ -1146,10 +1150,7 @@ void clipdb_destroy(clipdb_ctx *c) {
         for (Buffer *b : bufs) free_buffer(*b);
         if (c->pinned.p) cudaFreeHost(c->pinned.p);
         if (c->stage.p) cudaFreeHost(c->stage.p);
-        for (int i = 0; i < 2; i++) {
-            if (c->sql_stage[i].p) cudaFreeHost(c->sql_stage[i].p);
-            if (c->sql_done[i]) cudaEventDestroy(c->sql_done[i]);
-        }
+        for (void *p : c->sql_slots) cudaFreeHost(p);
         if (c->pinned_aux.p) cudaFreeHost(c->pinned_aux.p);
         if (c->pinned_flags.p) cudaFreeHost(c->pinned_flags.p);
         for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -1200,6 +1201,7 @@ static int64_t *option_slot(clipdb_ctx *c, const char *name) {
     if (!strcmp(name, "scan_chunk")) return &c->scan_chunk;
     if (!strcmp(name, "fuse_tail")) return &c->fuse_tail;
     if (!strcmp(name, "host_tier_from_row")) return &c->host_tier_from_row;
+    if (!strcmp(name, "sqlite_readers")) return &c->sqlite_readers;
     if (!strcmp(name, "xchg_timeout_ms")) return &c->xchg_timeout_ms;
     if (!strcmp(name, "batch_min_nq")) return &c->batch_min_nq;
     if (!strcmp(name, "batch_cand_cap")) return &c->batch_cand_cap;
@@ -1410,15 +1412,119 @@ static const char *const SQL_LOAD_ROWS =
     "CROSS JOIN images AS i ON i.id = ie.image_id "
     "WHERE v.rowid > ?1 AND v.rowid <= ?2 ORDER BY v.rowid";
 
+namespace {
+
+// one staging slot of the native loader: a pinned row buffer + what the host keeps per row
+struct SqlSlot {
+    std::vector<int64_t> ids, image_ids;
+    std::vector<double> mtimes;
+    std::string paths;
+    int64_t m = 0;
+};
+
+// an open read-only connection inside one read transaction, with the row statement prepared
+struct SqlReader {
+    const SqliteApi *sq = nullptr;
+    void *db = nullptr, *st_rows = nullptr;
+    std::string err;
+
+    bool open(const SqliteApi *api, const char *db_path) {
+        sq = api;
+        const std::string uri = std::string("file:") + db_path + "?mode=ro";
+        if (sq->open_v2(uri.c_str(), &db, SQLITE_OPEN_READONLY_ | SQLITE_OPEN_URI_, nullptr) != SQLITE_OK_) {
+            err = std::string("cannot open the database: ") + (db ? sq->errmsg(db) : "out of memory");
+            return false;
+        }
+        sq->busy_timeout(db, 30000);
+        if (sq->exec(db, "BEGIN", nullptr, nullptr, nullptr) != SQLITE_OK_ ||
+            sq->prepare_v2(db, SQL_LOAD_ROWS, -1, &st_rows, nullptr) != SQLITE_OK_) {
+            err = std::string("cannot prepare the row statement: ") + sq->errmsg(db);
+            return false;
+        }
+        return true;
+    }
+
+    // rows with rowid in (lo, hi] into `slot` / `pinned`, at most `cap` of them; false (and err) on failure
+    bool read_range(int64_t lo, int64_t hi, int32_t dim, int64_t cap, uint8_t *pinned, SqlSlot &slot) {
+        const size_t row_bytes = static_cast<size_t>(dim) * sizeof(float);
+        slot.m = 0;
+        slot.paths.clear();
+        sq->reset(st_rows);
+        sq->bind_int64(st_rows, 1, lo);
+        sq->bind_int64(st_rows, 2, hi);
+        int rc;
+        while ((rc = sq->step(st_rows)) == SQLITE_ROW_) {
+            const int nbytes = sq->column_bytes(st_rows, 4);
+            const void *blob = sq->column_blob(st_rows, 4);
+            if (static_cast<size_t>(nbytes) != row_bytes || !blob) {
+                char msg[160];
+                snprintf(msg, sizeof msg, "vec0 rowid %lld: %d bytes, expected float32[%d]", sq->column_int64(st_rows, 0),
+                         nbytes, dim);
+                err = msg;
+                return false;
+            }
+            if (slot.m >= cap) {
+                err = "more rows in a rowid stripe than rowids (corrupt table?)";
+                return false;
+            }
+            memcpy(pinned + static_cast<size_t>(slot.m) * row_bytes, blob, row_bytes);
+            slot.ids[slot.m] = sq->column_int64(st_rows, 0);
+            slot.image_ids[slot.m] = sq->column_int64(st_rows, 1);
+            slot.mtimes[slot.m] = sq->column_double(st_rows, 2);
+            const unsigned char *path = sq->column_text(st_rows, 3);
+            if (path) slot.paths.append(reinterpret_cast<const char *>(path));
+            slot.paths.push_back('\0');
+            slot.m++;
+        }
+        if (rc != SQLITE_DONE_) {
+            err = std::string("reading vec0 failed: ") + sq->errmsg(db);
+            return false;
+        }
+        return true;
+    }
+
+    ~SqlReader() {
+        if (st_rows) sq->finalize(st_rows);
+        if (db) {
+            sq->exec(db, "ROLLBACK", nullptr, nullptr, nullptr);
+            sq->close_v2(db);
+        }
+    }
+};
+
+bool sql_scalar_i64(const SqliteApi *sq, void *db, const char *sql, int64_t a, int64_t b, int64_t *out, bool *is_null) {
+    void *st = nullptr;
+    if (sq->prepare_v2(db, sql, -1, &st, nullptr) != SQLITE_OK_) return false;
+    sq->bind_int64(st, 1, a);
+    sq->bind_int64(st, 2, b);
+    bool ok = false;
+    if (sq->step(st) == SQLITE_ROW_) {
+        ok = true;
+        *is_null = sq->column_bytes(st, 0) == 0 && sq->column_int64(st, 0) == 0 && sq->column_text(st, 0) == nullptr;
+        *out = sq->column_int64(st, 0);
+    }
+    sq->finalize(st);
+    return ok;
+}
+
+}  // namespace
+
 int clipdb_append_sqlite(clipdb_ctx *c, const char *db_path, int64_t min_rowid, int64_t max_rowid, int64_t chunk_rows,
                          clipdb_sqlite_chunk_fn on_chunk, void *user, int64_t *out_vec0_rows, int64_t *out_joined_rows) {
     if (!c || !db_path) return CLIPDB_ERR_INVALID;
+    if (out_vec0_rows) *out_vec0_rows = 0;
+    if (out_joined_rows) *out_joined_rows = 0;
     const SqliteApi *sq = sqlite_api();
     if (!sq) {
         std::lock_guard<std::mutex> lk(c->mu);
         return fail(c, CLIPDB_ERR_UNSUPPORTED, "append_sqlite: libsqlite3.so.0 is not available to the native loader");
     }
+    auto report = [&](int code, const std::string &what) {
+        std::lock_guard<std::mutex> lk(c->mu);
+        return fail(c, code, "append_sqlite: %s", what.c_str());
+    };
     int32_t dim = 0;
+    int readers = 1;
     {
         std::lock_guard<std::mutex> lk(c->mu);
         if (!c->rows || !c->owns_rows || c->dim <= 0)
@@ -1426,137 +1532,211 @@ int clipdb_append_sqlite(clipdb_ctx *c, const char *db_path, int64_t min_rowid, 
         if (!c->rowids && c->n > 0)
             return fail(c, CLIPDB_ERR_STATE, "append_sqlite: the store must carry explicit rowids");
         dim = c->dim;
-        if (chunk_rows <= 0) chunk_rows = 8192;
-        DeviceGuard g(c->device);
-        const size_t bytes = static_cast<size_t>(chunk_rows) * dim * sizeof(float);
-        for (int i = 0; i < 2; i++) {
-            if (!c->sql_stage[i].p || c->sql_stage[i].bytes < bytes) {
-                if (c->sql_stage[i].p) {
-                    CU_TRY(c, cudaStreamSynchronize(c->stream));
-                    cudaFreeHost(c->sql_stage[i].p);
-                    c->sql_stage[i].p = nullptr;
-                }
-                CU_TRY(c, cudaMallocHost(&c->sql_stage[i].p, bytes));
-                c->sql_stage[i].bytes = bytes;
-            }
-            if (!c->sql_done[i]) CU_TRY(c, cudaEventCreateWithFlags(&c->sql_done[i], cudaEventDisableTiming));
-        }
+        readers = static_cast<int>(c->sqlite_readers < 1 ? 1 : (c->sqlite_readers > 16 ? 16 : c->sqlite_readers));
     }
-    auto report = [&](int code, const char *what, void *db) {
-        std::lock_guard<std::mutex> lk(c->mu);
-        return fail(c, code, "append_sqlite: %s%s%s", what, db ? ": " : "", db ? sq->errmsg(db) : "");
-    };
-    void *db = nullptr;
-    const std::string uri = std::string("file:") + db_path + "?mode=ro";
-    if (sq->open_v2(uri.c_str(), &db, SQLITE_OPEN_READONLY_ | SQLITE_OPEN_URI_, nullptr) != SQLITE_OK_) {
-        const int rc = report(CLIPDB_ERR_INVALID, "cannot open the database", db);
-        if (db) sq->close_v2(db);
-        return rc;
+    if (chunk_rows <= 0) chunk_rows = 8192;
+
+    // ---- the control connection: what kind of table, how many rows, which rowids
+    SqlReader control;
+    if (!control.open(sq, db_path)) {
+        // a database without vec0 / image_embeddings / images cannot even prepare the statement
+        return report(strstr(control.err.c_str(), "prepare") ? CLIPDB_ERR_UNSUPPORTED : CLIPDB_ERR_INVALID, control.err);
     }
-    sq->busy_timeout(db, 30000);
-    void *st_kind = nullptr, *st_count = nullptr, *st_rows = nullptr;
-    int rc = CLIPDB_OK;
-    int64_t vec0_rows = 0, joined = 0;
-    std::vector<int64_t> ids(chunk_rows), image_ids(chunk_rows);
-    std::vector<double> mtimes(chunk_rows);
-    std::string paths;
-    bool in_txn = false;
-    do {
-        // only a plain table named vec0 is read here; the virtual table / its shadow tables go through the Python reader
-        if (sq->prepare_v2(db, "SELECT type, sql FROM sqlite_master WHERE name = 'vec0'", -1, &st_kind, nullptr) != SQLITE_OK_) {
-            rc = report(CLIPDB_ERR_INVALID, "cannot read the schema", db);
-            break;
-        }
+    {
+        void *st = nullptr;
         bool plain = false;
-        if (sq->step(st_kind) == SQLITE_ROW_) {
-            const char *type = reinterpret_cast<const char *>(sq->column_text(st_kind, 0));
-            const char *sql = reinterpret_cast<const char *>(sq->column_text(st_kind, 1));
+        if (sq->prepare_v2(control.db, "SELECT type, sql FROM sqlite_master WHERE name = 'vec0'", -1, &st, nullptr) == SQLITE_OK_ &&
+            sq->step(st) == SQLITE_ROW_) {
+            const char *type = reinterpret_cast<const char *>(sq->column_text(st, 0));
+            const char *sql = reinterpret_cast<const char *>(sq->column_text(st, 1));
             plain = type && !strcmp(type, "table") && !(sql && (strstr(sql, "VIRTUAL") || strstr(sql, "virtual")));
         }
-        if (!plain) {
-            rc = report(CLIPDB_ERR_UNSUPPORTED, "vec0 is not a plain table (use the Python reader)", nullptr);
-            break;
-        }
-        if (sq->exec(db, "BEGIN", nullptr, nullptr, nullptr) != SQLITE_OK_) {
-            rc = report(CLIPDB_ERR_INVALID, "BEGIN failed", db);
-            break;
-        }
-        in_txn = true;
-        if (sq->prepare_v2(db, "SELECT COUNT(*) FROM vec0 WHERE rowid > ?1 AND rowid <= ?2", -1, &st_count, nullptr) != SQLITE_OK_ ||
-            sq->prepare_v2(db, SQL_LOAD_ROWS, -1, &st_rows, nullptr) != SQLITE_OK_) {
-            rc = report(CLIPDB_ERR_INVALID, "cannot prepare the statements", db);
-            break;
-        }
-        sq->bind_int64(st_count, 1, min_rowid);
-        sq->bind_int64(st_count, 2, max_rowid);
-        if (sq->step(st_count) == SQLITE_ROW_) vec0_rows = sq->column_int64(st_count, 0);
-        sq->bind_int64(st_rows, 1, min_rowid);
-        sq->bind_int64(st_rows, 2, max_rowid);
+        if (st) sq->finalize(st);
+        // only a plain table named vec0 is read here; the virtual table / its shadow tables go through the binding's reader
+        if (!plain) return report(CLIPDB_ERR_UNSUPPORTED, "vec0 is not a plain table (use the Python reader)");
+    }
+    int64_t vec0_rows = 0, first = 0, last = 0;
+    bool null_a = false, null_b = false, null_c = false;
+    if (!sql_scalar_i64(sq, control.db, "SELECT COUNT(*) FROM vec0 WHERE rowid > ?1 AND rowid <= ?2", min_rowid, max_rowid,
+                        &vec0_rows, &null_a) ||
+        !sql_scalar_i64(sq, control.db, "SELECT MIN(rowid) FROM vec0 WHERE rowid > ?1 AND rowid <= ?2", min_rowid, max_rowid,
+                        &first, &null_b) ||
+        !sql_scalar_i64(sq, control.db, "SELECT MAX(rowid) FROM vec0 WHERE rowid > ?1 AND rowid <= ?2", min_rowid, max_rowid,
+                        &last, &null_c))
+        return report(CLIPDB_ERR_INVALID, std::string("cannot count vec0: ") + sq->errmsg(control.db));
+    if (out_vec0_rows) *out_vec0_rows = vec0_rows;
+    if (vec0_rows == 0) return CLIPDB_OK;
 
+    // ---- stripes of `chunk_rows` consecutive rowid VALUES: a stripe holds at most chunk_rows rows, so it fits one
+    // staging slot whatever the joins drop, and stripes committed in order are rows appended in rowid order.  Several
+    // readers (own connection, own statement) fill stripes ahead of the committer.  A sparse rowid space (many more
+    // stripes than rows warrant) is read by one reader as a single stripe sequence instead.
+    const uint64_t span = static_cast<uint64_t>(last) - static_cast<uint64_t>(first) + 1;
+    uint64_t n_stripes = (span + static_cast<uint64_t>(chunk_rows) - 1) / static_cast<uint64_t>(chunk_rows);
+    const uint64_t dense = static_cast<uint64_t>(vec0_rows) / static_cast<uint64_t>(chunk_rows) + 1;
+    const bool striped = n_stripes <= 4 * dense;
+    if (!striped) readers = 1;
+    if (static_cast<uint64_t>(readers) > n_stripes) readers = static_cast<int>(n_stripes);
+    const int n_slots = striped ? 2 * readers : 2;
+
+    const size_t slot_bytes = static_cast<size_t>(chunk_rows) * dim * sizeof(float);
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        DeviceGuard g(c->device);
+        if (c->sql_slot_bytes < slot_bytes || static_cast<int>(c->sql_slots.size()) < n_slots) {
+            CU_TRY(c, cudaStreamSynchronize(c->stream));
+            for (void *p : c->sql_slots) cudaFreeHost(p);
+            c->sql_slots.clear();
+            c->sql_slot_bytes = 0;
+            for (int i = 0; i < n_slots; i++) {
+                void *p = nullptr;
+                CU_TRY(c, cudaMallocHost(&p, slot_bytes));
+                c->sql_slots.push_back(p);
+            }
+            c->sql_slot_bytes = slot_bytes;
+        }
+    }
+    std::vector<SqlSlot> slots(n_slots);
+    for (SqlSlot &sl : slots) {
+        sl.ids.resize(chunk_rows);
+        sl.image_ids.resize(chunk_rows);
+        sl.mtimes.resize(chunk_rows);
+    }
+    int64_t joined = 0;
+    // commit one filled slot: append (DMA from pinned memory), wait for the copy, hand the metadata to the host
+    auto commit = [&](int slot_index) -> int {
+        SqlSlot &sl = slots[slot_index];
+        if (sl.m == 0) return CLIPDB_OK;
+        {
+            std::lock_guard<std::mutex> lk(c->mu);
+            DeviceGuard g(c->device);
+            RC_TRY(append_rows_locked(c, static_cast<const float *>(c->sql_slots[slot_index]), sl.ids.data(), sl.m));
+            CU_TRY(c, cudaStreamSynchronize(c->stream));
+        }
+        if (on_chunk && on_chunk(user, sl.m, sl.ids.data(), sl.image_ids.data(), sl.mtimes.data(), sl.paths.data(),
+                                 static_cast<int64_t>(sl.paths.size())) != 0)
+            return report(CLIPDB_ERR_INVALID, "the chunk callback asked to stop");
+        joined += sl.m;
+        return CLIPDB_OK;
+    };
+
+    int rc = CLIPDB_OK;
+    if (!striped) {
+        // one reader, one pass: chunks of chunk_rows ROWS cut from a single ordered statement, two slots alternating
+        const SqliteApi *api = sq;
+        api->reset(control.st_rows);
+        api->bind_int64(control.st_rows, 1, min_rowid);
+        api->bind_int64(control.st_rows, 2, max_rowid);
         const size_t row_bytes = static_cast<size_t>(dim) * sizeof(float);
-        int buf = 0;
-        int64_t fill = 0;
-        bool used[2] = {false, false};
-        auto flush = [&]() -> int {
-            if (fill == 0) return CLIPDB_OK;
-            {
-                std::lock_guard<std::mutex> lk(c->mu);
-                DeviceGuard g(c->device);
-                RC_TRY(append_rows_locked(c, static_cast<const float *>(c->sql_stage[buf].p), ids.data(), fill));
-                CU_TRY(c, cudaEventRecord(c->sql_done[buf], c->stream));
-                used[buf] = true;
-            }
-            if (on_chunk && on_chunk(user, fill, ids.data(), image_ids.data(), mtimes.data(), paths.data(),
-                                     static_cast<int64_t>(paths.size())) != 0)
-                return report(CLIPDB_ERR_INVALID, "the chunk callback asked to stop", nullptr);
-            joined += fill;
-            fill = 0;
-            paths.clear();
-            buf ^= 1;
-            if (used[buf]) {   // the copy that last read this buffer must be done before it is refilled
-                DeviceGuard g(c->device);
-                if (cudaEventSynchronize(c->sql_done[buf]) != cudaSuccess)
-                    return report(CLIPDB_ERR_CUDA, "waiting for the staging copy failed", nullptr);
-            }
-            return CLIPDB_OK;
-        };
-        int step_rc;
-        while ((step_rc = sq->step(st_rows)) == SQLITE_ROW_) {
-            const int nbytes = sq->column_bytes(st_rows, 4);
-            const void *blob = sq->column_blob(st_rows, 4);
+        int buf = 0, step_rc;
+        slots[0].m = slots[1].m = 0;
+        while (rc == CLIPDB_OK && (step_rc = api->step(control.st_rows)) == SQLITE_ROW_) {
+            SqlSlot &sl = slots[buf];
+            const int nbytes = api->column_bytes(control.st_rows, 4);
+            const void *blob = api->column_blob(control.st_rows, 4);
             if (static_cast<size_t>(nbytes) != row_bytes || !blob) {
-                std::lock_guard<std::mutex> lk(c->mu);
-                rc = fail(c, CLIPDB_ERR_INVALID, "append_sqlite: vec0 rowid %lld: %d bytes, expected float32[%d]",
-                          sq->column_int64(st_rows, 0), nbytes, dim);
+                char msg[160];
+                snprintf(msg, sizeof msg, "vec0 rowid %lld: %d bytes, expected float32[%d]",
+                         api->column_int64(control.st_rows, 0), nbytes, dim);
+                rc = report(CLIPDB_ERR_INVALID, msg);
                 break;
             }
-            memcpy(static_cast<uint8_t *>(c->sql_stage[buf].p) + static_cast<size_t>(fill) * row_bytes, blob, row_bytes);
-            ids[fill] = sq->column_int64(st_rows, 0);
-            image_ids[fill] = sq->column_int64(st_rows, 1);
-            mtimes[fill] = sq->column_double(st_rows, 2);
-            const unsigned char *path = sq->column_text(st_rows, 3);
-            if (path) paths.append(reinterpret_cast<const char *>(path));
-            paths.push_back('\0');
-            if (++fill == chunk_rows && (rc = flush()) != CLIPDB_OK) break;
+            memcpy(static_cast<uint8_t *>(c->sql_slots[buf]) + static_cast<size_t>(sl.m) * row_bytes, blob, row_bytes);
+            sl.ids[sl.m] = api->column_int64(control.st_rows, 0);
+            sl.image_ids[sl.m] = api->column_int64(control.st_rows, 1);
+            sl.mtimes[sl.m] = api->column_double(control.st_rows, 2);
+            const unsigned char *path = api->column_text(control.st_rows, 3);
+            if (path) sl.paths.append(reinterpret_cast<const char *>(path));
+            sl.paths.push_back('\0');
+            if (++sl.m == chunk_rows) {
+                rc = commit(buf);
+                sl.m = 0;
+                sl.paths.clear();
+            }
         }
-        if (rc != CLIPDB_OK) break;
-        if (step_rc != SQLITE_DONE_) {
-            rc = report(CLIPDB_ERR_INVALID, "reading vec0 failed", db);
-            break;
+        if (rc == CLIPDB_OK && step_rc != SQLITE_DONE_)
+            rc = report(CLIPDB_ERR_INVALID, std::string("reading vec0 failed: ") + api->errmsg(control.db));
+        if (rc == CLIPDB_OK) rc = commit(buf);
+    } else {
+        std::mutex mx;
+        std::condition_variable cv;
+        std::vector<uint8_t> filled(n_stripes, 0);
+        uint64_t committed = 0, next = 0;
+        bool stop = false;
+        std::string worker_err;
+        auto worker = [&](SqlReader *rd) {
+            for (;;) {
+                uint64_t s;
+                {
+                    std::unique_lock<std::mutex> lk(mx);
+                    s = next++;
+                    if (s >= n_stripes) return;
+                    // the slot of stripe s was last used by stripe s - n_slots: wait until that one is committed
+                    cv.wait(lk, [&] { return stop || s < committed + static_cast<uint64_t>(n_slots); });
+                    if (stop) return;
+                }
+                const int slot_index = static_cast<int>(s % static_cast<uint64_t>(n_slots));
+                // rowids in (lo, hi] with lo = first - 1 + s * chunk_rows, clipped to the caller's range
+                const uint64_t off = s * static_cast<uint64_t>(chunk_rows);
+                const int64_t lo = static_cast<int64_t>(static_cast<uint64_t>(first) + off) - 1;
+                int64_t hi = (span - off <= static_cast<uint64_t>(chunk_rows)) ? last
+                                                                               : static_cast<int64_t>(static_cast<uint64_t>(lo) + static_cast<uint64_t>(chunk_rows));
+                const bool ok = rd->read_range(lo < min_rowid ? min_rowid : lo, hi, dim, chunk_rows,
+                                               static_cast<uint8_t *>(c->sql_slots[slot_index]), slots[slot_index]);
+                std::lock_guard<std::mutex> lk(mx);
+                if (!ok) {
+                    if (worker_err.empty()) worker_err = rd->err;
+                    stop = true;
+                } else {
+                    filled[s] = 1;
+                }
+                cv.notify_all();
+                if (!ok) return;
+            }
+        };
+        // the control connection is reader 0; the others open their own (a connection is used by one thread only)
+        std::vector<std::unique_ptr<SqlReader>> extra;
+        std::vector<std::thread> threads;
+        bool opened = true;
+        for (int r = 1; r < readers; r++) {
+            extra.emplace_back(new SqlReader());
+            if (!extra.back()->open(sq, db_path)) {
+                worker_err = extra.back()->err;
+                opened = false;
+                break;
+            }
         }
-        rc = flush();
-    } while (false);
-    if (st_kind) sq->finalize(st_kind);
-    if (st_count) sq->finalize(st_count);
-    if (st_rows) sq->finalize(st_rows);
-    if (in_txn) sq->exec(db, "ROLLBACK", nullptr, nullptr, nullptr);
-    sq->close_v2(db);
+        if (!opened) {
+            rc = report(CLIPDB_ERR_INVALID, worker_err);
+        } else {
+            threads.emplace_back(worker, &control);
+            for (auto &rd : extra) threads.emplace_back(worker, rd.get());
+            for (uint64_t s = 0; s < n_stripes && rc == CLIPDB_OK; s++) {
+                {
+                    std::unique_lock<std::mutex> lk(mx);
+                    cv.wait(lk, [&] { return stop || filled[s]; });
+                    if (!filled[s]) break;     // a reader failed
+                }
+                rc = commit(static_cast<int>(s % static_cast<uint64_t>(n_slots)));
+                std::lock_guard<std::mutex> lk(mx);
+                committed = s + 1;
+                if (rc != CLIPDB_OK) stop = true;
+                cv.notify_all();
+            }
+            {
+                std::lock_guard<std::mutex> lk(mx);
+                if (rc != CLIPDB_OK) stop = true;
+                cv.notify_all();
+            }
+            for (std::thread &t : threads) t.join();
+            if (rc == CLIPDB_OK && !worker_err.empty()) rc = report(CLIPDB_ERR_INVALID, worker_err);
+        }
+    }
     {
         std::lock_guard<std::mutex> lk(c->mu);
         DeviceGuard g(c->device);
         cudaStreamSynchronize(c->stream);
     }
-    if (out_vec0_rows) *out_vec0_rows = vec0_rows;
     if (out_joined_rows) *out_joined_rows = joined;
     return rc;
 }

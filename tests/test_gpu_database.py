@@ -341,3 +341,39 @@ def test_tiered_shards_on_several_gpus(tmp_path):
                            reference_answer(db_path, rows[9], k, folders))
         many = db.search_embeddings(rows[100:140], k=5)
         assert [r[0][0] for r in many] == [synth.default_paths(n)[i] for i in range(100, 140)]
+
+
+@pytest.mark.parametrize("readers", [1, 4])
+def test_native_reader_on_a_sparse_rowid_space_and_with_many_readers(tmp_path, readers):
+    """Stripes are ranges of rowid VALUES; a table whose rowids are mostly gaps is read as one ordered pass instead,
+    and the answer does not depend on how many connections read the stripes."""
+    assert have_gpu()
+    import sqlite3 as sq3
+    from clip_database_b200 import GpuIndex, loader
+    n = 5000
+    rows = synth.unit_rows(n, DIM, 95)
+    dense = str(tmp_path / "dense.db")
+    synth.write_reference_db(dense, rows, rowid_start=1000, drop_mapping_for=[0, 127, 128, 4999])
+    sparse = str(tmp_path / "sparse.db")
+    synth.write_reference_db(sparse, rows, rowid_start=1000)
+    w = sq3.connect(sparse)
+    w.execute("DELETE FROM vec0 WHERE (rowid - 1000) % 10 != 0")           # 500 rows over a span of 5000 rowids
+    w.commit()
+    w.close()
+    for path in (dense, sparse):
+        want = loader.read_store(path)
+        with GpuIndex(0) as idx:
+            idx.set_option("sqlite_readers", readers)
+            idx.reserve(len(want.rowids) + 10, DIM, explicit_rowids=True)
+            got_ids, got_paths, chunks = [], [], []
+            vec0_rows, joined = idx.append_sqlite(path, on_chunk=lambda i, im, mt, p: (got_ids.append(i), got_paths.extend(p),
+                                                                                      chunks.append(len(i))),
+                                                  chunk_rows=128)
+            assert joined == len(want.rowids) == idx.num_rows and vec0_rows == want.vec0_count
+            assert np.array_equal(np.concatenate(got_ids), want.rowids) and got_paths == want.file_paths
+            assert max(chunks) <= 128
+            with GpuIndex(0) as ref_idx:
+                ref_idx.load(want.rows, want.rowids)
+                q = synth.unit_rows(4, DIM, 96)
+                a, b = idx.search(q, 10), ref_idx.search(q, 10)
+                assert np.array_equal(a.rowids, b.rowids) and np.array_equal(a.distances.view(np.uint32), b.distances.view(np.uint32))
