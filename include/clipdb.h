@@ -127,9 +127,11 @@ int clipdb_stage_buffer(clipdb_ctx *ctx, int64_t bytes, void **out_host);
 /* Native loader: append to the (reserved) store the rows the reference's search statement scans — `vec0` in rowid
  * order, INNER JOINed to `image_embeddings` (vec0.rowid = ie.rowid) and `images` (ie.image_id = i.id), idb:1564-1571
  * — for vec0 rowids in (min_rowid, max_rowid], read from the SQLite file with SQLite's own C library (libsqlite3.so.0,
- * resolved with dlopen) inside one read transaction.  Every float32 blob is copied once, from SQLite's page buffer
- * into a pinned double buffer, and leaves for the GPU by DMA while the next chunk is being read; vec0 rows without
- * both partners are dropped, as the INNER JOINs drop them (idb:1569-1570).  After every chunk of up to `chunk_rows`
+ * resolved with dlopen).  The rowid range is cut into stripes of `chunk_rows` consecutive rowid values; up to
+ * option "sqlite_readers" (default 4) connections, each inside its own read transaction, fill stripes ahead of one
+ * committer that appends them in rowid order.  Every float32 blob is copied once, from SQLite's page buffer into a
+ * pinned staging slot, and leaves for the GPU by DMA; vec0 rows without both partners are dropped, as the INNER
+ * JOINs drop them (idb:1569-1570).  A sparse rowid space (mostly gaps) is read in one ordered pass instead.  After every chunk of up to `chunk_rows`
  * rows `on_chunk` (nullable) receives what the host keeps per row: the rowids, image ids, `images.last_modified`
  * and the file paths (`n` NUL-terminated UTF-8 strings back to back, `paths_bytes` in total); a non-zero return
  * stops the load.  Only a plain table named vec0 is read here (CLIPDB_ERR_UNSUPPORTED otherwise, and when
