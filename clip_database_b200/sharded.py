@@ -183,7 +183,31 @@ class CudaShardBackend:
                 t.zeros(nq, dtype=t.int32, device=self.device))
 
     def queries_to_device(self, queries: np.ndarray):
-        return self.torch.from_numpy(np.ascontiguousarray(queries, dtype=np.float32)).to(self.device)
+        """Host queries -> device through a pinned staging buffer (one async H2D, no host-side sync)."""
+        t = self.torch
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        key = q.shape
+        if getattr(self, "_hq_key", None) != key:
+            self._hq = t.empty(key, dtype=t.float32).pin_memory()
+            self._dq = t.empty(key, dtype=t.float32, device=self.device)
+            self._hq_key = key
+        self._hq.numpy()[:] = q
+        self._dq.copy_(self._hq, non_blocking=True)
+        return self._dq
+
+    def fetch_batch(self, out_dist, out_rowids, out_n, flags):
+        """(rowids, dist, counts, flags) of a batched search as numpy copies: four async D2H copies into pinned
+        memory and ONE stream synchronisation."""
+        t = self.torch
+        src = (out_rowids, out_dist, out_n, flags.contiguous())
+        key = tuple((x.shape, x.dtype) for x in src)
+        if getattr(self, "_hb_key", None) != key:
+            self._hb = [t.empty(x.shape, dtype=x.dtype).pin_memory() for x in src]
+            self._hb_key = key
+        for h, d in zip(self._hb, src):
+            h.copy_(d, non_blocking=True)
+        t.cuda.current_stream(self.device).synchronize()
+        return tuple(h.numpy().copy() for h in self._hb)
 
     def new_outputs(self, k: int):
         """(dist[k], rowids[k], n[1]) as views into ONE packed device record, so the host
@@ -347,10 +371,12 @@ class ShardedIndex:
         nq = queries.shape[0]
         d_q = self.backend.queries_to_device(queries)
         out_dist, out_rowids, out_n, flags = self.search_batch_device(d_q, k)
-        flagged = np.flatnonzero(flags.contiguous().cpu().numpy().view(np.int32).reshape(-1, nq).any(axis=0))
-        ids = out_rowids.cpu().numpy().copy()
-        dist = out_dist.cpu().numpy().copy()
-        counts = out_n.cpu().numpy().copy()
+        if hasattr(self.backend, "fetch_batch"):
+            ids, dist, counts, h_flags = self.backend.fetch_batch(out_dist, out_rowids, out_n, flags)
+        else:
+            ids, dist, counts = (x.cpu().numpy().copy() for x in (out_rowids, out_dist, out_n))
+            h_flags = flags.contiguous().cpu().numpy()
+        flagged = np.flatnonzero(h_flags.view(np.int32).reshape(-1, nq).any(axis=0))
         if (counts < 0).any():
             raise RuntimeError("sharded batch search: a peer GPU did not deliver in time, or the ranks asked "
                                "different questions (every rank must issue the same searches)")
