@@ -25,6 +25,18 @@ from .index import GpuIndex
 Result = List[Tuple[str, float]]
 
 
+def _serialised(method):
+    """One search / refresh / reload at a time per ``ImageDatabase``: a refresh from one thread (``dropin`` runs it
+    before every search) must not move the host-side row metadata under a search in another."""
+    import functools
+
+    @functools.wraps(method)
+    def locked(self, *args, **kwargs):
+        with self._lock:
+            return method(self, *args, **kwargs)
+    return locked
+
+
 class Embedder:
     """Interface for the out-of-scope model: text / image path -> float32[dim] (or None)."""
 
@@ -144,6 +156,8 @@ class ImageDatabase:
         if binary_score_mode not in ("reference", "popcount"):
             raise ValueError("binary_score_mode must be 'reference' (uint8 wrap-around, as the reference "
                              "computes it) or 'popcount'")
+        import threading
+        self._lock = threading.RLock()
         self.binary_score_mode = binary_score_mode
         self.batch_store = bool(batch_store)
         self.hbm_budget_bytes = hbm_budget_bytes
@@ -258,6 +272,7 @@ class ImageDatabase:
             + ("" if need16 else "; batch_store=True keeps only a bf16 copy resident (half the bytes) and tiers the "
                                  "float32 rows into host memory") + "; or shard over more GPUs with devices=[...]")
 
+    @_serialised
     def reload(self) -> None:
         """(Re)read the whole database into HBM, streamed: every chunk of rows goes from SQLite through a pinned
         staging buffer straight into the resident store.  With several GPUs the shard boundaries are computed
@@ -337,6 +352,7 @@ class ImageDatabase:
             self._watch = loader.connect(self.db_path)
         return self._watch
 
+    @_serialised
     def refresh(self, force: bool = False) -> int:
         """Bring the resident store in line with what a fresh connection would see now — what the reference does
         implicitly by reopening SQLite for every search (image_database.py:1475).  Free when nothing was
@@ -485,6 +501,7 @@ class ImageDatabase:
                                      negative_weights=neg_ws, filter_folders=filter_folders,
                                      profile=profile, show_duplicates=show_duplicates)
 
+    @_serialised
     def search_embeddings(self, embeddings, k: int = 10, filter_folders: Optional[Sequence[str]] = None
                           ) -> List[Result]:
         """Many ready-made query embeddings (e.g. one per interactive session) in one call: with
@@ -535,6 +552,7 @@ class ImageDatabase:
             self._mask_key = key
         return True
 
+    @_serialised
     def search_embedding(self, embedding1, k: int = 10, embedding2=None,
                          weights: Tuple[float, float] = (0.5, 0.5),
                          negative_embeddings: Sequence = (), negative_weights: Sequence[float] = (),
