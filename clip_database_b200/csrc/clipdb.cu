@@ -1576,7 +1576,8 @@ int clipdb_append_sqlite(clipdb_ctx *c, const char *db_path, int64_t min_rowid, 
     const uint64_t dense = static_cast<uint64_t>(vec0_rows) / static_cast<uint64_t>(chunk_rows) + 1;
     const bool striped = n_stripes <= 4 * dense;
     if (!striped) readers = 1;
-    if (static_cast<uint64_t>(readers) > n_stripes) readers = static_cast<int>(n_stripes);
+    // a small load does not repay the extra connections and pinned slots (38 MB each): one more reader per 8 stripes
+    if (static_cast<uint64_t>(readers) > 1 + n_stripes / 8) readers = static_cast<int>(1 + n_stripes / 8);
     const int n_slots = striped ? 2 * readers : 2;
 
     const size_t slot_bytes = static_cast<size_t>(chunk_rows) * dim * sizeof(float);
