@@ -37,3 +37,31 @@ def embedding_call(kwargs, vectors):
         nw = kwargs.get("negative_weights")
         ws.append(nw[i] if nw and i < len(nw) else kwargs.get("negative_weight", 0.5))
     return e1, e2, weights, negs, ws
+
+
+def rescan_golden():
+    import json
+    with open(os.path.join(_HERE, "golden", "reference_rescan.json")) as f:
+        return json.load(f)
+
+
+def apply_rescan_stage(conn, stage, dim=1152):
+    """Replay, with plain SQL, exactly the row-level writes the reference's own ``_commit_batch`` made in this stage
+    (recorded by tests/golden/make_golden_rescan.py): deleted / upserted rows of images, image_embeddings, vec0."""
+    from clip_database_b200 import synth
+    cur = conn.cursor()
+    for image_id in stage["images"]["deleted"]:
+        cur.execute("DELETE FROM images WHERE id = ?", (image_id,))
+    for image_id, file_path, mtime, file_hash in stage["images"]["upserted"]:
+        cur.execute("INSERT OR REPLACE INTO images (id, file_path, last_modified, file_hash) VALUES (?, ?, ?, ?)",
+                    (image_id, file_path, mtime, file_hash))
+    for rowid in stage["vec0"]["deleted"]:
+        cur.execute("DELETE FROM vec0 WHERE rowid = ?", (rowid,))
+    for rowid, seed in stage["vec0"]["upserted"]:
+        cur.execute("INSERT OR REPLACE INTO vec0 (rowid, embedding) VALUES (?, ?)",
+                    (rowid, synth.unit_rows(1, dim, seed)[0].tobytes()))
+    for rowid in stage["image_embeddings"]["deleted"]:
+        cur.execute("DELETE FROM image_embeddings WHERE rowid = ?", (rowid,))
+    for rowid, image_id in stage["image_embeddings"]["upserted"]:
+        cur.execute("INSERT OR REPLACE INTO image_embeddings (rowid, image_id) VALUES (?, ?)", (rowid, image_id))
+    conn.commit()
