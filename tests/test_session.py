@@ -93,3 +93,38 @@ def test_load_vector_and_embedder_hook(tmp_path):
         load_embedder("fake_embedder:NotAnEmbedder")
     with pytest.raises(ValueError):
         load_embedder("no_colon")
+
+
+def test_grammar_matches_the_references_own_loop(tmp_path):
+    """tests/golden/reference_session.json: the reference's interactive loop (image_database.py:2070-2299) was fed this
+    script with ``search()`` replaced by a recorder (tests/golden/make_golden_session.py).  ``parse_line`` must turn
+    every line into the same call — or the same message — with the same state carried from line to line."""
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    golden = json.load(open(os.path.join(here, "golden", "reference_session.json")))
+    d1, d2 = tmp_path / "photos", tmp_path / "scans"
+    d1.mkdir()
+    d2.mkdir()
+
+    def real(s):
+        return s.replace("{DIR2}", str(d2)).replace("{DIR}", str(d1)) if isinstance(s, str) else s
+    st = SessionState()
+    searches = 0
+    for rec in golden["records"]:
+        item = parse_line(real(rec["line"]), st)
+        want = rec["search"]
+        if want is None:
+            assert isinstance(item, Command), rec["line"]
+            assert item.message == real(rec["first_message"]), rec["line"]
+            if item.kind == "quit":
+                break
+            continue
+        searches += 1
+        assert isinstance(item, SearchRequest), rec["line"]
+        got = dict(query=item.query, **item.kwargs(st))
+        got["weights"] = list(got["weights"])
+        want = dict(want)
+        want["filter_folders"] = [real(f) for f in want["filter_folders"]] if want["filter_folders"] else None
+        assert got == want, rec["line"]
+    assert searches == 23 and item.kind == "quit"
