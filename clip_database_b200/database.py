@@ -433,6 +433,12 @@ class ImageDatabase:
             self._vec0_count = loader.count_vec0(conn)
         return touched
 
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
     def close(self) -> None:
         if self._watch is not None:
             self._watch.close()
