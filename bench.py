@@ -1473,7 +1473,33 @@ def measure_sharded_batch(args, torch, dist, idx, fused_side, nccl_side, rows_pe
             times[name].append(max_over_ranks(ev0.elapsed_time(ev1)) / steps)
     best = {name: float(np.mean(v)) for name, v in times.items()}
     winner = min(best, key=best.get)
-    return {"workload": "B=%d, k=%d batched queries against the %d-row sharded store (configs[2] queries on the configs[4] "
+    # ONE query through the same pre-selection over the sharded store (what a bf16 copy buys a single search: half
+    # the bytes of the float32 scan), checked against the exact sharded scan
+    side = fused_side if fused_side.fused else nccl_side
+    k1 = args.k
+    one_q = d_q[1][:1]
+    for _ in range(warm):
+        side.search_batch_device(one_q, k1)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        side.search_batch_device(one_q, k1)
+    ev1.record()
+    barrier()
+    one_ms = max_over_ranks(ev0.elapsed_time(ev1)) / steps
+    b_ids, b_d, b_n = side.search_batch(host_q[1][:1], k1)
+    e_ids, e_d = side.search(host_q[1][0], k1)
+    same_one = bool(np.array_equal(b_ids[0, :b_n[0]], e_ids) and
+                    np.array_equal(b_d[0, :b_n[0]].view(np.uint32), e_d.view(np.uint32)))
+    votes = [None] * world
+    dist.all_gather_object(votes, same_one)
+    if not all(votes):
+        return {"error": "one query through the pre-selection differs from the exact sharded scan"}
+    single = {"ms_per_query": one_ms, "queries_per_s": 1e3 / one_ms, "k": k1,
+              "scanned_GBps_bf16": rows_per_gpu * world * BF16_ROW_BYTES / 1e9 / (one_ms / 1e3),
+              "bit_identical_to_exact_scan": True}
+    return {"single_query_through_bf16_preselect": single, "workload": "B=%d, k=%d batched queries against the %d-row sharded store (configs[2] queries on the configs[4] "
                         "store)" % (B, kb, rows_per_gpu * world),
             "ms_per_step": {name: v for name, v in best.items()}, "ms_per_step_runs": times,
             "queries_per_s": {name: B * 1e3 / v for name, v in best.items()},
