@@ -1458,21 +1458,6 @@ def measure_sharded_batch(args, torch, dist, idx, fused_side, nccl_side, rows_pe
     if not all(votes):
         return {"error": "fused and NCCL batched exchange disagree", "ranks": [r for r, v in enumerate(votes) if not v]}
     steps, warm, reps = max(5, min(args.steps, 10)), 3, 2
-    times = {name: [] for name in sides}
-    for _ in range(reps):
-        for name, sh in sides.items():
-            for i in range(warm):
-                sh.search_batch_device(d_q[i % 4], kb)
-            barrier()
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record()
-            for i in range(steps):
-                sh.search_batch_device(d_q[i % 4], kb)
-            ev1.record()
-            barrier()
-            times[name].append(max_over_ranks(ev0.elapsed_time(ev1)) / steps)
-    best = {name: float(np.mean(v)) for name, v in times.items()}
-    winner = min(best, key=best.get)
     # ONE query through the same pre-selection over the sharded store (what a bf16 copy buys a single search: half
     # the bytes of the float32 scan), checked against the exact sharded scan
     side = fused_side if fused_side.fused else nccl_side
@@ -1499,6 +1484,21 @@ def measure_sharded_batch(args, torch, dist, idx, fused_side, nccl_side, rows_pe
     single = {"ms_per_query": one_ms, "queries_per_s": 1e3 / one_ms, "k": k1,
               "scanned_GBps_bf16": rows_per_gpu * world * BF16_ROW_BYTES / 1e9 / (one_ms / 1e3),
               "bit_identical_to_exact_scan": True}
+    times = {name: [] for name in sides}
+    for _ in range(reps):
+        for name, sh in sides.items():
+            for i in range(warm):
+                sh.search_batch_device(d_q[i % 4], kb)
+            barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for i in range(steps):
+                sh.search_batch_device(d_q[i % 4], kb)
+            ev1.record()
+            barrier()
+            times[name].append(max_over_ranks(ev0.elapsed_time(ev1)) / steps)
+    best = {name: float(np.mean(v)) for name, v in times.items()}
+    winner = min(best, key=best.get)
     return {"single_query_through_bf16_preselect": single, "workload": "B=%d, k=%d batched queries against the %d-row sharded store (configs[2] queries on the configs[4] "
                         "store)" % (B, kb, rows_per_gpu * world),
             "ms_per_step": {name: v for name, v in best.items()}, "ms_per_step_runs": times,
