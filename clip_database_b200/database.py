@@ -523,7 +523,8 @@ class ImageDatabase:
             k = self.index.num_rows
         use_mask = self._install_mask(filter_folders)
         multi = hasattr(self.index, "shards")
-        if multi and getattr(self.index, "batch_enabled", False) and not use_mask and 1 <= k <= 128:
+        if multi and getattr(self.index, "batch_enabled", False) and not use_mask and \
+                1 <= k <= min(128, min(hi - lo for lo, hi in self.index.bounds)):
             res = self.index.search_batch(q, k)          # one batched pass per 256 queries on every GPU
             multi = False
         else:
